@@ -1,0 +1,130 @@
+/* tclip_b200.h — C ABI of libtclip_b200.so: the B200 (sm_100a) implementation of transductive-CLIP's batched EM
+ * inference loop (EM-Dirichlet / Hard EM-Dirichlet first; k-means family next).
+ *
+ * The reference (SegoleneMartin/transductive-CLIP) is pure Python/PyTorch and has no FFI; the entry points below are
+ * what a binding for its `src/methods` hot path would call, one per stage of `run_method`, plus one fused driver.
+ * Each declaration cites the reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, sizes, and a `void* stream` that is a `cudaStream_t` (NULL = default stream);
+ *   - every function returns 0 (TCLIP_OK) or a negative TCLIP_ERR_* code; `tclip_last_error()` has the message;
+ *   - nothing allocates user-visible memory: scratch comes from a caller-provided workspace whose size is returned
+ *     by the matching `*_workspace_bytes` query; nothing synchronises the stream or the device;
+ *   - all tensors are dense row-major float32 unless stated: T tasks, n queries, K classes, D feature dim, S support
+ *     samples;  u [T,n,K], x/logz [T,n,D], alpha/y [T,K,D], v/colsum [T,K];  D <= 1024 for the M-step;
+ *   - there is no CPU path: calling into a device that is not compute capability 10.x fails with TCLIP_ERR_DEVICE.
+ */
+#ifndef TCLIP_B200_H_
+#define TCLIP_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCLIP_OK 0
+#define TCLIP_ERR_INVALID (-1)   /* bad argument (null pointer, size out of range, D > 1024, ...) */
+#define TCLIP_ERR_CUDA (-2)      /* a CUDA runtime call or kernel launch failed */
+#define TCLIP_ERR_DEVICE (-3)    /* current device is not an sm_100 part */
+#define TCLIP_ERR_WORKSPACE (-4) /* workspace missing or too small */
+
+#define TCLIP_MM_DENSE 0      /* iterate every (task, class) row in every M-step, like the reference */
+#define TCLIP_MM_SKIP_DEAD 1  /* iterate empty-cluster rows once, replay their cached criterion terms afterwards */
+
+/* ---- library / device --------------------------------------------------------------------------------------- */
+int tclip_version(void);                 /* 100 * major + minor */
+const char* tclip_last_error(void);      /* message of the last failing call on this thread ("" if none) */
+int tclip_device_check(int device);      /* TCLIP_OK iff `device` is compute capability 10.x (B200) */
+int tclip_mm_max_dim(void);              /* largest D the M-step kernel supports (1024) */
+
+/* ---- stage entry points ------------------------------------------------------------------------------------- */
+
+/* out = log(x + 1e-15), `count` elements.
+ * Replaces torch.log(query + self.eps): src/methods/zero_shot/em_dirichlet.py:38,219;
+ * few_shot/em_dirichlet.py:187-190. */
+int tclip_log_features(const float* x, float* out, long long count, void* stream);
+
+/* colsum[t,k] = sum_n u[t,n,k]; live[t,k] = colsum > 1e-15; v[t,k] = log(colsum/n + 1e-15) + 1.
+ * `v` and `live` may be NULL.  Replaces cluster_sizes / nonzero_clusters (zero_shot/em_dirichlet.py:217-218) and
+ * v_update (:145-151). */
+int tclip_dirichlet_colsum_v(const float* u, float* colsum, float* v, int* live, int T, int n, int K, void* stream);
+
+/* Moments y_cst.  Zero-shot (support_sum == NULL): y = sum_n u logz / max(colsum,1e-15), rows with
+ * colsum <= 1e-15 filled with -10 (zero_shot/em_dirichlet.py:219-222).  Few-shot: y = (1/(support_count + colsum))
+ * * (support_sum + sum_n u logz) (few_shot/em_dirichlet.py:196-200). */
+int tclip_dirichlet_moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
+                            const float* support_count, float* y, int T, int n, int K, int D, void* stream);
+
+/* Few-shot, iteration-invariant: support_count[t,k] = #{s: y_s[t,s] == k}, support_sum[t,k,:] = sum of
+ * log_support[t,s,:] over those s.  Replaces the [T,S,K,D] one-hot product of few_shot/em_dirichlet.py:182,199.
+ * y_s is int64 [T,S]. */
+int tclip_dirichlet_support_stats(const float* log_support, const long long* y_s, float* support_sum,
+                                  float* support_count, int T, int S, int K, int D, void* stream);
+
+/* The MM M-step on n_rows = T*K rows of length D: up to iter_mm iterations of
+ *   c = |2(lnG(1) - lnG(a+1) + psi(a+1) a)/a^2| (pi^2/6 for a <= 1e-11);  b = psi(a+1) - psi(sum_d a) - c a - y;
+ *   a <- (-b + sqrt(b^2 + 4c)) / (2c)
+ * stopping after iteration l in {check_every, 2 check_every, ...} iff ||a_new-a||^2/||a||^2 < tol over ALL rows
+ * (batch-global); the result is the last a_new.  alpha_out may alias alpha_in.  *iters_done_dev (device int) receives
+ * the number of iterations executed.  Replaces curvature + update_alpha (zero_shot/em_dirichlet.py:153-177). */
+size_t tclip_dirichlet_mm_workspace_bytes(int n_rows);
+int tclip_dirichlet_mm(const float* alpha_in, float* alpha_out, const float* y, int n_rows, int D, int iter_mm,
+                       int check_every, float tol, int* iters_done_dev, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* alpha[row] <- work[row] for live rows (live == NULL: all rows), and the logged outer criterion
+ * *criterion = mean_t ||alpha_old - alpha||_F / ||alpha_old||_F; task_criterion [T] may be NULL.
+ * `rowstat` is scratch of T*K*16 bytes.  Replaces zero_shot/em_dirichlet.py:224-226,236-238. */
+int tclip_dirichlet_commit(float* alpha, const float* work, const int* live, void* rowstat, float* task_criterion,
+                           float* criterion, int T, int K, int D, void* stream);
+
+/* E-step: u = softmax_k(lnG(sum_d a) - sum_d lnG(a) + sum_d (a-1) logz + lambd v / n); hard != 0 replaces u by the
+ * one-hot of argmax_k u.  labels [T,n] int32 (may be NULL) always receives argmax_k of the softmaxed values, lowest
+ * index on ties.  `norm` is scratch of T*K*8 bytes.  Replaces get_logits + u_update
+ * (zero_shot/em_dirichlet.py:28-40,132-143) and zero_shot/hard_em_dirichlet.py:256-258. */
+int tclip_dirichlet_estep(const float* alpha, const float* logz, const float* v, float lambd, void* norm, float* u,
+                          int* labels, int T, int n, int K, int D, int hard, void* stream);
+
+/* Inputs of the label matching: per task the clusters in order of first appearance among `labels`, their sizes, the
+ * cluster index of every query, and proto[t,c,:] = mean raw feature of cluster c (rows c >= n_clusters[t] are 0).
+ * All int outputs are int32; cluster_label/cluster_size/sample_cluster are [T,n], n_clusters [T], proto [T,n,D].
+ * Replaces compute_acc_clustering's prototypes and the cost-matrix rows of compute_graph_matching
+ * (zero_shot/em_dirichlet.py:61-70; src/utils.py:380-399). */
+int tclip_cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
+                             int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D, void* stream);
+
+/* ---- fused driver: the whole run_method loop, enqueued on one stream without host synchronisation -------------- */
+typedef struct tclip_dirichlet_problem {
+  int n_task, n_query, n_class, dim; /* T, n, K, D (D == K: softmax features) */
+  int n_support;                     /* S; 0 = zero-shot */
+  int iters;                         /* outer EM iterations (args.iter) */
+  int iter_mm;                       /* MM iterations per M-step (args.iter_mm) */
+  int check_every;                   /* 50 in the reference */
+  float tol;                         /* 1e-11 in the reference */
+  float lambd;                       /* int(K/5)*n_query (zero-shot) or int(K/k_eff)*n_query (few-shot) */
+  int hard;                          /* 1 = Hard EM-Dirichlet */
+  int mm_mode;                       /* TCLIP_MM_DENSE / TCLIP_MM_SKIP_DEAD (zero-shot only) */
+  const float* x_q;                  /* [T,n,D] query softmax features */
+  const float* x_s;                  /* [T,S,D] support features or NULL */
+  const long long* y_s;              /* [T,S] int64 support labels or NULL */
+  float* u;                          /* out [T,n,K] */
+  float* alpha;                      /* out [T,K,D] */
+  float* v;                          /* out [T,K] */
+  int* labels;                       /* out [T,n] argmax_k u */
+  float* criterions;                 /* out [iters] */
+  int* mm_iters;                     /* out [iters] MM iterations executed per outer iteration */
+  int* n_live;                       /* out [iters] non-empty clusters per outer iteration (all tasks) */
+  long long* mm_rows;                /* out [iters] rows actually iterated x iterations (work done), may be NULL */
+  void* const* iter_events;          /* optional [iters] cudaEvent_t recorded after each outer iteration */
+} tclip_dirichlet_problem;
+
+/* Runs zero_shot/em_dirichlet.py:195-244 (hard: zero_shot/hard_em_dirichlet.py:215-269) or, with n_support > 0,
+ * few_shot/em_dirichlet.py:166-218 (hard: few_shot/hard_em_dirichlet.py:187-249), up to but excluding the accuracy. */
+size_t tclip_dirichlet_em_workspace_bytes(const tclip_dirichlet_problem* p);
+int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCLIP_B200_H_ */

@@ -1,0 +1,465 @@
+// capi.cu — the C ABI of libtclip_b200.so (declared in include/tclip_b200.h) and the fused EM driver.
+//
+// The driver enqueues the whole `run_method` loop of the reference (src/methods/zero_shot/em_dirichlet.py:195-244 and
+// its hard / few-shot siblings) on one stream with no host synchronisation: the MM early exit is a device-side flag.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/tclip_b200.h"
+#include "tclip_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(TCLIP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define TCLIP_CUDA(call)                                   \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);  \
+  } while (0)
+
+// one capability probe per device and process; the kernels are built for sm_100a only
+int current_device_ok() {
+  static int verdict[64] = {};
+  int dev = 0;
+  TCLIP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(TCLIP_ERR_DEVICE, "device index %d out of range", dev);
+  if (verdict[dev] == 0) {
+    int major = 0;
+    TCLIP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    verdict[dev] = (major == 10) ? 1 : -1;
+  }
+  if (verdict[dev] < 0)
+    return fail(TCLIP_ERR_DEVICE, "device %d is not compute capability 10.x; libtclip_b200 has no other code path", dev);
+  return TCLIP_OK;
+}
+
+inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+// bump allocator over the caller's workspace
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align_up(count * sizeof(T));
+    return r;
+  }
+};
+
+constexpr int kMaxChecks = 64;  // cached criterion terms per dead row (iter_mm / check_every must stay below)
+
+struct EmWorkspace {
+  float* logz;
+  float* work;
+  float* y;
+  float* colsum;
+  int* live;
+  double* norm;
+  double2* rowstat;
+  double2* partials;
+  tclip::MMState* state;
+  tclip::MMState* state_free;  // never raised: dead-row trajectories ignore the batch-global exit
+  float* task_crit;
+  float* log_support;
+  float* support_sum;
+  float* support_count;
+  // skip-dead mode
+  int* cache_valid;
+  double2* cache;       // [rows, n_checks]
+  double2* extra;       // [n_checks] sum of the cached terms over all dead rows
+  int* list_live;
+  int* list_new;
+  int* counts;          // [0] = live rows, [1] = newly dead rows
+  size_t bytes;
+};
+
+int num_checks(int iter_mm, int check_every) {
+  if (check_every <= 0) return 0;
+  return (iter_mm - 1) / check_every;  // check points l = ce, 2ce, ... <= iter_mm - 1
+}
+
+EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
+  const size_t T = p.n_task, n = p.n_query, K = p.n_class, D = p.dim, S = p.n_support;
+  const size_t rows = T * K;
+  Carver c(ws);
+  EmWorkspace w{};
+  w.logz = c.take<float>(T * n * D);
+  w.work = c.take<float>(rows * D);
+  w.y = c.take<float>(rows * D);
+  w.colsum = c.take<float>(rows);
+  w.live = c.take<int>(rows);
+  w.norm = c.take<double>(rows);
+  w.rowstat = c.take<double2>(rows);
+  w.partials = c.take<double2>(tclip::mm_num_blocks((int)rows));
+  w.state = c.take<tclip::MMState>(1);
+  w.state_free = c.take<tclip::MMState>(1);
+  w.task_crit = c.take<float>(T);
+  if (S > 0) {
+    w.log_support = c.take<float>(T * S * D);
+    w.support_sum = c.take<float>(rows * D);
+    w.support_count = c.take<float>(rows);
+  }
+  if (p.mm_mode == TCLIP_MM_SKIP_DEAD && S == 0) {
+    const size_t nc = num_checks(p.iter_mm, p.check_every);
+    w.cache_valid = c.take<int>(rows);
+    w.cache = c.take<double2>(rows * (nc ? nc : 1));
+    w.extra = c.take<double2>(nc ? nc : 1);
+    w.list_live = c.take<int>(rows);
+    w.list_new = c.take<int>(rows);
+    w.counts = c.take<int>(4);
+  }
+  w.bytes = c.off;
+  return w;
+}
+
+int validate(const tclip_dirichlet_problem* p) {
+  if (!p) return fail(TCLIP_ERR_INVALID, "problem is NULL");
+  if (p->n_task < 1 || p->n_query < 1 || p->n_class < 1 || p->dim < 1)
+    return fail(TCLIP_ERR_INVALID, "n_task/n_query/n_class/dim must be >= 1");
+  if (p->dim > tclip::mm_max_dim())
+    return fail(TCLIP_ERR_INVALID, "dim %d exceeds the M-step kernel limit %d", p->dim, tclip::mm_max_dim());
+  if (p->n_query > 1024) return fail(TCLIP_ERR_INVALID, "n_query %d > 1024", p->n_query);
+  if (p->iters < 0 || p->iter_mm < 1) return fail(TCLIP_ERR_INVALID, "iters >= 0 and iter_mm >= 1 required");
+  if (p->n_support < 0) return fail(TCLIP_ERR_INVALID, "n_support < 0");
+  if ((long long)p->n_task * p->n_class > 0x7fffffffLL / 4) return fail(TCLIP_ERR_INVALID, "n_task * n_class too large");
+  if (p->mm_mode != TCLIP_MM_DENSE && p->mm_mode != TCLIP_MM_SKIP_DEAD) return fail(TCLIP_ERR_INVALID, "bad mm_mode");
+  if (num_checks(p->iter_mm, p->check_every) > kMaxChecks)
+    return fail(TCLIP_ERR_INVALID, "iter_mm / check_every > %d", kMaxChecks);
+  return TCLIP_OK;
+}
+
+// ---- small driver-side kernels --------------------------------------------------------------------------------
+__global__ void fill_kernel(float* p, float v, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void zero_int_kernel(int* p, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+
+// Stable compaction of the row classes (single CTA so the order, hence every later summation order, is fixed):
+//   live rows                      -> list_live   (iterated in the main loop)
+//   dead rows without a valid cache -> list_new    (full trajectory once, terms cached)
+__global__ void __launch_bounds__(1024)
+classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ list_live,
+                     int* __restrict__ list_new, int* __restrict__ counts, int rows) {
+  __shared__ int s_live[1024], s_new[1024];
+  const int per = (rows + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(rows, lo + per);
+  int nl = 0, nn = 0;
+  for (int r = lo; r < hi; ++r) {
+    if (live[r]) ++nl;
+    else if (!cache_valid[r]) ++nn;
+  }
+  s_live[threadIdx.x] = nl;
+  s_new[threadIdx.x] = nn;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    const int a = threadIdx.x >= o ? s_live[threadIdx.x - o] : 0;
+    const int b = threadIdx.x >= o ? s_new[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_live[threadIdx.x] += a;
+    s_new[threadIdx.x] += b;
+    __syncthreads();
+  }
+  int pl = s_live[threadIdx.x] - nl, pn = s_new[threadIdx.x] - nn;
+  for (int r = lo; r < hi; ++r) {
+    if (live[r]) {
+      list_live[pl++] = r;
+      cache_valid[r] = 0;
+    } else if (!cache_valid[r]) {
+      list_new[pn++] = r;
+      cache_valid[r] = 1;
+    }
+  }
+  if (threadIdx.x == 1023) {
+    counts[0] = s_live[1023];
+    counts[1] = s_new[1023];
+  }
+}
+
+// extra[c] = sum over dead rows of cache[row, c]  (one CTA per check, fixed order)
+__global__ void __launch_bounds__(256)
+sum_cache_kernel(const int* __restrict__ live, const double2* __restrict__ cache, double2* __restrict__ extra, int rows,
+                 int n_checks) {
+  __shared__ double2 red[256];
+  const int c = blockIdx.x;
+  double2 acc = make_double2(0.0, 0.0);
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    if (!live[r]) {
+      const double2 v = cache[(long)r * n_checks + c];
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      red[threadIdx.x].x += red[threadIdx.x + w].x;
+      red[threadIdx.x].y += red[threadIdx.x + w].y;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) extra[c] = red[0];
+}
+
+__global__ void __launch_bounds__(256) count_live_kernel(const int* __restrict__ live, int rows, int* out) {
+  __shared__ int red[256];
+  int c = 0;
+  for (int r = threadIdx.x; r < rows; r += 256) c += live[r];
+  red[threadIdx.x] = c;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
+__global__ void record_work_kernel(const tclip::MMState* state, const int* counts, const int* n_live_dev, int rows,
+                                   int iter_mm, int* mm_iters, int* n_live, long long* mm_rows) {
+  const int done = state->iters_done;
+  *mm_iters = done;
+  *n_live = n_live_dev ? *n_live_dev : rows;
+  if (mm_rows) {
+    if (counts) *mm_rows = (long long)counts[0] * done + (long long)counts[1] * iter_mm;
+    else *mm_rows = (long long)rows * done;
+  }
+}
+
+}  // namespace
+
+// ======================================================================================================================
+extern "C" {
+
+int tclip_version(void) { return 100; }
+
+const char* tclip_last_error(void) { return g_last_error.c_str(); }
+
+int tclip_mm_max_dim(void) { return tclip::mm_max_dim(); }
+
+int tclip_device_check(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return fail(TCLIP_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(TCLIP_ERR_DEVICE, "device %d not present (%d devices)", device, count);
+  int major = 0, minor = 0;
+  TCLIP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  TCLIP_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10)
+    return fail(TCLIP_ERR_DEVICE, "device %d is sm_%d%d; libtclip_b200 is built for sm_100a only", device, major, minor);
+  return TCLIP_OK;
+}
+
+int tclip_log_features(const float* x, float* out, long long count, void* stream) {
+  if (!x || !out || count < 0) return fail(TCLIP_ERR_INVALID, "tclip_log_features: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::log_features(x, out, (long)count, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_dirichlet_colsum_v(const float* u, float* colsum, float* v, int* live, int T, int n, int K, void* stream) {
+  if (!u || !colsum || T < 1 || n < 1 || K < 1) return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_colsum_v: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::colsum_v(u, colsum, v, live, T, n, K, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_dirichlet_moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
+                            const float* support_count, float* y, int T, int n, int K, int D, void* stream) {
+  if (!u || !logz || !colsum || !y || T < 1 || n < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_moments: bad arguments");
+  if ((support_sum == nullptr) != (support_count == nullptr))
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_moments: support_sum and support_count go together");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::moments(u, logz, colsum, support_sum, support_count, y, T, n, K, D, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_dirichlet_support_stats(const float* log_support, const long long* y_s, float* support_sum,
+                                  float* support_count, int T, int S, int K, int D, void* stream) {
+  if (!log_support || !y_s || !support_sum || !support_count || T < 1 || S < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_support_stats: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::support_stats(log_support, y_s, support_sum, support_count, T, S, K, D, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+size_t tclip_dirichlet_mm_workspace_bytes(int n_rows) {
+  if (n_rows < 1) return 0;
+  return align_up(sizeof(double2) * (size_t)tclip::mm_num_blocks(n_rows)) + align_up(sizeof(tclip::MMState));
+}
+
+int tclip_dirichlet_mm(const float* alpha_in, float* alpha_out, const float* y, int n_rows, int D, int iter_mm,
+                       int check_every, float tol, int* iters_done_dev, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (!alpha_in || !alpha_out || !y || n_rows < 1 || iter_mm < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_mm: bad arguments");
+  if (D < 1 || D > tclip::mm_max_dim())
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_mm: D=%d outside [1, %d]", D, tclip::mm_max_dim());
+  if (!workspace || workspace_bytes < tclip_dirichlet_mm_workspace_bytes(n_rows))
+    return fail(TCLIP_ERR_WORKSPACE, "tclip_dirichlet_mm: workspace too small (%zu < %zu)", workspace_bytes,
+                tclip_dirichlet_mm_workspace_bytes(n_rows));
+  if (int rc = current_device_ok()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(workspace);
+  tclip::MMLaunch l{};
+  l.alpha_in = alpha_in;
+  l.alpha_out = alpha_out;
+  l.y = y;
+  l.n_rows = n_rows;
+  l.D = D;
+  l.n_blocks = tclip::mm_num_blocks(n_rows);
+  l.partials = c.take<double2>(l.n_blocks);
+  l.state = c.take<tclip::MMState>(1);
+  TCLIP_CUDA(tclip::mm_run(l, iter_mm, check_every, tol, nullptr, st));
+  if (iters_done_dev)
+    TCLIP_CUDA(cudaMemcpyAsync(iters_done_dev, &l.state->iters_done, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return TCLIP_OK;
+}
+
+int tclip_dirichlet_commit(float* alpha, const float* work, const int* live, void* rowstat, float* task_criterion,
+                           float* criterion, int T, int K, int D, void* stream) {
+  if (!alpha || !work || !rowstat || !criterion || T < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_commit: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::commit(alpha, work, live, (double2*)rowstat, task_criterion, criterion, T, K, D,
+                           (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_dirichlet_estep(const float* alpha, const float* logz, const float* v, float lambd, void* norm, float* u,
+                          int* labels, int T, int n, int K, int D, int hard, void* stream) {
+  if (!alpha || !logz || !v || !norm || !u || T < 1 || n < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_estep: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::estep(alpha, logz, v, lambd, (double*)norm, u, labels, T, n, K, D, hard, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
+                             int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D, void* stream) {
+  if (!labels || !feats || !cluster_label || !cluster_size || !sample_cluster || !n_clusters || !proto || T < 1 ||
+      n < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_cluster_prototypes: bad arguments");
+  if (n > 1024) return fail(TCLIP_ERR_INVALID, "tclip_cluster_prototypes: n=%d > 1024", n);
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::cluster_prototypes(labels, feats, cluster_label, cluster_size, sample_cluster, n_clusters, proto,
+                                       T, n, D, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+size_t tclip_dirichlet_em_workspace_bytes(const tclip_dirichlet_problem* p) {
+  if (validate(p) != TCLIP_OK) return 0;
+  return carve(*p, nullptr).bytes;
+}
+
+int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate(p)) return rc;
+  if (!p->x_q || !p->u || !p->alpha || !p->v || !p->criterions || !p->mm_iters || !p->n_live)
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_em_run: x_q/u/alpha/v/criterions/mm_iters/n_live must be set");
+  const bool few = p->n_support > 0;
+  if (few && (!p->x_s || !p->y_s)) return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_em_run: few-shot needs x_s and y_s");
+  const size_t need = carve(*p, nullptr).bytes;
+  if (!workspace || workspace_bytes < need)
+    return fail(TCLIP_ERR_WORKSPACE, "tclip_dirichlet_em_run: workspace too small (%zu < %zu)", workspace_bytes, need);
+  if (int rc = current_device_ok()) return rc;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = p->n_task, n = p->n_query, K = p->n_class, D = p->dim, S = p->n_support;
+  const int rows = T * K;
+  const bool skip = (p->mm_mode == TCLIP_MM_SKIP_DEAD) && !few;
+  const int nc = num_checks(p->iter_mm, p->check_every);
+  EmWorkspace w = carve(*p, workspace);
+
+  // initialisation: v = 0, u = query, alpha = 1 (em_dirichlet.py:202-210); features logged once
+  TCLIP_CUDA(cudaMemsetAsync(p->v, 0, sizeof(float) * (size_t)rows, st));
+  TCLIP_CUDA(cudaMemcpyAsync(p->u, p->x_q, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
+  fill_kernel<<<(unsigned)(((long)rows * D + 255) / 256), 256, 0, st>>>(p->alpha, 1.0f, (long)rows * D);
+  TCLIP_CUDA(tclip::log_features(p->x_q, w.logz, (long)T * n * D, st));
+  if (few) {
+    TCLIP_CUDA(tclip::log_features(p->x_s, w.log_support, (long)T * S * D, st));
+    TCLIP_CUDA(tclip::support_stats(w.log_support, p->y_s, w.support_sum, w.support_count, T, S, K, D, st));
+  }
+  if (skip) {
+    zero_int_kernel<<<(rows + 255) / 256, 256, 0, st>>>(w.cache_valid, rows);
+    TCLIP_CUDA(cudaMemsetAsync(w.state_free, 0, sizeof(tclip::MMState), st));
+  }
+
+  for (int it = 0; it < p->iters; ++it) {
+    // cluster sizes of the current u, live mask, and v (v_update uses the same u, em_dirichlet.py:230)
+    TCLIP_CUDA(tclip::colsum_v(p->u, w.colsum, p->v, few ? nullptr : w.live, T, n, K, st));
+    TCLIP_CUDA(tclip::moments(p->u, w.logz, w.colsum, w.support_sum, w.support_count, w.y, T, n, K, D, st));
+
+    tclip::MMLaunch l{};
+    l.alpha_in = p->alpha;
+    l.alpha_out = w.work;
+    l.y = w.y;
+    l.D = D;
+    l.partials = w.partials;
+    l.state = w.state;
+    if (!skip) {
+      l.n_rows = rows;
+      l.n_blocks = tclip::mm_num_blocks(rows);
+      TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nullptr, st));
+    } else {
+      classify_rows_kernel<<<1, 1024, 0, st>>>(w.live, w.cache_valid, w.list_live, w.list_new, w.counts, rows);
+      // newly dead rows: full trajectory from their kept row with y = -10, criterion terms cached per check
+      tclip::MMLaunch d = l;
+      d.row_list = w.list_new;
+      d.n_rows_dev = w.counts + 1;
+      d.n_rows = rows;
+      d.n_blocks = tclip::mm_num_blocks(rows);
+      d.state = w.state_free;
+      d.row_cache = w.cache;
+      d.n_checks = nc;
+      TCLIP_CUDA(tclip::mm_run(d, p->iter_mm, p->check_every, p->tol, nullptr, st));
+      if (nc > 0) sum_cache_kernel<<<nc, 256, 0, st>>>(w.live, w.cache, w.extra, rows, nc);
+      l.row_list = w.list_live;
+      l.n_rows_dev = w.counts;
+      l.n_rows = rows;
+      l.n_blocks = tclip::mm_num_blocks(rows);
+      TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nc > 0 ? w.extra : nullptr, st));
+    }
+    int* n_live_dev = nullptr;
+    if (!few) {
+      count_live_kernel<<<1, 256, 0, st>>>(w.live, rows, p->n_live + it);
+      n_live_dev = p->n_live + it;
+    }
+    record_work_kernel<<<1, 1, 0, st>>>(w.state, skip ? w.counts : nullptr, n_live_dev, rows, p->iter_mm,
+                                         p->mm_iters + it, p->n_live + it, p->mm_rows ? p->mm_rows + it : nullptr);
+    // empty clusters keep their previous row; logged criterion (em_dirichlet.py:224-226,236-238)
+    TCLIP_CUDA(tclip::commit(p->alpha, w.work, few ? nullptr : w.live, w.rowstat, w.task_crit, p->criterions + it, T,
+                             K, D, st));
+    // u <- softmax(logits + lambda v / n) [-> one-hot]
+    TCLIP_CUDA(tclip::estep(p->alpha, w.logz, p->v, p->lambd, w.norm, p->u, p->labels, T, n, K, D, p->hard, st));
+    if (p->iter_events && p->iter_events[it]) TCLIP_CUDA(cudaEventRecord((cudaEvent_t)p->iter_events[it], st));
+  }
+  TCLIP_CUDA(cudaGetLastError());
+  return TCLIP_OK;
+}
+
+}  // extern "C"

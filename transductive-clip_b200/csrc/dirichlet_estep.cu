@@ -1,0 +1,474 @@
+// dirichlet_estep.cu — everything of the Dirichlet EM loop that is not the MM M-step (sm_100a).
+//
+// Reference call sites (SegoleneMartin/transductive-CLIP, src/methods/zero_shot/em_dirichlet.py unless noted):
+//   cluster sizes, live mask, v_update       :145-151, :217-218      -> colsum_v_kernel
+//   moments y_cst (+ few-shot support terms) :219-222, few_shot/em_dirichlet.py:196-200 -> moments_kernel
+//   empty-cluster restore + outer criterion  :224-226, :236-238      -> commit_kernel, criterion_kernel
+//   Dirichlet log-normaliser                 :35-36                  -> lognorm_kernel
+//   contraction log z . (alpha-1)^T          :37-38                  -> logits_kernel
+//   softmax / argmax one-hot                 :142-143, hard_em_dirichlet.py:256-258 -> softmax_kernel
+//   prototypes for label matching            :61-70, utils.py:380-399 -> cluster_order_kernel, prototypes_kernel
+//
+// Layouts (all row-major, innermost last): u [T,n,K], logz [T,n,D], alpha/y/work [T,K,D], colsum/v [T,K].
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "tclip_kernels.cuh"
+
+namespace tclip {
+
+namespace {
+
+constexpr float kEps = 1e-15f;
+
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- log(z + eps) -----------------------------------------------------------------------------------------------
+__global__ void log_features_kernel(const float* __restrict__ x, float* __restrict__ out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = logf(x[i] + kEps);
+}
+
+// ---- cluster sizes, live mask and the dual variable v ------------------------------------------------------------
+// colsum[t,k] = sum_n u[t,n,k];  live = colsum > 1e-15;  v = log(colsum / n + 1e-15) + 1
+__global__ void colsum_v_kernel(const float* __restrict__ u, float* __restrict__ colsum, float* __restrict__ v,
+                                int* __restrict__ live, int n, int K) {
+  const int t = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float* up = u + (long)t * n * K + k;
+  float s = 0.0f;
+  for (int i = 0; i < n; ++i) s += up[(long)i * K];
+  colsum[(long)t * K + k] = s;
+  if (v) v[(long)t * K + k] = logf(s / (float)n + kEps) + 1.0f;
+  if (live) live[(long)t * K + k] = s > kEps ? 1 : 0;
+}
+
+// ---- moments: y[t,k,d] = sum_n u[t,n,k] logz[t,n,d] / colsum[t,k]  (a [K x n] . [n x D] product per task) --------
+// 64(k) x 64(d) tile per CTA, 256 threads, 4x4 outputs per thread, n staged through shared memory.
+constexpr int kMomTile = 64;
+constexpr int kMomStage = 16;
+
+__global__ void __launch_bounds__(256)
+moments_kernel(const float* __restrict__ u, const float* __restrict__ logz, const float* __restrict__ colsum,
+               const float* __restrict__ support_sum, const float* __restrict__ support_count,
+               float* __restrict__ y, int n, int K, int D, int few_shot) {
+  __shared__ float us[kMomStage][kMomTile + 4];
+  __shared__ float ls[kMomStage][kMomTile + 4];
+  const int t = blockIdx.z;
+  const int k0 = blockIdx.y * kMomTile;
+  const int d0 = blockIdx.x * kMomTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* ub = u + (long)t * n * K;
+  const float* lb = logz + (long)t * n * D;
+
+  // a CTA whose 64 clusters are all empty only has to write the fill value
+  float acc[4][4] = {};
+  for (int n0 = 0; n0 < n; n0 += kMomStage) {
+    for (int i = threadIdx.x; i < kMomStage * kMomTile; i += 256) {
+      const int r = i / kMomTile, c = i % kMomTile;
+      const int nn = n0 + r;
+      us[r][c] = (nn < n && k0 + c < K) ? ub[(long)nn * K + k0 + c] : 0.0f;
+      ls[r][c] = (nn < n && d0 + c < D) ? lb[(long)nn * D + d0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kMomStage; ++r) {
+      float uu[4], ll[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uu[i] = us[r][ty * 4 + i];
+        ll[i] = ls[r][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(uu[i], ll[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+    const float cs = colsum[(long)t * K + k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + tx * 4 + j;
+      if (d >= D) continue;
+      const long o = ((long)t * K + k) * D + d;
+      float val;
+      if (few_shot) {
+        // (1 / (count_s + sum u)) * (support_sum + sum u logz): few_shot/em_dirichlet.py:196-200
+        val = (1.0f / (support_count[(long)t * K + k] + cs)) * (support_sum[o] + acc[i][j]);
+      } else {
+        val = cs > kEps ? acc[i][j] / fmaxf(cs, kEps) : -10.0f;
+      }
+      y[o] = val;
+    }
+  }
+}
+
+// ---- few-shot support statistics (iteration invariant): per-class count and per-class sum of log-features -------
+__global__ void support_stats_kernel(const float* __restrict__ log_support, const long long* __restrict__ y_s,
+                                     float* __restrict__ support_sum, float* __restrict__ support_count, int S,
+                                     int K, int D) {
+  // one CTA per (task, class): samples are scanned in index order so the sum order is deterministic
+  const int t = blockIdx.y, k = blockIdx.x;
+  const long long* ys = y_s + (long)t * S;
+  const float* xs = log_support + (long)t * S * D;
+  __shared__ int members[1024];
+  __shared__ int count;
+  int total = 0;
+  for (int base = 0; base < S; base += 1024) {
+    if (threadIdx.x == 0) {
+      int c = 0;
+      for (int i = base; i < min(S, base + 1024); ++i)
+        if (ys[i] == k) members[c++] = i;
+      count = c;
+    }
+    __syncthreads();
+    const int c = count;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float acc = (base == 0) ? 0.0f : support_sum[((long)t * K + k) * D + d];
+      for (int m = 0; m < c; ++m) acc += xs[(long)members[m] * D + d];
+      support_sum[((long)t * K + k) * D + d] = acc;
+    }
+    total += c;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) support_count[(long)t * K + k] = (float)total;
+}
+
+// ---- commit: empty clusters keep their previous row; per-row pieces of the outer criterion ------------------------
+// rowstat[row] = (||old - new||^2, ||old||^2) over the row; alpha[row] <- work[row] when the cluster is live.
+__global__ void __launch_bounds__(128)
+commit_kernel(float* __restrict__ alpha, const float* __restrict__ work, const int* __restrict__ live,
+              double2* __restrict__ rowstat, int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bool lv = live ? live[row] != 0 : true;
+  float* a = alpha + (long)row * D;
+  const float* w = work + (long)row * D;
+  float dsq = 0.0f, osq = 0.0f;
+  for (int d = lane; d < D; d += 32) {
+    const float o = a[d];
+    const float nw = lv ? w[d] : o;
+    const float df = o - nw;
+    dsq = fmaf(df, df, dsq);
+    osq = fmaf(o, o, osq);
+    if (lv) a[d] = nw;
+  }
+  const double ds = warp_sum_f64((double)dsq), os = warp_sum_f64((double)osq);
+  if (lane == 0) rowstat[row] = make_double2(ds, os);
+}
+
+// criterion[t] = ||alpha_old - alpha||_F / ||alpha_old||_F per task, then the mean over tasks (one CTA, fixed order)
+__global__ void __launch_bounds__(256)
+criterion_kernel(const double2* __restrict__ rowstat, float* __restrict__ task_crit, float* __restrict__ crit_out,
+                 int T, int K) {
+  __shared__ double red[256];
+  double total = 0.0;
+  for (int t = 0; t < T; ++t) {
+    double dx = 0.0, dy = 0.0;
+    for (int k = threadIdx.x; k < K; k += 256) {
+      const double2 r = rowstat[(long)t * K + k];
+      dx += r.x;
+      dy += r.y;
+    }
+    red[threadIdx.x] = dx;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+      __syncthreads();
+    }
+    const double num = red[0];
+    __syncthreads();
+    red[threadIdx.x] = dy;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+      __syncthreads();
+    }
+    const double den = red[0];
+    __syncthreads();
+    const float c = sqrtf((float)num) / sqrtf((float)den);
+    if (threadIdx.x == 0 && task_crit) task_crit[t] = c;
+    total += (double)c;
+  }
+  if (threadIdx.x == 0) *crit_out = (float)(total / (double)T);
+}
+
+// ---- Dirichlet log-normaliser: norm[t,k] = lnGamma(sum_d a) - sum_d lnGamma(a), float64, one warp per row --------
+__global__ void __launch_bounds__(128)
+lognorm_kernel(const float* __restrict__ alpha, double* __restrict__ norm, int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* a = alpha + (long)row * D;
+  double s = 0.0, lg = 0.0;
+  for (int d = lane; d < D; d += 32) {
+    const double v = (double)a[d];
+    s += v;
+    lg += lgamma(v);
+  }
+  s = warp_sum_f64(s);
+  lg = warp_sum_f64(lg);
+  if (lane == 0) norm[row] = lgamma(s) - lg;
+}
+
+// ---- contraction l3[t,n,k] = sum_d logz[t,n,d] (alpha[t,k,d] - 1): [n x D] . [D x K] per task ---------------------
+// 64(n) x 64(k) tile, BK = 16, 256 threads, 4x4 per thread; partial sums per BK slab are folded into the running
+// total so the summation is blocked rather than a single 1000-term chain.
+constexpr int kLgTile = 64;
+constexpr int kLgBK = 16;
+
+__global__ void __launch_bounds__(256)
+logits_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, float* __restrict__ l3, int n, int K,
+              int D) {
+  __shared__ float as[kLgBK][kLgTile + 4];  // logz tile, transposed: [d][n]
+  __shared__ float bs[kLgBK][kLgTile + 4];  // (alpha-1) tile, transposed: [d][k]
+  const int t = blockIdx.z;
+  const int n0 = blockIdx.y * kLgTile;
+  const int k0 = blockIdx.x * kLgTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* ab = logz + (long)t * n * D;
+  const float* bb = alpha + (long)t * K * D;
+  float acc[4][4] = {};
+  for (int d0 = 0; d0 < D; d0 += kLgBK) {
+    for (int i = threadIdx.x; i < kLgTile * kLgBK; i += 256) {
+      const int r = i / kLgBK, c = i % kLgBK;
+      const int d = d0 + c;
+      as[c][r] = (n0 + r < n && d < D) ? ab[(long)(n0 + r) * D + d] : 0.0f;
+      bs[c][r] = (k0 + r < K && d < D) ? bb[(long)(k0 + r) * D + d] - 1.0f : 0.0f;
+    }
+    __syncthreads();
+    float part[4][4] = {};
+#pragma unroll
+    for (int c = 0; c < kLgBK; ++c) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = as[c][ty * 4 + i];
+        bv[i] = bs[c][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int nn = n0 + ty * 4 + i;
+    if (nn >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) l3[((long)t * n + nn) * K + k] = acc[i][j];
+    }
+  }
+}
+
+// ---- responsibilities: u = softmax_k(norm + l3 + lambda v / n); optional argmax -> one-hot ------------------------
+// One warp per (task, query).  labels = argmax of the *softmaxed* float32 values, first index wins
+// (hard_em_dirichlet.py:256-258).  `u` may alias `l3` (each warp reads its row before overwriting it).
+__global__ void __launch_bounds__(128)
+softmax_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
+               float* u, int* __restrict__ labels, int rows, int n, int K, int hard) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int t = row / n;
+  const float* x = l3 + (long)row * K;
+  const double* nm = norm + (long)t * K;
+  const float* vv = v + (long)t * K;
+  float* out = u + (long)row * K;
+  const float fn = (float)n;
+
+  float mx = -CUDART_INF_F;
+  for (int k = lane; k < K; k += 32) {
+    const float logit = (float)(nm[k] + (double)x[k]) + (lambd * vv[k]) / fn;
+    mx = fmaxf(mx, logit);
+  }
+  mx = warp_max_f32(mx);
+  float sum = 0.0f;
+  for (int k = lane; k < K; k += 32) {
+    const float logit = (float)(nm[k] + (double)x[k]) + (lambd * vv[k]) / fn;
+    sum += expf(logit - mx);
+  }
+  sum = warp_sum_f32(sum);
+  float best = -1.0f;
+  int best_k = 0x7fffffff;
+  for (int k = lane; k < K; k += 32) {
+    const float logit = (float)(nm[k] + (double)x[k]) + (lambd * vv[k]) / fn;
+    const float p = expf(logit - mx) / sum;
+    if (p > best) {  // strict: the lowest k of this lane's stripe wins ties
+      best = p;
+      best_k = k;
+    }
+    if (!hard) out[k] = p;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    if (ob > best || (ob == best && ok < best_k)) {
+      best = ob;
+      best_k = ok;
+    }
+  }
+  if (hard) {
+    for (int k = lane; k < K; k += 32) out[k] = (k == best_k) ? 1.0f : 0.0f;
+  }
+  if (lane == 0 && labels) labels[row] = best_k;
+}
+
+// ---- label matching inputs -----------------------------------------------------------------------------------------
+// Per task: clusters in order of first appearance among the predictions (utils.py:389-396), the cluster index of
+// every query, and the cluster sizes.  n <= 1024 queries per task.
+__global__ void cluster_order_kernel(const int* __restrict__ labels, int* __restrict__ cluster_label,
+                                     int* __restrict__ cluster_size, int* __restrict__ sample_cluster,
+                                     int* __restrict__ n_clusters, int n) {
+  extern __shared__ int sh[];
+  int* lab = sh;          // [n]
+  int* first = sh + n;    // [n] 1 when this sample opens a new cluster
+  int* rank = sh + 2 * n; // [n] cluster index of the sample's cluster
+  const int t = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    lab[i] = labels[(long)t * n + i];
+    cluster_label[(long)t * n + i] = -1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int f = 1;
+    for (int j = 0; j < i; ++j) f &= (lab[j] != lab[i]);
+    first[i] = f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // index of the first sample carrying my label, then the number of cluster openings before it
+    int j0 = i;
+    for (int j = 0; j < i; ++j)
+      if (lab[j] == lab[i]) {
+        j0 = j;
+        break;
+      }
+    int r = 0;
+    for (int j = 0; j < j0; ++j) r += first[j];
+    rank[i] = r;
+    sample_cluster[(long)t * n + i] = r;
+    if (first[i]) cluster_label[(long)t * n + r] = lab[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    int sz = 0;
+    for (int i = 0; i < n; ++i) sz += (rank[i] == c);
+    cluster_size[(long)t * n + c] = sz;
+  }
+  if (threadIdx.x == 0) {
+    int nc = 0;
+    for (int i = 0; i < n; ++i) nc += first[i];
+    n_clusters[t] = nc;
+  }
+}
+
+// proto[t,c,:] = mean of the raw features of the queries in cluster c (index order), c < n_clusters[t]; rest zero.
+__global__ void prototypes_kernel(const float* __restrict__ feats, const int* __restrict__ sample_cluster,
+                                  const int* __restrict__ cluster_size, const int* __restrict__ n_clusters,
+                                  float* __restrict__ proto, int n, int D) {
+  const int t = blockIdx.y, c = blockIdx.x;
+  float* out = proto + ((long)t * n + c) * D;
+  if (c >= n_clusters[t]) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = 0.0f;
+    return;
+  }
+  const float inv = fmaxf((float)cluster_size[(long)t * n + c], kEps);
+  const int* sc = sample_cluster + (long)t * n;
+  const float* x = feats + (long)t * n * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.0f;
+    for (int i = 0; i < n; ++i)
+      if (sc[i] == c) acc += x[(long)i * D + d];
+    out[d] = acc / inv;
+  }
+}
+
+}  // namespace
+
+// ---- host-side launchers ------------------------------------------------------------------------------------------
+cudaError_t log_features(const float* x, float* out, long count, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  log_features_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(x, out, count);
+  return cudaGetLastError();
+}
+
+cudaError_t colsum_v(const float* u, float* colsum, float* v, int* live, int T, int n, int K, cudaStream_t st) {
+  colsum_v_kernel<<<dim3((K + 127) / 128, T), 128, 0, st>>>(u, colsum, v, live, n, K);
+  return cudaGetLastError();
+}
+
+cudaError_t moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
+                    const float* support_count, float* y, int T, int n, int K, int D, cudaStream_t st) {
+  const int few = support_sum != nullptr;
+  moments_kernel<<<dim3((D + kMomTile - 1) / kMomTile, (K + kMomTile - 1) / kMomTile, T), 256, 0, st>>>(
+      u, logz, colsum, support_sum, support_count, y, n, K, D, few);
+  return cudaGetLastError();
+}
+
+cudaError_t support_stats(const float* log_support, const long long* y_s, float* support_sum, float* support_count,
+                          int T, int S, int K, int D, cudaStream_t st) {
+  support_stats_kernel<<<dim3(K, T), 256, 0, st>>>(log_support, y_s, support_sum, support_count, S, K, D);
+  return cudaGetLastError();
+}
+
+cudaError_t commit(float* alpha, const float* work, const int* live, double2* rowstat, float* task_crit,
+                   float* crit_out, int T, int K, int D, cudaStream_t st) {
+  const int rows = T * K;
+  commit_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, work, live, rowstat, rows, D);
+  criterion_kernel<<<1, 256, 0, st>>>(rowstat, task_crit, crit_out, T, K);
+  return cudaGetLastError();
+}
+
+cudaError_t estep(const float* alpha, const float* logz, const float* v, float lambd, double* norm, float* u,
+                  int* labels, int T, int n, int K, int D, int hard, cudaStream_t st) {
+  const int rows = T * K;
+  lognorm_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, norm, rows, D);
+  logits_kernel<<<dim3((K + kLgTile - 1) / kLgTile, (n + kLgTile - 1) / kLgTile, T), 256, 0, st>>>(logz, alpha, u, n,
+                                                                                                  K, D);
+  const int qrows = T * n;
+  softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(u, norm, v, lambd, u, labels, qrows, n, K, hard);
+  return cudaGetLastError();
+}
+
+cudaError_t cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
+                               int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
+                               cudaStream_t st) {
+  if (n > 1024) return cudaErrorInvalidValue;
+  cluster_order_kernel<<<T, 128, 3 * n * sizeof(int), st>>>(labels, cluster_label, cluster_size, sample_cluster,
+                                                            n_clusters, n);
+  prototypes_kernel<<<dim3(n, T), 256, 0, st>>>(feats, sample_cluster, cluster_size, n_clusters, proto, n, D);
+  return cudaGetLastError();
+}
+
+}  // namespace tclip

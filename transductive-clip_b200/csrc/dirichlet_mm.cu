@@ -1,0 +1,237 @@
+// dirichlet_mm.cu — the Dirichlet M-step: majorise-minimise fixed point on alpha (sm_100a).
+//
+// Replaces `curvature` + `update_alpha` of the reference (src/methods/zero_shot/em_dirichlet.py:153-177; identical
+// copies in zero_shot/hard_em_dirichlet.py:153-177 and few_shot/{em,hard_em}_dirichlet.py:123-147), which is 99.6 %
+// of the reference's run time.
+//
+// Layout: alpha, y are [rows, D] float32 row-major, rows = n_task * n_class, D = feature dim (<= 1024).
+// One warp owns one row: element d lives in lane d % 32, register slot d / 32, so a row of D <= 1024 floats stays
+// in registers for a whole chunk of MM iterations; HBM sees 12 B per element per chunk (read alpha, read y, write
+// alpha), i.e. the kernel is FP32/MUFU-issue bound, not memory bound (DESIGN.md "MM kernel").
+//
+// The reference's early exit is *batch-global*: at l in {50, 100, ...} (l > 0) it stops iff
+// ||a_new - a||^2 / ||a||^2 < 1e-11 over the whole [n_task, K, D] tensor.  The iteration loop is therefore cut into
+// chunks that end exactly at those l: a chunk kernel emits per-block partial sums of the two norms for its last
+// iteration, a 1-block decide kernel folds them in a fixed order (deterministic) and raises a device-side `done`
+// flag that later chunk kernels test on entry.  No host synchronisation anywhere in the M-step.
+#include <cuda_runtime.h>
+
+#include <array>
+#include <utility>
+
+#include "tclip_kernels.cuh"
+#include "tclip_math.cuh"
+
+namespace tclip {
+
+namespace {
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum of the NG register slots of one lane as a balanced tree (fp32), last slot masked by `tail_ok`.
+template <int NG>
+__device__ __forceinline__ float lane_tree_sum(const float (&a)[NG], bool tail_ok) {
+  float t[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) t[g] = a[g];
+  t[NG - 1] = tail_ok ? t[NG - 1] : 0.0f;
+#pragma unroll
+  for (int w = 1; w < NG; w <<= 1) {
+#pragma unroll
+    for (int g = 0; g + w < NG; g += 2 * w) t[g] += t[g + w];
+  }
+  return t[0];
+}
+
+// NG = ceil(D / 32) register slots per lane; only the last slot can be partially populated.
+template <int NG>
+__global__ void __launch_bounds__(kMMThreads)
+mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict__ y,
+                const int* __restrict__ row_list, const int* __restrict__ n_rows_dev, int n_rows_host, int D,
+                int n_iters, int emit_check, double2* __restrict__ partials, const MMState* __restrict__ state,
+                double2* __restrict__ row_cache, int n_checks, int check_idx) {
+  if (state->done) return;  // an earlier chunk met the batch-global criterion: the M-step is over
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n_rows = n_rows_dev ? *n_rows_dev : n_rows_host;
+  const int slot = blockIdx.x * (kMMThreads / 32) + warp;
+  const bool active = slot < n_rows;
+  double dsq = 0.0, asq = 0.0;
+  long row = 0;
+
+  if (active) {
+    row = row_list ? row_list[slot] : slot;
+    const float* ain = alpha_in + row * D;
+    const float* yin = y + row * D;
+    float* aout = alpha_out + row * D;
+    const bool tail_ok = (NG - 1) * 32 + lane < D;
+
+    float a[NG], yy[NG];
+#pragma unroll
+    for (int g = 0; g < NG - 1; ++g) {
+      a[g] = ain[g * 32 + lane];
+      yy[g] = __ldg(yin + g * 32 + lane);
+    }
+    a[NG - 1] = tail_ok ? ain[(NG - 1) * 32 + lane] : 1.0f;   // padding lanes iterate on a harmless dummy
+    yy[NG - 1] = tail_ok ? __ldg(yin + (NG - 1) * 32 + lane) : -1.0f;
+
+    double s = warp_sum_f64((double)lane_tree_sum<NG>(a, tail_ok));
+    for (int it = 0; it < n_iters - 1; ++it) {
+      const double ps = digamma_f64(s);
+      const float hi = (float)ps;
+      const float lo = (float)(ps - (double)hi);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) a[g] = mm_update_element(a[g], yy[g], hi, lo);
+      s = warp_sum_f64((double)lane_tree_sum<NG>(a, tail_ok));
+    }
+    {  // last iteration of the chunk: also the one the criterion is evaluated on
+      const double ps = digamma_f64(s);
+      const float hi = (float)ps;
+      const float lo = (float)(ps - (double)hi);
+      float d2 = 0.0f, a2 = 0.0f;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float an = mm_update_element(a[g], yy[g], hi, lo);
+        const bool ok = (g < NG - 1) || tail_ok;
+        const float df = an - a[g];
+        d2 = ok ? fmaf(df, df, d2) : d2;
+        a2 = ok ? fmaf(a[g], a[g], a2) : a2;
+        a[g] = an;
+      }
+      dsq = (double)d2;
+      asq = (double)a2;
+    }
+#pragma unroll
+    for (int g = 0; g < NG - 1; ++g) aout[g * 32 + lane] = a[g];
+    if (tail_ok) aout[(NG - 1) * 32 + lane] = a[NG - 1];
+  }
+
+  if (emit_check == 2) {  // free-running rows: each row keeps its own terms
+    dsq = warp_sum_f64(dsq);
+    asq = warp_sum_f64(asq);
+    if (active && lane == 0) row_cache[row * n_checks + check_idx] = make_double2(dsq, asq);
+  } else if (emit_check) {
+    __shared__ double2 red[kMMThreads / 32];
+    dsq = warp_sum_f64(dsq);
+    asq = warp_sum_f64(asq);
+    if (lane == 0) red[warp] = make_double2(dsq, asq);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double2 acc = red[0];
+#pragma unroll
+      for (int w = 1; w < kMMThreads / 32; ++w) {
+        acc.x += red[w].x;
+        acc.y += red[w].y;
+      }
+      partials[blockIdx.x] = acc;
+    }
+  }
+}
+
+// Folds the per-block partials of the chunk that just ran (fixed order => bit-reproducible), applies the reference's
+// test `criterion < tol` (false for NaN, so a NaN never stops the loop) and keeps the executed-iteration count.
+__global__ void __launch_bounds__(256)
+mm_decide_kernel(const double2* __restrict__ partials, int n_partials, const double2* __restrict__ extra,
+                 int has_check, int iters_cum, float tol, MMState* state) {
+  if (state->done) return;
+  __shared__ double2 red[256];
+  double2 acc = make_double2(0.0, 0.0);
+  if (has_check) {
+    for (int i = threadIdx.x; i < n_partials; i += 256) {
+      const double2 p = partials[i];
+      acc.x += p.x;
+      acc.y += p.y;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      red[threadIdx.x].x += red[threadIdx.x + w].x;
+      red[threadIdx.x].y += red[threadIdx.x + w].y;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    state->iters_done = iters_cum;
+    if (has_check) {
+      double num = red[0].x, den = red[0].y;
+      if (extra) {  // norm contributions of rows that are not iterated in this launch (cached dead rows)
+        num += extra->x;
+        den += extra->y;
+      }
+      state->last_num = num;
+      state->last_den = den;
+      // the reference forms the ratio of two float32 squared norms; do the comparison on the float32 ratio too
+      const float crit = (float)num / (float)den;
+      if (crit < tol) state->done = 1;
+    }
+  }
+}
+
+__global__ void mm_reset_kernel(MMState* state) {
+  state->done = 0;
+  state->iters_done = 0;
+  state->last_num = 0.0;
+  state->last_den = 0.0;
+}
+
+template <int NG>
+void launch_chunk(const MMLaunch& p, int n_iters, int emit_check, int check_idx, cudaStream_t st) {
+  mm_chunk_kernel<NG><<<p.n_blocks, kMMThreads, 0, st>>>(p.alpha_in, p.alpha_out, p.y, p.row_list, p.n_rows_dev,
+                                                         p.n_rows, p.D, n_iters, emit_check, p.partials, p.state,
+                                                         p.row_cache, p.n_checks, check_idx);
+}
+
+using ChunkFn = void (*)(const MMLaunch&, int, int, int, cudaStream_t);
+
+template <int... I>
+constexpr auto make_table(std::integer_sequence<int, I...>) {
+  return std::array<ChunkFn, sizeof...(I)>{&launch_chunk<I + 1>...};
+}
+
+}  // namespace
+
+int mm_max_dim() { return 32 * kMMMaxSlots; }
+
+int mm_num_blocks(int n_rows) { return (n_rows + (kMMThreads / 32) - 1) / (kMMThreads / 32); }
+
+// Enqueue one full M-step (<= iter_mm MM iterations with the batch-global early exit) on `st`.
+cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const double2* extra_checks, cudaStream_t st) {
+  static constexpr auto table = make_table(std::make_integer_sequence<int, kMMMaxSlots>{});
+  if (p.D < 1 || p.D > mm_max_dim()) return cudaErrorInvalidValue;
+  const int ng = (p.D + 31) / 32;
+  const ChunkFn fn = table[ng - 1];
+  mm_reset_kernel<<<1, 1, 0, st>>>(p.state);
+  const float* first_in = p.alpha_in;
+  int start = 0, check_idx = 0;
+  while (start < iter_mm) {
+    // the chunk ends at the next l with l > 0, l % check_every == 0, or at the last iteration
+    int end = iter_mm - 1;
+    int has_check = 0;
+    if (check_every > 0) {
+      const int from = start > 1 ? start : 1;
+      const int cand = ((from + check_every - 1) / check_every) * check_every;  // first check point >= start
+      if (cand <= iter_mm - 1) {
+        end = cand;
+        has_check = 1;
+      }
+    }
+    MMLaunch q = p;
+    q.alpha_in = (start == 0) ? first_in : p.alpha_out;
+    const bool free_run = p.row_cache != nullptr;
+    fn(q, end - start + 1, has_check ? (free_run ? 2 : 1) : 0, check_idx, st);
+    const double2* extra = (has_check && extra_checks) ? extra_checks + check_idx : nullptr;
+    mm_decide_kernel<<<1, 256, 0, st>>>(p.partials, p.n_blocks, extra, free_run ? 0 : has_check, end + 1, tol,
+                                        p.state);
+    if (has_check) ++check_idx;
+    start = end + 1;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace tclip

@@ -1,0 +1,55 @@
+// tclip_kernels.cuh — internal C++ interface between the kernel translation units and the C-ABI (capi.cu).
+// Nothing here is exported; the public surface is include/tclip_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tclip {
+
+// ---- Dirichlet MM M-step (dirichlet_mm.cu) --------------------------------------------------------------------
+constexpr int kMMThreads = 128;    // 4 warps = 4 rows per CTA
+constexpr int kMMMaxSlots = 32;    // register slots per lane => D <= 1024
+
+struct MMState {          // lives in device memory; written only by the reset / decide kernels
+  int done;               // 1 once the batch-global criterion fell below tol
+  int iters_done;         // MM iterations executed so far in this M-step
+  double last_num;        // ||a_new - a||^2 at the last check
+  double last_den;        // ||a||^2      at the last check
+};
+
+struct MMLaunch {
+  const float* alpha_in;  // [rows_total, D] state the M-step starts from
+  float* alpha_out;       // [rows_total, D] working/result state (may alias alpha_in)
+  const float* y;         // [rows_total, D] moments y_cst
+  const int* row_list;    // optional: indices of the rows to iterate (nullptr = rows 0..n_rows-1)
+  const int* n_rows_dev;  // optional: device-side row count (overrides n_rows)
+  int n_rows;             // rows to iterate (upper bound when n_rows_dev is given)
+  int D;
+  int n_blocks;           // grid size = mm_num_blocks(n_rows)
+  double2* partials;      // [n_blocks] scratch for the criterion
+  MMState* state;
+  // "free-running" mode (row_cache != nullptr): ignore the batch-global exit, run all iter_mm iterations and store
+  // each row's own criterion terms per check point: row_cache[row * n_checks + check] = (||da||^2, ||a||^2)
+  double2* row_cache;
+  int n_checks;
+};
+
+int mm_max_dim();
+int mm_num_blocks(int n_rows);
+cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const double2* extra_checks, cudaStream_t st);
+
+// ---- the rest of the Dirichlet EM loop (dirichlet_estep.cu) ---------------------------------------------------------
+cudaError_t log_features(const float* x, float* out, long count, cudaStream_t st);
+cudaError_t colsum_v(const float* u, float* colsum, float* v, int* live, int T, int n, int K, cudaStream_t st);
+cudaError_t moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
+                    const float* support_count, float* y, int T, int n, int K, int D, cudaStream_t st);
+cudaError_t support_stats(const float* log_support, const long long* y_s, float* support_sum, float* support_count,
+                          int T, int S, int K, int D, cudaStream_t st);
+cudaError_t commit(float* alpha, const float* work, const int* live, double2* rowstat, float* task_crit,
+                   float* crit_out, int T, int K, int D, cudaStream_t st);
+cudaError_t estep(const float* alpha, const float* logz, const float* v, float lambd, double* norm, float* u,
+                  int* labels, int T, int n, int K, int D, int hard, cudaStream_t st);
+cudaError_t cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
+                               int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
+                               cudaStream_t st);
+
+}  // namespace tclip

@@ -1,0 +1,211 @@
+"""Tensor-level wrappers of the C ABI.  PyTorch is used for device memory and streams only; every operation below
+is a kernel of ``libtclip_b200.so`` launched on the current CUDA stream.  CPU tensors are rejected — there is no
+fallback path."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import DirichletProblem, TCLIP_MM_DENSE, TCLIP_MM_SKIP_DEAD, check
+
+__all__ = ["log_features", "colsum_v", "moments", "support_stats", "mm_update_alpha", "commit", "estep",
+           "cluster_prototypes", "dirichlet_em", "device_check", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor; tclip_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def device_check(device: int | None = None) -> None:
+    lib = _lib.load()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    check(lib.tclip_device_check(dev))
+
+
+def log_features(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    lib = _lib.load()
+    _need(x, torch.float32, "x")
+    out = torch.empty_like(x) if out is None else _need(out, torch.float32, "out")
+    check(lib.tclip_log_features(_ptr(x), _ptr(out), x.numel(), _stream()))
+    return out
+
+
+def colsum_v(u: torch.Tensor, want_v: bool = True, want_live: bool = True):
+    """(colsum [T,K], v [T,K] | None, live int32 [T,K] | None)."""
+    lib = _lib.load()
+    _need(u, torch.float32, "u")
+    T, n, K = u.shape
+    colsum = torch.empty(T, K, device=u.device, dtype=torch.float32)
+    v = torch.empty(T, K, device=u.device, dtype=torch.float32) if want_v else None
+    live = torch.empty(T, K, device=u.device, dtype=torch.int32) if want_live else None
+    check(lib.tclip_dirichlet_colsum_v(_ptr(u), _ptr(colsum), _ptr(v), _ptr(live), T, n, K, _stream()))
+    return colsum, v, live
+
+
+def moments(u, logz, colsum, support_sum=None, support_count=None) -> torch.Tensor:
+    lib = _lib.load()
+    _need(u, torch.float32, "u"), _need(logz, torch.float32, "logz"), _need(colsum, torch.float32, "colsum")
+    T, n, K = u.shape
+    D = logz.shape[2]
+    if support_sum is not None:
+        _need(support_sum, torch.float32, "support_sum"), _need(support_count, torch.float32, "support_count")
+    y = torch.empty(T, K, D, device=u.device, dtype=torch.float32)
+    check(lib.tclip_dirichlet_moments(_ptr(u), _ptr(logz), _ptr(colsum), _ptr(support_sum), _ptr(support_count),
+                                      _ptr(y), T, n, K, D, _stream()))
+    return y
+
+
+def support_stats(log_support: torch.Tensor, y_s: torch.Tensor, K: int):
+    lib = _lib.load()
+    _need(log_support, torch.float32, "log_support"), _need(y_s, torch.int64, "y_s")
+    T, S, D = log_support.shape
+    ssum = torch.empty(T, K, D, device=log_support.device, dtype=torch.float32)
+    scount = torch.empty(T, K, device=log_support.device, dtype=torch.float32)
+    check(lib.tclip_dirichlet_support_stats(_ptr(log_support), _ptr(y_s), _ptr(ssum), _ptr(scount), T, S, K, D,
+                                            _stream()))
+    return ssum, scount
+
+
+def mm_update_alpha(alpha0: torch.Tensor, y: torch.Tensor, iter_mm: int = 1000, check_every: int = 50,
+                    tol: float = 1e-11):
+    """The M-step on [..., D] rows.  Returns (alpha, iters_done int32 device tensor)."""
+    lib = _lib.load()
+    _need(alpha0, torch.float32, "alpha0"), _need(y, torch.float32, "y")
+    if alpha0.shape != y.shape:
+        raise ValueError("alpha0 and y must have the same shape")
+    D = alpha0.shape[-1]
+    rows = alpha0.numel() // D
+    out = torch.empty_like(alpha0)
+    nbytes = lib.tclip_dirichlet_mm_workspace_bytes(rows)
+    ws = torch.empty(nbytes, device=alpha0.device, dtype=torch.uint8)
+    iters = torch.zeros(1, device=alpha0.device, dtype=torch.int32)
+    check(lib.tclip_dirichlet_mm(_ptr(alpha0), _ptr(out), _ptr(y), rows, D, int(iter_mm), int(check_every), float(tol),
+                                 _ptr(iters), _ptr(ws), nbytes, _stream()))
+    return out, iters
+
+
+def commit(alpha: torch.Tensor, work: torch.Tensor, live: torch.Tensor | None):
+    """In place: alpha[row] <- work[row] on live rows.  Returns (criterion [1], task_criterion [T])."""
+    lib = _lib.load()
+    _need(alpha, torch.float32, "alpha"), _need(work, torch.float32, "work")
+    if live is not None:
+        _need(live, torch.int32, "live")
+    T, K, D = alpha.shape
+    rowstat = torch.empty(T * K * 2, device=alpha.device, dtype=torch.float64)
+    task_crit = torch.empty(T, device=alpha.device, dtype=torch.float32)
+    crit = torch.empty(1, device=alpha.device, dtype=torch.float32)
+    check(lib.tclip_dirichlet_commit(_ptr(alpha), _ptr(work), _ptr(live), _ptr(rowstat), _ptr(task_crit), _ptr(crit),
+                                     T, K, D, _stream()))
+    return crit, task_crit
+
+
+def estep(alpha: torch.Tensor, logz: torch.Tensor, v: torch.Tensor, lambd: float, hard: bool):
+    """(u [T,n,K], labels int32 [T,n])."""
+    lib = _lib.load()
+    _need(alpha, torch.float32, "alpha"), _need(logz, torch.float32, "logz"), _need(v, torch.float32, "v")
+    T, K, D = alpha.shape
+    n = logz.shape[1]
+    norm = torch.empty(T, K, device=alpha.device, dtype=torch.float64)
+    u = torch.empty(T, n, K, device=alpha.device, dtype=torch.float32)
+    labels = torch.empty(T, n, device=alpha.device, dtype=torch.int32)
+    check(lib.tclip_dirichlet_estep(_ptr(alpha), _ptr(logz), _ptr(v), float(lambd), _ptr(norm), _ptr(u), _ptr(labels),
+                                    T, n, K, D, int(bool(hard)), _stream()))
+    return u, labels
+
+
+def cluster_prototypes(labels: torch.Tensor, feats: torch.Tensor):
+    """Inputs of the label matching: dict(cluster_label, cluster_size, sample_cluster [T,n] int32,
+    n_clusters [T] int32, proto [T,n,D])."""
+    lib = _lib.load()
+    _need(labels, torch.int32, "labels"), _need(feats, torch.float32, "feats")
+    T, n, D = feats.shape
+    dev = feats.device
+    out = {
+        "cluster_label": torch.empty(T, n, device=dev, dtype=torch.int32),
+        "cluster_size": torch.empty(T, n, device=dev, dtype=torch.int32),
+        "sample_cluster": torch.empty(T, n, device=dev, dtype=torch.int32),
+        "n_clusters": torch.empty(T, device=dev, dtype=torch.int32),
+        "proto": torch.empty(T, n, D, device=dev, dtype=torch.float32),
+    }
+    check(lib.tclip_cluster_prototypes(_ptr(labels), _ptr(feats), _ptr(out["cluster_label"]), _ptr(out["cluster_size"]),
+                                       _ptr(out["sample_cluster"]), _ptr(out["n_clusters"]), _ptr(out["proto"]),
+                                       T, n, D, _stream()))
+    return out
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """One cached scratch buffer per device, grown on demand (a new method object is built per batch)."""
+    key = (device.type, device.index)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _WORKSPACES.pop(key, None)
+        ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lambd: float, hard: bool,
+                 x_s: torch.Tensor | None = None, y_s: torch.Tensor | None = None, check_every: int = 50,
+                 tol: float = 1e-11, mm_mode: int = TCLIP_MM_DENSE, record_events: bool = False) -> dict:
+    """The fused driver ``tclip_dirichlet_em_run``: the whole EM loop enqueued on the current stream.
+    Returns device tensors u, alpha, v, labels, criterions, mm_iters, n_live, mm_rows (+ ``events``)."""
+    lib = _lib.load()
+    _need(x_q, torch.float32, "x_q")
+    T, n, D = x_q.shape
+    K = int(n_class)
+    dev = x_q.device
+    S = 0
+    if x_s is not None:
+        _need(x_s, torch.float32, "x_s"), _need(y_s, torch.int64, "y_s")
+        S = x_s.shape[1]
+    if D != K:
+        raise ValueError("the Dirichlet methods need softmax features: feature dim must equal n_class")
+    out = {
+        "u": torch.empty(T, n, K, device=dev, dtype=torch.float32),
+        "alpha": torch.empty(T, K, D, device=dev, dtype=torch.float32),
+        "v": torch.empty(T, K, device=dev, dtype=torch.float32),
+        "labels": torch.zeros(T, n, device=dev, dtype=torch.int32),
+        "criterions": torch.zeros(max(iters, 1), device=dev, dtype=torch.float32)[:iters],
+        "mm_iters": torch.zeros(max(iters, 1), device=dev, dtype=torch.int32)[:iters],
+        "n_live": torch.zeros(max(iters, 1), device=dev, dtype=torch.int32)[:iters],
+        "mm_rows": torch.zeros(max(iters, 1), device=dev, dtype=torch.int64)[:iters],
+    }
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(iters)] if record_events else []
+    ev_arr = None
+    if events:
+        for e in events:  # torch creates the underlying cudaEvent_t lazily
+            e.record()
+        ev_arr = (ctypes.c_void_p * iters)(*[e.cuda_event for e in events])
+    p = DirichletProblem(
+        n_task=T, n_query=n, n_class=K, dim=D, n_support=S, iters=int(iters), iter_mm=int(iter_mm),
+        check_every=int(check_every), tol=float(tol), lambd=float(lambd), hard=int(bool(hard)), mm_mode=int(mm_mode),
+        x_q=_ptr(x_q), x_s=_ptr(x_s), y_s=_ptr(y_s), u=_ptr(out["u"]), alpha=_ptr(out["alpha"]), v=_ptr(out["v"]),
+        labels=_ptr(out["labels"]), criterions=_ptr(out["criterions"]), mm_iters=_ptr(out["mm_iters"]),
+        n_live=_ptr(out["n_live"]), mm_rows=_ptr(out["mm_rows"]),
+        iter_events=ctypes.cast(ev_arr, ctypes.POINTER(ctypes.c_void_p)) if ev_arr is not None else None)
+    nbytes = lib.tclip_dirichlet_em_workspace_bytes(ctypes.byref(p))
+    if nbytes == 0:
+        check(-1)
+    ws = _workspace(nbytes, dev)
+    check(lib.tclip_dirichlet_em_run(ctypes.byref(p), _ptr(ws), ws.numel(), _stream()))
+    out["events"] = events
+    return out

@@ -1,0 +1,91 @@
+"""Synthetic ``task_dic`` batches with the layout the reference's task generators produce.
+
+The reference builds a batch from cached CLIP features (``src/task_generator_zero_shot.py:49-65``,
+``src/task_generator_few_shot.py:83-99``): ``x_q`` float32 [T, n_query, F], ``y_q`` int64 [T, n_query, 1]
+(+ ``x_s`` [T, S, F], ``y_s`` [T, S, 1] for few-shot).  Neither CLIP weights nor the datasets exist offline,
+so benchmarks and parity tests use the calibrated generator of SURVEY.md §8(d):
+
+  text prototypes  txt = normalize(randn(K, E)),  E = 1024
+  per task         k_eff ~ U{3..10} (``src/sampler_zero_shot.py:54``); classes = randperm(K)[:k_eff]
+                   y = classes[randint(k_eff, n)];  img = normalize(txt[y] + s * randn(n, E) / sqrt(E)),  s = 9
+  softmax feature  z = softmax(T * img @ txt.T),  T = 30 (``src/utils.py:287-290``)
+
+Pure host code (torch CPU); everything is driven by one seeded ``torch.Generator``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+EMBED_DIM = 1024
+NOISE_SCALE = 9.0
+
+
+def text_prototypes(K: int, seed: int, embed_dim: int = EMBED_DIM) -> torch.Tensor:
+    """Unit-norm class prototypes [K, E]; a fixed function of (K, seed, E)."""
+    g = torch.Generator().manual_seed(int(seed) * 7919 + 13)
+    t = torch.randn(K, embed_dim, generator=g)
+    return t / t.norm(dim=-1, keepdim=True)
+
+
+def _embed(txt: torch.Tensor, labels: torch.Tensor, g: torch.Generator, noise: float) -> torch.Tensor:
+    e = txt.shape[1]
+    img = txt[labels] + noise * torch.randn(labels.shape[0], e, generator=g) / math.sqrt(e)
+    return img / img.norm(dim=-1, keepdim=True)
+
+
+def _features(img: torch.Tensor, txt: torch.Tensor, temperature: float, softmax_feature: bool) -> torch.Tensor:
+    if softmax_feature:
+        return (temperature * img @ txt.T).softmax(dim=-1)
+    return img
+
+
+def make_zero_shot_batch(n_task: int, K: int, n_query: int = 75, seed: int = 0, temperature: float = 30.0,
+                         softmax_feature: bool = True, noise: float = NOISE_SCALE, embed_dim: int = EMBED_DIM,
+                         k_eff_range: tuple[int, int] = (3, 10), batch_index: int = 0):
+    """One ``run_task`` batch.  Returns (task_dic, txt) — txt is what the stub text model returns."""
+    txt = text_prototypes(K, seed, embed_dim)
+    g = torch.Generator().manual_seed(int(seed) * 1000003 + int(batch_index) * 101 + 1)
+    xs, ys = [], []
+    lo, hi = k_eff_range
+    hi = min(hi, K)
+    lo = min(lo, hi)
+    for _ in range(n_task):
+        k_eff = int(torch.randint(lo, hi + 1, (1,), generator=g))
+        classes = torch.randperm(K, generator=g)[:k_eff]
+        y = classes[torch.randint(0, k_eff, (n_query,), generator=g)]
+        img = _embed(txt, y, g, noise)
+        xs.append(_features(img, txt, temperature, softmax_feature))
+        ys.append(y)
+    task_dic = {"x_q": torch.stack(xs).float().contiguous(),
+                "y_q": torch.stack(ys).long().unsqueeze(-1).contiguous()}
+    return task_dic, txt
+
+
+def make_few_shot_batch(n_task: int, K: int, shots: int, n_query: int = 75, k_eff: int = 5, seed: int = 0,
+                        temperature: float = 30.0, softmax_feature: bool = True, noise: float = NOISE_SCALE,
+                        embed_dim: int = EMBED_DIM, batch_index: int = 0):
+    """Few-shot batch: ``shots`` support samples of *every* class (``src/sampler_few_shot.py:64-76``), the
+    query drawn from ``k_eff`` classes (``config/main_config.yaml:7``).  S = K * shots."""
+    txt = text_prototypes(K, seed, embed_dim)
+    g = torch.Generator().manual_seed(int(seed) * 1000003 + int(batch_index) * 101 + 2)
+    xq, yq, xsup, ysup = [], [], [], []
+    for _ in range(n_task):
+        classes = torch.randperm(K, generator=g)[:min(k_eff, K)]
+        y = classes[torch.randint(0, classes.numel(), (n_query,), generator=g)]
+        xq.append(_features(_embed(txt, y, g, noise), txt, temperature, softmax_feature))
+        yq.append(y)
+        ys = torch.arange(K).repeat_interleave(shots)
+        ys = ys[torch.randperm(ys.numel(), generator=g)]
+        xsup.append(_features(_embed(txt, ys, g, noise), txt, temperature, softmax_feature))
+        ysup.append(ys)
+    task_dic = {"x_q": torch.stack(xq).float().contiguous(), "y_q": torch.stack(yq).long().unsqueeze(-1).contiguous(),
+                "x_s": torch.stack(xsup).float().contiguous(), "y_s": torch.stack(ysup).long().unsqueeze(-1).contiguous()}
+    return task_dic, txt
+
+
+def shard_batches(n_batches: int, rank: int, world_size: int) -> list[int]:
+    """Whole ``run_task`` batches are the unit of sharding (the MM break test is batch-global,
+    ``src/methods/zero_shot/em_dirichlet.py:169-175``): batch i goes to rank i mod W."""
+    return [i for i in range(n_batches) if i % world_size == rank]
