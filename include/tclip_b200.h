@@ -37,6 +37,13 @@ int tclip_version(void);                 /* 100 * major + minor */
 const char* tclip_last_error(void);      /* message of the last failing call on this thread ("" if none) */
 int tclip_device_check(int device);      /* TCLIP_OK iff `device` is compute capability 10.x (B200) */
 int tclip_mm_max_dim(void);              /* largest D the M-step kernel supports (1024) */
+long long tclip_launch_count(void);      /* kernels launched by this library in this process so far */
+
+/* Roofline denominators for the M-step (it is FP32/MUFU issue bound, not HBM or tensor bound): launches a
+ * register-only microbenchmark, which = 0: dependent FFMA chains (*ops_out = flop executed), which = 1: MUFU
+ * rcp/sqrt/lg2 chains (*ops_out = MUFU operations).  Time it with events on `stream`.  sink: >= 4 bytes of device
+ * memory (never written in practice).  No reference counterpart (measurement only). */
+int tclip_probe_issue_rate(int which, float* sink, int n_blocks, int iters, double* ops_out, void* stream);
 
 /* ---- stage entry points ------------------------------------------------------------------------------------- */
 
@@ -117,6 +124,7 @@ typedef struct tclip_dirichlet_problem {
   int* n_live;                       /* out [iters] non-empty clusters per outer iteration (all tasks) */
   long long* mm_rows;                /* out [iters] rows actually iterated x iterations (work done), may be NULL */
   void* const* iter_events;          /* optional [iters] cudaEvent_t recorded after each outer iteration */
+  void* const* mm_events;            /* optional [2*iters] cudaEvent_t recorded before / after each M-step */
 } tclip_dirichlet_problem;
 
 /* Runs zero_shot/em_dirichlet.py:195-244 (hard: zero_shot/hard_em_dirichlet.py:215-269) or, with n_support > 0,

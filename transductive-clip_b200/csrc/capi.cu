@@ -12,6 +12,10 @@
 #include "../../include/tclip_b200.h"
 #include "tclip_kernels.cuh"
 
+namespace tclip {
+std::atomic<long long> g_launches{0};
+}
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -261,6 +265,23 @@ const char* tclip_last_error(void) { return g_last_error.c_str(); }
 
 int tclip_mm_max_dim(void) { return tclip::mm_max_dim(); }
 
+long long tclip_launch_count(void) { return tclip::g_launches.load(std::memory_order_relaxed); }
+
+int tclip_probe_issue_rate(int which, float* sink, int n_blocks, int iters, double* ops_out, void* stream) {
+  if (!sink || n_blocks < 1 || iters < 1 || (which != 0 && which != 1))
+    return fail(TCLIP_ERR_INVALID, "tclip_probe_issue_rate: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  const double per_cta = 256.0 * 8.0 * 64.0 * (double)iters;  // threads x chains x unroll x iters (probe.cu)
+  if (which == 0) {
+    TCLIP_CUDA(tclip::probe_ffma(sink, n_blocks, iters, (cudaStream_t)stream));
+    if (ops_out) *ops_out = 2.0 * per_cta * n_blocks;  // flop
+  } else {
+    TCLIP_CUDA(tclip::probe_mufu(sink, n_blocks, iters, (cudaStream_t)stream));
+    if (ops_out) *ops_out = per_cta * n_blocks;  // MUFU operations
+  }
+  return TCLIP_OK;
+}
+
 int tclip_device_check(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -399,6 +420,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
   TCLIP_CUDA(cudaMemsetAsync(p->v, 0, sizeof(float) * (size_t)rows, st));
   TCLIP_CUDA(cudaMemcpyAsync(p->u, p->x_q, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
   fill_kernel<<<(unsigned)(((long)rows * D + 255) / 256), 256, 0, st>>>(p->alpha, 1.0f, (long)rows * D);
+  tclip::note_launch();
   TCLIP_CUDA(tclip::log_features(p->x_q, w.logz, (long)T * n * D, st));
   if (few) {
     TCLIP_CUDA(tclip::log_features(p->x_s, w.log_support, (long)T * S * D, st));
@@ -406,6 +428,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
   }
   if (skip) {
     zero_int_kernel<<<(rows + 255) / 256, 256, 0, st>>>(w.cache_valid, rows);
+    tclip::note_launch();
     TCLIP_CUDA(cudaMemsetAsync(w.state_free, 0, sizeof(tclip::MMState), st));
   }
 
@@ -414,6 +437,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     TCLIP_CUDA(tclip::colsum_v(p->u, w.colsum, p->v, few ? nullptr : w.live, T, n, K, st));
     TCLIP_CUDA(tclip::moments(p->u, w.logz, w.colsum, w.support_sum, w.support_count, w.y, T, n, K, D, st));
 
+    if (p->mm_events && p->mm_events[2 * it]) TCLIP_CUDA(cudaEventRecord((cudaEvent_t)p->mm_events[2 * it], st));
     tclip::MMLaunch l{};
     l.alpha_in = p->alpha;
     l.alpha_out = w.work;
@@ -427,6 +451,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nullptr, st));
     } else {
       classify_rows_kernel<<<1, 1024, 0, st>>>(w.live, w.cache_valid, w.list_live, w.list_new, w.counts, rows);
+      tclip::note_launch();
       // newly dead rows: full trajectory from their kept row with y = -10, criterion terms cached per check
       tclip::MMLaunch d = l;
       d.row_list = w.list_new;
@@ -437,20 +462,27 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       d.row_cache = w.cache;
       d.n_checks = nc;
       TCLIP_CUDA(tclip::mm_run(d, p->iter_mm, p->check_every, p->tol, nullptr, st));
-      if (nc > 0) sum_cache_kernel<<<nc, 256, 0, st>>>(w.live, w.cache, w.extra, rows, nc);
+      if (nc > 0) {
+        sum_cache_kernel<<<nc, 256, 0, st>>>(w.live, w.cache, w.extra, rows, nc);
+        tclip::note_launch();
+      }
       l.row_list = w.list_live;
       l.n_rows_dev = w.counts;
       l.n_rows = rows;
       l.n_blocks = tclip::mm_num_blocks(rows);
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nc > 0 ? w.extra : nullptr, st));
     }
+    if (p->mm_events && p->mm_events[2 * it + 1])
+      TCLIP_CUDA(cudaEventRecord((cudaEvent_t)p->mm_events[2 * it + 1], st));
     int* n_live_dev = nullptr;
     if (!few) {
       count_live_kernel<<<1, 256, 0, st>>>(w.live, rows, p->n_live + it);
+      tclip::note_launch();
       n_live_dev = p->n_live + it;
     }
     record_work_kernel<<<1, 1, 0, st>>>(w.state, skip ? w.counts : nullptr, n_live_dev, rows, p->iter_mm,
                                          p->mm_iters + it, p->n_live + it, p->mm_rows ? p->mm_rows + it : nullptr);
+    tclip::note_launch();
     // empty clusters keep their previous row; logged criterion (em_dirichlet.py:224-226,236-238)
     TCLIP_CUDA(tclip::commit(p->alpha, w.work, few ? nullptr : w.live, w.rowstat, w.task_crit, p->criterions + it, T,
                              K, D, st));

@@ -420,11 +420,13 @@ __global__ void prototypes_kernel(const float* __restrict__ feats, const int* __
 cudaError_t log_features(const float* x, float* out, long count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   log_features_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(x, out, count);
+  note_launch(1);
   return cudaGetLastError();
 }
 
 cudaError_t colsum_v(const float* u, float* colsum, float* v, int* live, int T, int n, int K, cudaStream_t st) {
   colsum_v_kernel<<<dim3((K + 127) / 128, T), 128, 0, st>>>(u, colsum, v, live, n, K);
+  note_launch(1);
   return cudaGetLastError();
 }
 
@@ -433,12 +435,14 @@ cudaError_t moments(const float* u, const float* logz, const float* colsum, cons
   const int few = support_sum != nullptr;
   moments_kernel<<<dim3((D + kMomTile - 1) / kMomTile, (K + kMomTile - 1) / kMomTile, T), 256, 0, st>>>(
       u, logz, colsum, support_sum, support_count, y, n, K, D, few);
+  note_launch(1);
   return cudaGetLastError();
 }
 
 cudaError_t support_stats(const float* log_support, const long long* y_s, float* support_sum, float* support_count,
                           int T, int S, int K, int D, cudaStream_t st) {
   support_stats_kernel<<<dim3(K, T), 256, 0, st>>>(log_support, y_s, support_sum, support_count, S, K, D);
+  note_launch(1);
   return cudaGetLastError();
 }
 
@@ -447,6 +451,7 @@ cudaError_t commit(float* alpha, const float* work, const int* live, double2* ro
   const int rows = T * K;
   commit_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, work, live, rowstat, rows, D);
   criterion_kernel<<<1, 256, 0, st>>>(rowstat, task_crit, crit_out, T, K);
+  note_launch(2);
   return cudaGetLastError();
 }
 
@@ -458,6 +463,7 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
                                                                                                   K, D);
   const int qrows = T * n;
   softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(u, norm, v, lambd, u, labels, qrows, n, K, hard);
+  note_launch(3);
   return cudaGetLastError();
 }
 
@@ -468,6 +474,7 @@ cudaError_t cluster_prototypes(const int* labels, const float* feats, int* clust
   cluster_order_kernel<<<T, 128, 3 * n * sizeof(int), st>>>(labels, cluster_label, cluster_size, sample_cluster,
                                                             n_clusters, n);
   prototypes_kernel<<<dim3(n, T), 256, 0, st>>>(feats, sample_cluster, cluster_size, n_clusters, proto, n, D);
+  note_launch(2);
   return cudaGetLastError();
 }
 

@@ -207,6 +207,7 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
   const int ng = (p.D + 31) / 32;
   const ChunkFn fn = table[ng - 1];
   mm_reset_kernel<<<1, 1, 0, st>>>(p.state);
+  note_launch();
   const float* first_in = p.alpha_in;
   int start = 0, check_idx = 0;
   while (start < iter_mm) {
@@ -228,6 +229,7 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
     const double2* extra = (has_check && extra_checks) ? extra_checks + check_idx : nullptr;
     mm_decide_kernel<<<1, 256, 0, st>>>(p.partials, p.n_blocks, extra, free_run ? 0 : has_check, end + 1, tol,
                                         p.state);
+    note_launch(2);
     if (has_check) ++check_idx;
     start = end + 1;
   }

@@ -3,7 +3,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 namespace tclip {
+
+// kernels launched by this library in this process (tclip_launch_count); bumped by every launcher
+extern std::atomic<long long> g_launches;
+inline void note_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- Dirichlet MM M-step (dirichlet_mm.cu) --------------------------------------------------------------------
 constexpr int kMMThreads = 128;    // 4 warps = 4 rows per CTA
@@ -51,5 +57,9 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
 cudaError_t cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
                                int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
                                cudaStream_t st);
+
+// ---- issue-rate microbenchmarks used as roofline denominators (probe.cu) ------------------------------------------
+cudaError_t probe_ffma(float* sink, int n_blocks, int iters, cudaStream_t st);   // 2 * 8 * 256 * iters * 64 flop / CTA... see probe.cu
+cudaError_t probe_mufu(float* sink, int n_blocks, int iters, cudaStream_t st);
 
 }  // namespace tclip

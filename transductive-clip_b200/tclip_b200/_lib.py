@@ -42,6 +42,7 @@ class DirichletProblem(ctypes.Structure):
         ("u", c_void_p), ("alpha", c_void_p), ("v", c_void_p), ("labels", c_void_p),
         ("criterions", c_void_p), ("mm_iters", c_void_p), ("n_live", c_void_p), ("mm_rows", c_void_p),
         ("iter_events", POINTER(c_void_p)),
+        ("mm_events", POINTER(c_void_p)),
     ]
 
 
@@ -51,6 +52,8 @@ SIGNATURES = {
     "tclip_last_error": (c_char_p, []),
     "tclip_device_check": (c_int, [c_int]),
     "tclip_mm_max_dim": (c_int, []),
+    "tclip_launch_count": (c_longlong, []),
+    "tclip_probe_issue_rate": (c_int, [c_int, c_void_p, c_int, c_int, POINTER(ctypes.c_double), c_void_p]),
     "tclip_log_features": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "tclip_dirichlet_colsum_v": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tclip_dirichlet_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -121,6 +121,7 @@ class _DirichletBase(object):
         self.u, self.alpha, self.v, self.labels = res["u"], res["alpha"], res["v"], res["labels"]
         self.mm_iters, self.n_live, self.mm_rows = res["mm_iters"], res["n_live"], res["mm_rows"]
         self._em_events = (start, res["events"])
+        self._mm_events = res["mm_events"]
         crit = res["criterions"]
         if self.hard and self.few_shot:
             crit = torch.zeros_like(crit)  # few_shot/hard_em_dirichlet.py:234-244 logs a criterion that is always 0

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import DirichletProblem, TCLIP_MM_DENSE, TCLIP_MM_SKIP_DEAD, check
 
 __all__ = ["log_features", "colsum_v", "moments", "support_stats", "mm_update_alpha", "commit", "estep",
-           "cluster_prototypes", "dirichlet_em", "device_check", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
+           "cluster_prototypes", "dirichlet_em", "device_check", "launch_count", "probe_issue_rate", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -190,22 +190,47 @@ def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lamb
         "mm_rows": torch.zeros(max(iters, 1), device=dev, dtype=torch.int64)[:iters],
     }
     events = [torch.cuda.Event(enable_timing=True) for _ in range(iters)] if record_events else []
-    ev_arr = None
+    mm_events = [torch.cuda.Event(enable_timing=True) for _ in range(2 * iters)] if record_events else []
+    ev_arr = mm_arr = None
     if events:
-        for e in events:  # torch creates the underlying cudaEvent_t lazily
+        for e in events + mm_events:  # torch creates the underlying cudaEvent_t lazily
             e.record()
         ev_arr = (ctypes.c_void_p * iters)(*[e.cuda_event for e in events])
+        mm_arr = (ctypes.c_void_p * (2 * iters))(*[e.cuda_event for e in mm_events])
     p = DirichletProblem(
         n_task=T, n_query=n, n_class=K, dim=D, n_support=S, iters=int(iters), iter_mm=int(iter_mm),
         check_every=int(check_every), tol=float(tol), lambd=float(lambd), hard=int(bool(hard)), mm_mode=int(mm_mode),
         x_q=_ptr(x_q), x_s=_ptr(x_s), y_s=_ptr(y_s), u=_ptr(out["u"]), alpha=_ptr(out["alpha"]), v=_ptr(out["v"]),
         labels=_ptr(out["labels"]), criterions=_ptr(out["criterions"]), mm_iters=_ptr(out["mm_iters"]),
         n_live=_ptr(out["n_live"]), mm_rows=_ptr(out["mm_rows"]),
-        iter_events=ctypes.cast(ev_arr, ctypes.POINTER(ctypes.c_void_p)) if ev_arr is not None else None)
+        iter_events=ctypes.cast(ev_arr, ctypes.POINTER(ctypes.c_void_p)) if ev_arr is not None else None,
+        mm_events=ctypes.cast(mm_arr, ctypes.POINTER(ctypes.c_void_p)) if mm_arr is not None else None)
     nbytes = lib.tclip_dirichlet_em_workspace_bytes(ctypes.byref(p))
     if nbytes == 0:
         check(-1)
     ws = _workspace(nbytes, dev)
     check(lib.tclip_dirichlet_em_run(ctypes.byref(p), _ptr(ws), ws.numel(), _stream()))
     out["events"] = events
+    out["mm_events"] = mm_events
     return out
+
+
+def launch_count() -> int:
+    """Kernels launched by libtclip_b200 in this process so far."""
+    return int(_lib.load().tclip_launch_count())
+
+
+def probe_issue_rate(which: str, n_blocks: int, iters: int, device=None) -> tuple[float, float]:
+    """Run the register-only FFMA (``"ffma"``) or MUFU (``"mufu"``) microbenchmark once on the current stream.
+    Returns (operations executed, milliseconds)."""
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    sink = torch.zeros(4, device=dev, dtype=torch.float32)
+    ops_out = ctypes.c_double(0.0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(lib.tclip_probe_issue_rate(0 if which == "ffma" else 1, _ptr(sink), int(n_blocks), int(iters),
+                                     ctypes.byref(ops_out), _stream()))
+    e1.record()
+    e1.synchronize()
+    return ops_out.value, e0.elapsed_time(e1)
