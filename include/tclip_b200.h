@@ -41,7 +41,8 @@ long long tclip_launch_count(void);      /* kernels launched by this library in 
 
 /* Roofline denominators for the M-step (it is FP32/MUFU issue bound, not HBM or tensor bound): launches a
  * register-only microbenchmark, which = 0: dependent FFMA chains (*ops_out = flop executed), which = 1: MUFU
- * rcp/sqrt/lg2 chains (*ops_out = MUFU operations).  Time it with events on `stream`.  sink: >= 4 bytes of device
+ * rcp/sqrt/lg2 chains (*ops_out = MUFU operations), which = 2: packed FFMA2 chains (*ops_out = flop), which = 3: the
+ * M-step's mix, 4 FFMA2 : 1 MUFU (*ops_out = FFMA2 thread-instructions).  Time it with events on `stream`.  sink: >= 4 bytes of device
  * memory (never written in practice).  No reference counterpart (measurement only). */
 int tclip_probe_issue_rate(int which, float* sink, int n_blocks, int iters, double* ops_out, void* stream);
 

@@ -1,0 +1,86 @@
+"""CPU: the M-step's special-function arithmetic (csrc/tclip_math.cuh compiled as plain C++ by
+tests/build_host_shim.sh) against SciPy in float64, and the host twin of the MM inner loop against the oracle."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+from scipy import special
+
+from oracle import restated as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHIM = os.path.join(HERE, "_build", "libtclip_host_math.so")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    if not os.path.isfile(SHIM):
+        subprocess.run(["bash", os.path.join(HERE, "build_host_shim.sh")], check=True)
+    lib = ctypes.CDLL(SHIM)
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    lib.tclip_host_psi1_N.argtypes = [f32p, f32p, f32p, ctypes.c_int]
+    lib.tclip_host_mm_update.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
+    lib.tclip_host_digamma.argtypes = [ctypes.c_double]
+    lib.tclip_host_digamma.restype = ctypes.c_double
+    lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return lib
+
+
+def _grid():
+    return np.concatenate([np.logspace(-12, -1, 200), np.linspace(0.05, 0.08, 50), np.logspace(-1, 6, 600)]).astype(np.float32)
+
+
+def test_psi_and_curvature_numerator(shim):
+    a = _grid()
+    psi1, N = np.empty_like(a), np.empty_like(a)
+    shim.tclip_host_psi1_N(a, psi1, N, a.size)
+    a64 = a.astype(np.float64)
+    psi_ref = special.digamma(a64 + 1)
+    n_ref = a64 * psi_ref - special.gammaln(a64 + 1)
+    # below ~1e-3 the float64 difference above cancels catastrophically: use the Taylor series
+    # N(a) = sum_{k>=2} (-1)^k zeta(k) (1 - 1/k) a^k as the yard-stick there
+    small = a64 < 1e-3
+    n_ref[small] = sum((-1) ** k * special.zeta(k) * (1 - 1 / k) * a64[small] ** k for k in range(2, 9))
+    assert np.max(np.abs(psi1 - psi_ref) / np.maximum(np.abs(psi_ref), 1.0)) < 1e-6
+    # N = a psi(a+1) - lnGamma(a+1) >= 0, ~ a^2 pi^2/12 for small a, ~ a for large a
+    assert np.max(np.abs(N - n_ref) / n_ref) < 2e-4   # worst just above the Taylor/Stirling switch at a = 1/16
+    assert np.max(np.abs(N - n_ref)[a > 1] / n_ref[a > 1]) < 2e-6
+
+
+def test_digamma_f64(shim):
+    for s in (1e-3, 0.5, 1.0, 9.99, 10.0, 123.4, 1e5, 3e8):
+        assert abs(shim.tclip_host_digamma(s) - special.digamma(s)) <= 1e-12 * max(1.0, abs(special.digamma(s)))
+
+
+def test_one_mm_update_matches_the_reference_formula(shim):
+    """a_new = (-b + sqrt(b^2 + 4c)) / (2c) in float64 with torch's special functions (em_dirichlet.py:153-167)."""
+    g = np.random.default_rng(0)
+    a = _grid()
+    a = a[(a >= 1e-3) | (a <= 1e-11)]   # in between the float64 evaluation of c below cancels; covered by the N test
+    y = -g.uniform(0.5, 12.0, a.size).astype(np.float32)
+    s = 37.5
+    out = np.empty_like(a)
+    shim.tclip_host_mm_update(a, y, out, a.size, float(special.digamma(s)))
+    a64, y64 = torch.from_numpy(a).double(), torch.from_numpy(y).double()
+    psi1 = torch.polygamma(0, a64 + 1)
+    c = torch.where(a64 > 1e-11, (2 * (-torch.lgamma(a64 + 1) + psi1 * a64) / a64 ** 2).abs(),
+                    torch.polygamma(1, torch.ones(1, dtype=torch.float64)))
+    b = psi1 - special.digamma(s) - c * a64 - y64
+    ref = ((-b + torch.sqrt(b * b + 4 * c)) / (2 * c)).numpy()
+    assert np.max(np.abs(out - ref) / ref) < 3e-6
+
+
+def test_mm_rows_track_the_oracle(shim):
+    g = torch.Generator().manual_seed(3)
+    rows, D, iters = 6, 40, 120
+    y = torch.log(torch.softmax(2 * torch.randn(rows, 6, D, generator=g), -1)).mean(1).contiguous()
+    a = np.ones((rows, D), dtype=np.float32)
+    shim.tclip_host_mm_rows(a, y.numpy(), rows, D, iters)
+    ref, done = R.mm_update_alpha(torch.ones(rows, D, dtype=torch.float64), y.double(), iters, check_every=0 or 10 ** 9)
+    assert done == iters
+    assert np.max(np.abs(a - ref.numpy()) / ref.numpy()) < 2e-5

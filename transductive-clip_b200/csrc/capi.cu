@@ -268,16 +268,22 @@ int tclip_mm_max_dim(void) { return tclip::mm_max_dim(); }
 long long tclip_launch_count(void) { return tclip::g_launches.load(std::memory_order_relaxed); }
 
 int tclip_probe_issue_rate(int which, float* sink, int n_blocks, int iters, double* ops_out, void* stream) {
-  if (!sink || n_blocks < 1 || iters < 1 || (which != 0 && which != 1))
+  if (!sink || n_blocks < 1 || iters < 1 || which < 0 || which > 3)
     return fail(TCLIP_ERR_INVALID, "tclip_probe_issue_rate: bad arguments");
   if (int rc = current_device_ok()) return rc;
   const double per_cta = 256.0 * 8.0 * 64.0 * (double)iters;  // threads x chains x unroll x iters (probe.cu)
   if (which == 0) {
     TCLIP_CUDA(tclip::probe_ffma(sink, n_blocks, iters, (cudaStream_t)stream));
     if (ops_out) *ops_out = 2.0 * per_cta * n_blocks;  // flop
-  } else {
+  } else if (which == 1) {
     TCLIP_CUDA(tclip::probe_mufu(sink, n_blocks, iters, (cudaStream_t)stream));
     if (ops_out) *ops_out = per_cta * n_blocks;  // MUFU operations
+  } else if (which == 2) {
+    TCLIP_CUDA(tclip::probe_ffma2(sink, n_blocks, iters, (cudaStream_t)stream));
+    if (ops_out) *ops_out = 4.0 * per_cta * n_blocks;  // flop (2 lanes x 2)
+  } else {
+    TCLIP_CUDA(tclip::probe_mix(sink, n_blocks, iters, (cudaStream_t)stream));
+    if (ops_out) *ops_out = per_cta * n_blocks;  // FFMA2 instructions per thread-chain (+ 1/4 as many MUFU)
   }
   return TCLIP_OK;
 }

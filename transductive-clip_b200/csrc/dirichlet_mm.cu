@@ -32,23 +32,25 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   return v;
 }
 
-// Sum of the NG register slots of one lane as a balanced tree (fp32), last slot masked by `tail_ok`.
-template <int NG>
-__device__ __forceinline__ float lane_tree_sum(const float (&a)[NG], bool tail_ok) {
-  float t[NG];
+// Sum of the NP register pairs of one lane as a balanced tree of packed adds (fp32).
+template <int NP>
+__device__ __forceinline__ float lane_tree_sum(const float2 (&a)[NP], float2 tail_mask) {
+  float2 t[NP];
 #pragma unroll
-  for (int g = 0; g < NG; ++g) t[g] = a[g];
-  t[NG - 1] = tail_ok ? t[NG - 1] : 0.0f;
+  for (int j = 0; j < NP; ++j) t[j] = a[j];
+  t[NP - 1] = f2mul(t[NP - 1], tail_mask);
 #pragma unroll
-  for (int w = 1; w < NG; w <<= 1) {
+  for (int w = 1; w < NP; w <<= 1) {
 #pragma unroll
-    for (int g = 0; g + w < NG; g += 2 * w) t[g] += t[g + w];
+    for (int j = 0; j + w < NP; j += 2 * w) t[j] = f2add(t[j], t[j + w]);
   }
-  return t[0];
+  return t[0].x + t[0].y;
 }
 
-// NG = ceil(D / 32) register slots per lane; only the last slot can be partially populated.
-template <int NG>
+// NP = ceil(D / 64) register pairs per lane: pair j holds elements d = (2j) * 32 + lane and (2j + 1) * 32 + lane, so
+// every global access is a coalesced 128-byte row segment.  Only the last pair can hold padding (masked in the sums).
+// All add / mul / fma work is issued as packed FFMA2 / FMUL2 / FADD2 (tclip_math.cuh: mm_update_pair).
+template <int NP>
 __global__ void __launch_bounds__(kMMThreads)
 mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict__ y,
                 const int* __restrict__ row_list, const int* __restrict__ n_rows_dev, int n_rows_host, int D,
@@ -68,46 +70,57 @@ mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict
     const float* ain = alpha_in + row * D;
     const float* yin = y + row * D;
     float* aout = alpha_out + row * D;
-    const bool tail_ok = (NG - 1) * 32 + lane < D;
+    const int dx = (2 * NP - 2) * 32 + lane, dy = (2 * NP - 1) * 32 + lane;  // elements of the last pair
+    const bool ok_x = dx < D, ok_y = dy < D;
+    const float2 tail_mask = make_float2(ok_x ? 1.0f : 0.0f, ok_y ? 1.0f : 0.0f);
 
-    float a[NG], yy[NG];
+    float2 a[NP], ny[NP];
 #pragma unroll
-    for (int g = 0; g < NG - 1; ++g) {
-      a[g] = ain[g * 32 + lane];
-      yy[g] = __ldg(yin + g * 32 + lane);
+    for (int j = 0; j < NP - 1; ++j) {
+      a[j] = make_float2(ain[(2 * j) * 32 + lane], ain[(2 * j + 1) * 32 + lane]);
+      ny[j] = make_float2(-__ldg(yin + (2 * j) * 32 + lane), -__ldg(yin + (2 * j + 1) * 32 + lane));
     }
-    a[NG - 1] = tail_ok ? ain[(NG - 1) * 32 + lane] : 1.0f;   // padding lanes iterate on a harmless dummy
-    yy[NG - 1] = tail_ok ? __ldg(yin + (NG - 1) * 32 + lane) : -1.0f;
+    // padding lanes iterate on a harmless dummy (a = 1, y = -1)
+    a[NP - 1] = make_float2(ok_x ? ain[dx] : 1.0f, ok_y ? ain[dy] : 1.0f);
+    ny[NP - 1] = make_float2(ok_x ? -__ldg(yin + dx) : 1.0f, ok_y ? -__ldg(yin + dy) : 1.0f);
 
-    double s = warp_sum_f64((double)lane_tree_sum<NG>(a, tail_ok));
+    double s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     for (int it = 0; it < n_iters - 1; ++it) {
       const double ps = digamma_f64(s);
       const float hi = (float)ps;
       const float lo = (float)(ps - (double)hi);
 #pragma unroll
-      for (int g = 0; g < NG; ++g) a[g] = mm_update_element(a[g], yy[g], hi, lo);
-      s = warp_sum_f64((double)lane_tree_sum<NG>(a, tail_ok));
+      for (int j = 0; j < NP; ++j) a[j] = mm_update_pair(a[j], ny[j], hi, lo);
+      s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     }
     {  // last iteration of the chunk: also the one the criterion is evaluated on
       const double ps = digamma_f64(s);
       const float hi = (float)ps;
       const float lo = (float)(ps - (double)hi);
-      float d2 = 0.0f, a2 = 0.0f;
+      float2 d2 = make_float2(0.0f, 0.0f), a2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const float an = mm_update_element(a[g], yy[g], hi, lo);
-        const bool ok = (g < NG - 1) || tail_ok;
-        const float df = an - a[g];
-        d2 = ok ? fmaf(df, df, d2) : d2;
-        a2 = ok ? fmaf(a[g], a[g], a2) : a2;
-        a[g] = an;
+      for (int j = 0; j < NP; ++j) {
+        const float2 an = mm_update_pair(a[j], ny[j], hi, lo);
+        float2 df = f2add(an, make_float2(-a[j].x, -a[j].y));
+        float2 ao = a[j];
+        if (j == NP - 1) {
+          df = f2mul(df, tail_mask);
+          ao = f2mul(ao, tail_mask);
+        }
+        d2 = f2fma(df, df, d2);
+        a2 = f2fma(ao, ao, a2);
+        a[j] = an;
       }
-      dsq = (double)d2;
-      asq = (double)a2;
+      dsq = (double)(d2.x + d2.y);
+      asq = (double)(a2.x + a2.y);
     }
 #pragma unroll
-    for (int g = 0; g < NG - 1; ++g) aout[g * 32 + lane] = a[g];
-    if (tail_ok) aout[(NG - 1) * 32 + lane] = a[NG - 1];
+    for (int j = 0; j < NP - 1; ++j) {
+      aout[(2 * j) * 32 + lane] = a[j].x;
+      aout[(2 * j + 1) * 32 + lane] = a[j].y;
+    }
+    if (ok_x) aout[dx] = a[NP - 1].x;
+    if (ok_y) aout[dy] = a[NP - 1].y;
   }
 
   if (emit_check == 2) {  // free-running rows: each row keeps its own terms
@@ -180,9 +193,9 @@ __global__ void mm_reset_kernel(MMState* state) {
   state->last_den = 0.0;
 }
 
-template <int NG>
+template <int NP>
 void launch_chunk(const MMLaunch& p, int n_iters, int emit_check, int check_idx, cudaStream_t st) {
-  mm_chunk_kernel<NG><<<p.n_blocks, kMMThreads, 0, st>>>(p.alpha_in, p.alpha_out, p.y, p.row_list, p.n_rows_dev,
+  mm_chunk_kernel<NP><<<p.n_blocks, kMMThreads, 0, st>>>(p.alpha_in, p.alpha_out, p.y, p.row_list, p.n_rows_dev,
                                                          p.n_rows, p.D, n_iters, emit_check, p.partials, p.state,
                                                          p.row_cache, p.n_checks, check_idx);
 }
@@ -202,10 +215,10 @@ int mm_num_blocks(int n_rows) { return (n_rows + (kMMThreads / 32) - 1) / (kMMTh
 
 // Enqueue one full M-step (<= iter_mm MM iterations with the batch-global early exit) on `st`.
 cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const double2* extra_checks, cudaStream_t st) {
-  static constexpr auto table = make_table(std::make_integer_sequence<int, kMMMaxSlots>{});
+  static constexpr auto table = make_table(std::make_integer_sequence<int, kMMMaxSlots / 2>{});
   if (p.D < 1 || p.D > mm_max_dim()) return cudaErrorInvalidValue;
-  const int ng = (p.D + 31) / 32;
-  const ChunkFn fn = table[ng - 1];
+  const int np = (p.D + 63) / 64;
+  const ChunkFn fn = table[np - 1];
   mm_reset_kernel<<<1, 1, 0, st>>>(p.state);
   note_launch();
   const float* first_in = p.alpha_in;

@@ -54,7 +54,67 @@ __global__ void __launch_bounds__(kProbeThreads) probe_mufu_kernel(float* sink, 
   if (s == 123.456f) sink[0] = s;
 }
 
+// packed FFMA2: flop per CTA = 2 * 2 * kProbeThreads * kProbeChains * kProbeUnroll * iters
+__global__ void __launch_bounds__(kProbeThreads) probe_ffma2_kernel(float* sink, int iters) {
+  float2 x[kProbeChains];
+#pragma unroll
+  for (int c = 0; c < kProbeChains; ++c) x[c] = make_float2(1.0f + 1e-3f * (float)(threadIdx.x + c), 1.0f);
+  const float2 m = make_float2(0.999f + 1e-9f * (float)blockIdx.x, 0.9999f), a = make_float2(1e-3f, 1e-4f);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < kProbeUnroll; ++k)
+#pragma unroll
+      for (int c = 0; c < kProbeChains; ++c) x[c] = __ffma2_rn(x[c], m, a);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int c = 0; c < kProbeChains; ++c) s += x[c].x + x[c].y;
+  if (s == 123.456f) sink[0] = s;
+}
+
+// the M-step's own mix: per trip 4 FFMA2 + 1 MUFU per chain, to see whether the two pipes overlap
+__global__ void __launch_bounds__(kProbeThreads) probe_mix_kernel(float* sink, int iters) {
+  float2 x[kProbeChains];
+  float u[kProbeChains];
+#pragma unroll
+  for (int c = 0; c < kProbeChains; ++c) {
+    x[c] = make_float2(1.0f + 1e-3f * (float)(threadIdx.x + c), 1.0f);
+    u[c] = 1.5f + 1e-3f * (float)c;
+  }
+  const float2 m = make_float2(0.999f + 1e-9f * (float)blockIdx.x, 0.9999f), a = make_float2(1e-3f, 1e-4f);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < kProbeUnroll / 4; ++k)
+#pragma unroll
+      for (int c = 0; c < kProbeChains; ++c) {
+        x[c] = __ffma2_rn(x[c], m, a);
+        x[c] = __ffma2_rn(x[c], m, a);
+        x[c] = __ffma2_rn(x[c], m, a);
+        x[c] = __ffma2_rn(x[c], m, a);
+        float r;
+        asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u[c]));
+        u[c] = r;
+      }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int c = 0; c < kProbeChains; ++c) s += x[c].x + x[c].y + u[c];
+  if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace
+
+cudaError_t probe_ffma2(float* sink, int n_blocks, int iters, cudaStream_t st) {
+  probe_ffma2_kernel<<<n_blocks, kProbeThreads, 0, st>>>(sink, iters);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t probe_mix(float* sink, int n_blocks, int iters, cudaStream_t st) {
+  probe_mix_kernel<<<n_blocks, kProbeThreads, 0, st>>>(sink, iters);
+  note_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t probe_ffma(float* sink, int n_blocks, int iters, cudaStream_t st) {
   probe_ffma_kernel<<<n_blocks, kProbeThreads, 0, st>>>(sink, iters);

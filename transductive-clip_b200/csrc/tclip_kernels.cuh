@@ -61,5 +61,7 @@ cudaError_t cluster_prototypes(const int* labels, const float* feats, int* clust
 // ---- issue-rate microbenchmarks used as roofline denominators (probe.cu) ------------------------------------------
 cudaError_t probe_ffma(float* sink, int n_blocks, int iters, cudaStream_t st);   // 2 * 8 * 256 * iters * 64 flop / CTA... see probe.cu
 cudaError_t probe_mufu(float* sink, int n_blocks, int iters, cudaStream_t st);
+cudaError_t probe_ffma2(float* sink, int n_blocks, int iters, cudaStream_t st);  // packed 2 x fp32 FMA
+cudaError_t probe_mix(float* sink, int n_blocks, int iters, cudaStream_t st);    // 4 FFMA2 : 1 MUFU
 
 }  // namespace tclip

@@ -135,6 +135,81 @@ TCLIP_HD float mm_update_element(float a, float y, float psis_hi, float psis_lo)
   return num * fast_rcp(den);
 }
 
+// ---- packed (2 x fp32) form of the same update ---------------------------------------------------------------------
+// Blackwell (sm_100) issues FFMA2 / FMUL2 / FADD2 on register pairs: one issue slot for two fp32 FMAs.  The scalar
+// kernel is issue-bound (ncu: 83 % issue-active, profiles/r1_mm_chunk_scalar.md), so the M-step evaluates two
+// elements of a row per instruction wherever the operation is an add / mul / fma; only the MUFU ops and the selects
+// stay scalar.  The small-a Taylor series is evaluated unconditionally here (no divergent branch).
+#if defined(__CUDA_ARCH__)
+TCLIP_D float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+TCLIP_D float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+TCLIP_D float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+#else
+struct float2 {
+  float x, y;
+};
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float2 f2fma(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+inline float2 f2mul(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+inline float2 f2add(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+#endif
+TCLIP_HD float2 f2(float c) { return make_float2(c, c); }
+
+// ny = -y (negated once at load time); returns the updated pair.
+TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, float psis_hi, float psis_lo) {
+  // Stirling part at X = a + 4 (same series as psi1_and_curvature_num), accumulated as -E so no negation is needed
+  const float2 x2 = f2add(a, f2(2.0f));
+  const float2 X = f2add(a, f2(4.0f));
+  const float2 t = f2mul(x2, x2);
+  const float2 P = f2mul(x2, f2add(t, f2(-1.0f)));     // (a+1)(a+2)(a+3)
+  const float2 ndP = f2fma(t, f2(-3.0f), f2(1.0f));     // -(3 x2^2 - 1)
+  const float2 XP = f2mul(X, P);
+  const float2 R = make_float2(fast_rcp(XP.x), fast_rcp(XP.y));
+  const float2 rX = f2mul(P, R);
+  const float2 rP = f2mul(X, R);
+  const float2 L = make_float2(fast_lg2(X.x), fast_lg2(X.y));
+  const float2 LP = make_float2(fast_lg2(P.x), fast_lg2(P.y));
+  const float2 z = f2mul(rX, rX);
+  float2 nsp = f2fma(z, f2(1.0f / 240.0f), f2(-1.0f / 252.0f));   // -S_psi / z
+  nsp = f2fma(z, nsp, f2(1.0f / 120.0f));
+  nsp = f2fma(z, nsp, f2(-1.0f / 12.0f));
+  float2 nsg = f2fma(z, f2(1.0f / 1680.0f), f2(-1.0f / 1260.0f));  // -S_gam / rX
+  nsg = f2fma(z, nsg, f2(1.0f / 360.0f));
+  nsg = f2fma(z, nsg, f2(-1.0f / 12.0f));
+  const float2 nE = f2fma(ndP, rP, f2fma(f2(-0.5f), rX, f2mul(nsp, z)));   // -E
+  const float2 psi1 = f2fma(L, f2(kLn2), nE);
+  // N = LP ln2 - 3.5 ln2 L + (a + 4 - ln(2 pi)/2) - a E - S_gam
+  float2 Ns = f2fma(nsg, rX, f2(4.0f - kHalfLn2Pi));
+  Ns = f2add(f2fma(a, nE, Ns), a);
+  Ns = f2fma(L, f2(-3.5f * kLn2), Ns);
+  Ns = f2fma(LP, f2(kLn2), Ns);
+  // Taylor form for a < 1/16: a^2 (c2 + c3 a + ... + c7 a^5), truncation < 1e-7 relative; evaluated unconditionally
+  float2 ts = f2fma(a, f2(-0.864299380613076709f), f2(0.847785884987040950f));
+  ts = f2fma(a, ts, f2(-0.829542204114695941f));
+  ts = f2fma(a, ts, f2(0.811742425283353644f));
+  ts = f2fma(a, ts, f2(-0.801371268773062857f));
+  ts = f2fma(a, ts, f2(0.822467033424113218f));
+  ts = f2mul(ts, f2mul(a, a));
+  float2 N;
+  N.x = a.x < kSmallA ? ts.x : fabsf(Ns.x);
+  N.y = a.y < kSmallA ? ts.y : fabsf(Ns.y);
+  // quadratic root, a-scaled and cancellation-free (see mm_update_element)
+  float2 g = f2add(psi1, f2(-psis_hi));
+  g = f2add(g, ny);
+  g = f2add(g, f2(-psis_lo));
+  const float2 bt = f2fma(a, g, f2mul(N, f2(-2.0f)));
+  const float2 Dt = f2fma(bt, bt, f2mul(N, f2(8.0f)));
+  const float2 r = make_float2(fast_sqrt(Dt.x), fast_sqrt(Dt.y));
+  const float2 q = make_float2(fabsf(bt.x) + r.x, fabsf(bt.y) + r.y);
+  const float2 aq = f2mul(a, q);
+  const float2 a2 = f2add(a, a);
+  const float2 N4 = f2mul(N, f2(4.0f));
+  const bool px = bt.x >= 0.0f, py = bt.y >= 0.0f;
+  const float2 num = make_float2(px ? a2.x : aq.x, py ? a2.y : aq.y);
+  const float2 den = make_float2(px ? q.x : N4.x, py ? q.y : N4.y);
+  return f2mul(num, make_float2(fast_rcp(den.x), fast_rcp(den.y)));
+}
+
 // psi(s) in float64, s > 0.  Used once per row and MM iteration (and by the host tests).
 TCLIP_HD double digamma_f64(double s) {
   double acc = 0.0;

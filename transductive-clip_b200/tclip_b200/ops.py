@@ -229,7 +229,7 @@ def probe_issue_rate(which: str, n_blocks: int, iters: int, device=None) -> tupl
     ops_out = ctypes.c_double(0.0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    check(lib.tclip_probe_issue_rate(0 if which == "ffma" else 1, _ptr(sink), int(n_blocks), int(iters),
+    check(lib.tclip_probe_issue_rate({"ffma": 0, "mufu": 1, "ffma2": 2, "mix": 3}[which], _ptr(sink), int(n_blocks), int(iters),
                                      ctypes.byref(ops_out), _stream()))
     e1.record()
     e1.synchronize()
