@@ -25,6 +25,7 @@ def shim():
     f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
     lib.tclip_host_psi1_N.argtypes = [f32p, f32p, f32p, ctypes.c_int]
     lib.tclip_host_mm_update.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
+    lib.tclip_host_mm_update_pair.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
     lib.tclip_host_digamma.argtypes = [ctypes.c_double]
     lib.tclip_host_digamma.restype = ctypes.c_double
     lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -65,7 +66,11 @@ def test_one_mm_update_matches_the_reference_formula(shim):
     y = -g.uniform(0.5, 12.0, a.size).astype(np.float32)
     s = 37.5
     out = np.empty_like(a)
+    out2 = np.empty_like(a)
+    a = a[: a.size // 2 * 2]
+    y, out, out2 = y[: a.size], out[: a.size], out2[: a.size]
     shim.tclip_host_mm_update(a, y, out, a.size, float(special.digamma(s)))
+    shim.tclip_host_mm_update_pair(a, y, out2, a.size, float(special.digamma(s)))   # the kernel's packed shift-4 form
     a64, y64 = torch.from_numpy(a).double(), torch.from_numpy(y).double()
     psi1 = torch.polygamma(0, a64 + 1)
     c = torch.where(a64 > 1e-11, (2 * (-torch.lgamma(a64 + 1) + psi1 * a64) / a64 ** 2).abs(),
@@ -73,6 +78,7 @@ def test_one_mm_update_matches_the_reference_formula(shim):
     b = psi1 - special.digamma(s) - c * a64 - y64
     ref = ((-b + torch.sqrt(b * b + 4 * c)) / (2 * c)).numpy()
     assert np.max(np.abs(out - ref) / ref) < 3e-6
+    assert np.max(np.abs(out2 - ref) / ref) < 3e-6
 
 
 def test_mm_rows_track_the_oracle(shim):

@@ -51,12 +51,13 @@ __device__ __forceinline__ float lane_tree_sum(const float2 (&a)[NP], float2 tai
 // every global access is a coalesced 128-byte row segment.  Only the last pair can hold padding (masked in the sums).
 // All add / mul / fma work is issued as packed FFMA2 / FMUL2 / FADD2 (tclip_math.cuh: mm_update_pair).
 template <int NP>
-__global__ void __launch_bounds__(kMMThreads)
+__global__ void __launch_bounds__(kMMThreads, kMMMinBlocks)
 mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict__ y,
                 const int* __restrict__ row_list, const int* __restrict__ n_rows_dev, int n_rows_host, int D,
                 int n_iters, int emit_check, double2* __restrict__ partials, const MMState* __restrict__ state,
                 double2* __restrict__ row_cache, int n_checks, int check_idx) {
   if (state->done) return;  // an earlier chunk met the batch-global criterion: the M-step is over
+  extern __shared__ float2 ny_smem[];  // [warps per CTA][NP][32] pairs of -y
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int n_rows = n_rows_dev ? *n_rows_dev : n_rows_host;
@@ -74,33 +75,33 @@ mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict
     const bool ok_x = dx < D, ok_y = dy < D;
     const float2 tail_mask = make_float2(ok_x ? 1.0f : 0.0f, ok_y ? 1.0f : 0.0f);
 
-    float2 a[NP], ny[NP];
+    // alpha stays in registers; -y (read-only, one LDS.64 per pair and iteration) lives in this warp's slice of shared
+    // memory, which keeps the kernel at <= 80 registers, i.e. 6 instead of 4 warps per scheduler to overlap the FMA and
+    // MUFU pipes (ncu: math-pipe-throttle was the top stall at 4 warps, profiles/r1_mm_chunk_packed.md)
+    float2* ny = ny_smem + (size_t)warp * NP * 32 + lane;
+    float2 a[NP];
 #pragma unroll
     for (int j = 0; j < NP - 1; ++j) {
       a[j] = make_float2(ain[(2 * j) * 32 + lane], ain[(2 * j + 1) * 32 + lane]);
-      ny[j] = make_float2(-__ldg(yin + (2 * j) * 32 + lane), -__ldg(yin + (2 * j + 1) * 32 + lane));
+      ny[j * 32] = make_float2(-__ldg(yin + (2 * j) * 32 + lane), -__ldg(yin + (2 * j + 1) * 32 + lane));
     }
     // padding lanes iterate on a harmless dummy (a = 1, y = -1)
     a[NP - 1] = make_float2(ok_x ? ain[dx] : 1.0f, ok_y ? ain[dy] : 1.0f);
-    ny[NP - 1] = make_float2(ok_x ? -__ldg(yin + dx) : 1.0f, ok_y ? -__ldg(yin + dy) : 1.0f);
+    ny[(NP - 1) * 32] = make_float2(ok_x ? -__ldg(yin + dx) : 1.0f, ok_y ? -__ldg(yin + dy) : 1.0f);
 
     double s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     for (int it = 0; it < n_iters - 1; ++it) {
-      const double ps = digamma_f64(s);
-      const float hi = (float)ps;
-      const float lo = (float)(ps - (double)hi);
+      const RowPsi rp = row_psi(s);
 #pragma unroll
-      for (int j = 0; j < NP; ++j) a[j] = mm_update_pair(a[j], ny[j], hi, lo);
+      for (int j = 0; j < NP; ++j) a[j] = mm_update_pair(a[j], ny[j * 32], rp);
       s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     }
     {  // last iteration of the chunk: also the one the criterion is evaluated on
-      const double ps = digamma_f64(s);
-      const float hi = (float)ps;
-      const float lo = (float)(ps - (double)hi);
+      const RowPsi rp = row_psi(s);
       float2 d2 = make_float2(0.0f, 0.0f), a2 = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
-        const float2 an = mm_update_pair(a[j], ny[j], hi, lo);
+        const float2 an = mm_update_pair(a[j], ny[j * 32], rp);
         float2 df = f2add(an, make_float2(-a[j].x, -a[j].y));
         float2 ao = a[j];
         if (j == NP - 1) {
@@ -195,7 +196,7 @@ __global__ void mm_reset_kernel(MMState* state) {
 
 template <int NP>
 void launch_chunk(const MMLaunch& p, int n_iters, int emit_check, int check_idx, cudaStream_t st) {
-  mm_chunk_kernel<NP><<<p.n_blocks, kMMThreads, 0, st>>>(p.alpha_in, p.alpha_out, p.y, p.row_list, p.n_rows_dev,
+  mm_chunk_kernel<NP><<<p.n_blocks, kMMThreads, (size_t)(kMMThreads / 32) * NP * 32 * sizeof(float2), st>>>(p.alpha_in, p.alpha_out, p.y, p.row_list, p.n_rows_dev,
                                                          p.n_rows, p.D, n_iters, emit_check, p.partials, p.state,
                                                          p.row_cache, p.n_checks, check_idx);
 }

@@ -1,11 +1,13 @@
 // TEST SHIM — exposes tclip_math.cuh to the CPU test-suite (tests/test_math_host.py) as plain C symbols.
-// Not part of libtclip_b200.so; compiled on demand with g++.  MUFU approximations are libm calls here, so this
-// checks the series / algebra, not the hardware approximations (those are covered by the -m gpu parity tests).
+// Not part of libtclip_b200.so; compiled on demand with g++.  MUFU rcp / sqrt are correctly rounded libm calls here and MUFU lg2 is
+// modelled after its measured error (tclip_math.cuh), so this checks the series / algebra and the sensitivity to the lg2
+// truncation; the hardware itself is covered by the -m gpu parity tests.
 #define TCLIP_HOST_MATH 1
 #include <math.h>
 #include "tclip_math.cuh"
 
 extern "C" {
+void tclip_host_set_lg2_exact(int exact) { tclip::host_lg2_exact() = exact; }
 void tclip_host_psi1_N(const float* a, float* psi1, float* N, int n) {
   for (int i = 0; i < n; ++i) {
     tclip::PsiN r = tclip::psi1_and_curvature_num(a[i]);
@@ -18,7 +20,16 @@ void tclip_host_mm_update(const float* a, const float* y, float* out, int n, dou
   const float lo = (float)(psis - (double)hi);
   for (int i = 0; i < n; ++i) out[i] = tclip::mm_update_element(a[i], y[i], hi, lo);
 }
-double tclip_host_digamma(double s) { return tclip::digamma_f64(s); }
+double tclip_host_digamma(double s) { return tclip::digamma_row(s); }
+// `s` is the row total (the kernel derives psi(s) from it itself)
+void tclip_host_mm_update_pair(const float* a, const float* y, float* out, int n, double s) {
+  const tclip::RowPsi rp = tclip::row_psi(s);
+  for (int i = 0; i + 1 < n; i += 2) {
+    tclip::float2 r = tclip::mm_update_pair(tclip::make_float2(a[i], a[i + 1]), tclip::make_float2(-y[i], -y[i + 1]), rp);
+    out[i] = r.x;
+    out[i + 1] = r.y;
+  }
+}
 // rows x D MM iterations on the host: the CPU twin of the kernel's inner loop (row sum in double).
 void tclip_host_mm_rows(float* alpha, const float* y, int rows, int D, int iters) {
   for (int r = 0; r < rows; ++r) {
@@ -27,10 +38,12 @@ void tclip_host_mm_rows(float* alpha, const float* y, int rows, int D, int iters
     for (int it = 0; it < iters; ++it) {
       double s = 0.0;
       for (int d = 0; d < D; ++d) s += (double)a[d];
-      const double ps = tclip::digamma_f64(s);
-      const float hi = (float)ps;
-      const float lo = (float)(ps - (double)hi);
-      for (int d = 0; d < D; ++d) a[d] = tclip::mm_update_element(a[d], yy[d], hi, lo);
+      const tclip::RowPsi rp = tclip::row_psi(s);
+      for (int d = 0; d + 1 < D; d += 2) {  // the kernel's packed form (D even here)
+        tclip::float2 r = tclip::mm_update_pair(tclip::make_float2(a[d], a[d + 1]), tclip::make_float2(-yy[d], -yy[d + 1]), rp);
+        a[d] = r.x;
+        a[d + 1] = r.y;
+      }
     }
   }
 }

@@ -25,6 +25,7 @@
 // The file also compiles as plain C++ (TCLIP_HOST_MATH) so tests/test_math_host.py can check the series against
 // SciPy on CPU; there the MUFU approximations are replaced by correctly rounded libm calls.
 #pragma once
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define TCLIP_HD __host__ __device__ __forceinline__
@@ -33,6 +34,7 @@
 #define TCLIP_HD inline
 #define TCLIP_D inline
 #include <cmath>
+#include <cstring>
 #endif
 
 namespace tclip {
@@ -43,24 +45,48 @@ constexpr float kSmallA = 0.0625f;  // TCLIP_SMALL_A: below this N(a) comes from
 
 // ---- MUFU wrappers -------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
+// TCLIP_EXACT_{RCP,LG2,SQRT}: diagnostic builds that swap one MUFU approximation for the correctly rounded operation
+// (scripts/build_variants.sh) to attribute the alpha error budget; never defined in the product build.
 TCLIP_D float fast_rcp(float x) {
+#ifdef TCLIP_EXACT_RCP
+  return __frcp_rn(x);
+#endif
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 TCLIP_D float fast_lg2(float x) {
+#ifdef TCLIP_EXACT_LG2
+  return log2f(x);
+#endif
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 TCLIP_D float fast_sqrt(float x) {
+#ifdef TCLIP_EXACT_SQRT
+  return __fsqrt_rn(x);
+#endif
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 #else
 inline float fast_rcp(float x) { return 1.0f / x; }
-inline float fast_lg2(float x) { return (float)std::log2((double)x); }
+// Host model of MUFU.LG2 as measured on B200 (profiles/r1_lg2_error.txt): results with |r| >= 1 are truncated toward
+// zero to float32 (<= 1 ulp, biased), results in (-1, 1) carry ~2e-7 absolute error (modelled as rounding to 2^-22).
+inline int& host_lg2_exact() {  // tests may switch the model off (1) to separate series error from MUFU error
+  static int exact = 0;
+  return exact;
+}
+inline float fast_lg2(float x) {
+  const double r = std::log2((double)x);
+  if (host_lg2_exact()) return (float)r;
+  if (std::fabs(r) < 1.0) return (float)(std::nearbyint(r * 4194304.0) / 4194304.0);
+  float f = (float)r;
+  if (std::fabs((double)f) > std::fabs(r)) f = std::nextafterf(f, 0.0f);
+  return f;
+}
 inline float fast_sqrt(float x) { return std::sqrt(x); }
 #endif
 
@@ -155,77 +181,190 @@ inline float2 f2add(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
 #endif
 TCLIP_HD float2 f2(float c) { return make_float2(c, c); }
 
+// x = 2^e m with m in [sqrt(1/2), sqrt(2)): returns m and e * 2^23 as a float (exact), integer pipe only.
+TCLIP_HD void split_exponent(float x, float& m, float& e23) {
+#if defined(__CUDA_ARCH__)
+  const int b = __float_as_int(x);
+  const int e = (b - 0x3f3504f3) & 0xff800000;
+  m = __int_as_float(b - e);
+  e23 = (float)e;
+#else
+  int b;
+  std::memcpy(&b, &x, 4);
+  const int e = (int)((unsigned)(b - 0x3f3504f3) & 0xff800000u);
+  const int mb = b - e;
+  std::memcpy(&m, &mb, 4);
+  e23 = (float)e;
+#endif
+}
+
 // ny = -y (negated once at load time); returns the updated pair.
-TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, float psis_hi, float psis_lo) {
-  // Stirling part at X = a + 4 (same series as psi1_and_curvature_num), accumulated as -E so no negation is needed
-  const float2 x2 = f2add(a, f2(2.0f));
-  const float2 X = f2add(a, f2(4.0f));
-  const float2 t = f2mul(x2, x2);
-  const float2 P = f2mul(x2, f2add(t, f2(-1.0f)));     // (a+1)(a+2)(a+3)
-  const float2 ndP = f2fma(t, f2(-3.0f), f2(1.0f));     // -(3 x2^2 - 1)
+//
+// Shift by 4 here (X = a + 5 >= 5, P = (a+1)(a+2)(a+3)(a+4) = w^2 - 1 with w = a^2 + 5a + 5), so both Stirling series
+// need three terms only (next terms < 1e-8), and everything is accumulated with the signs / factors the root needs:
+//   nE = -E,   E = 1/(2X) + S_psi(X) + P'/P,   psi(a+1) = ln X + nE
+//   M  = 2N >= 2 * 0.003 for a >= 1/16, far above its rounding error, so the reference's |.| is a no-op there
+//   M  = 2N = 2 [ln P - 4.5 ln X + (a + 5 - ln(2 pi)/2) + a nE - S_gam(X)]
+//   bt = a g - M,  Dt = bt^2 + 4M,  q = |bt| + sqrt(Dt),  a_new = bt >= 0 ? 2a / q : 2a q / (4M)
+//
+// ln X is NOT taken from MUFU.LG2: that unit truncates results with |r| >= 1 to float32 (mean error -0.45 ulp, e.g.
+// -9e-7 at x ~ 1e5) and is biased by +4..8e-8 even for results in (-1, 1) (measured: profiles/r1_lg2_error.txt).  A bias
+// common to the heavy elements of a row moves the ill-conditioned precision direction of the Dirichlet fit by
+// ~ 2 s / (D - 1) times the bias (3e3 at s = 1.7e5, D = 100): with MUFU.LG2 the alpha error against the float64
+// restatement was 5x the reference's own float32 error, with a correctly rounded log it is below it
+// (profiles/r1_alpha_error_attribution.txt).  So ln X = e ln2 + ln m with the exponent split off on the integer pipe and
+// ln m from a degree-6 minimax polynomial (7e-9 absolute) in round-to-nearest FFMA2s, and the row total s enters as
+//   psi(a+1) - psi(s) = (e - k) ln2 + ln m + nE - (psi(s) - k ln2),      2^k ~ s,
+// so the heavy elements (X ~ s) see small, accurately rounded terms only.  lg2(P), which only feeds the curvature,
+// stays on the MUFU.
+struct RowPsi {
+  float dpsi;  // psi(s) - k ln2, |.| < ~0.4 + 1/(2s): float32 carries it to ~3e-8, no lo word needed
+  float k23;   // k * 2^23 (exact)
+};
+
+TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, RowPsi rp) {
+  const float2 X = f2add(a, f2(5.0f));
+  const float2 w = f2fma(a, X, f2(5.0f));
+  const float2 P = f2fma(w, w, f2(-1.0f));
+  const float2 ndP = f2mul(w, f2fma(a, f2(-4.0f), f2(-10.0f)));   // -dP/da = -2w(2a + 5)
   const float2 XP = f2mul(X, P);
   const float2 R = make_float2(fast_rcp(XP.x), fast_rcp(XP.y));
   const float2 rX = f2mul(P, R);
   const float2 rP = f2mul(X, R);
-  const float2 L = make_float2(fast_lg2(X.x), fast_lg2(X.y));
+  float2 m, e23;
+  split_exponent(X.x, m.x, e23.x);
+  split_exponent(X.y, m.y, e23.y);
+  const float2 f = f2add(m, f2(-1.0f));                            // [-0.293, 0.414]
+  float2 lp = f2fma(f, f2(0.08671870082616806f), f2(-0.14378608763217926f));
+  lp = f2fma(f, lp, f2(0.14977926015853882f));
+  lp = f2fma(f, lp, f2(-0.16564473509788513f));
+  lp = f2fma(f, lp, f2(0.1995488703250885f));
+  lp = f2fma(f, lp, f2(-0.250016987323761f));
+  lp = f2fma(f, lp, f2(0.33334165811538696f));
+  const float2 lnm = f2fma(f2mul(f, f), f2fma(f, lp, f2(-0.5f)), f);   // ln m = f - f^2/2 + f^3 p(f)
+  const float2 lnX = f2fma(e23, f2(kLn2 / 8388608.0f), lnm);                          // e ln2 + ln m
+  const float2 lnXs = f2fma(f2add(e23, f2(-rp.k23)), f2(kLn2 / 8388608.0f), lnm);     // (e - k) ln2 + ln m
   const float2 LP = make_float2(fast_lg2(P.x), fast_lg2(P.y));
   const float2 z = f2mul(rX, rX);
-  float2 nsp = f2fma(z, f2(1.0f / 240.0f), f2(-1.0f / 252.0f));   // -S_psi / z
-  nsp = f2fma(z, nsp, f2(1.0f / 120.0f));
+  float2 nsp = f2fma(z, f2(-1.0f / 252.0f), f2(1.0f / 120.0f));    // -S_psi / z = -1/12 + z/120 - z^2/252
   nsp = f2fma(z, nsp, f2(-1.0f / 12.0f));
-  float2 nsg = f2fma(z, f2(1.0f / 1680.0f), f2(-1.0f / 1260.0f));  // -S_gam / rX
-  nsg = f2fma(z, nsg, f2(1.0f / 360.0f));
-  nsg = f2fma(z, nsg, f2(-1.0f / 12.0f));
-  const float2 nE = f2fma(ndP, rP, f2fma(f2(-0.5f), rX, f2mul(nsp, z)));   // -E
-  const float2 psi1 = f2fma(L, f2(kLn2), nE);
-  // N = LP ln2 - 3.5 ln2 L + (a + 4 - ln(2 pi)/2) - a E - S_gam
-  float2 Ns = f2fma(nsg, rX, f2(4.0f - kHalfLn2Pi));
-  Ns = f2add(f2fma(a, nE, Ns), a);
-  Ns = f2fma(L, f2(-3.5f * kLn2), Ns);
-  Ns = f2fma(LP, f2(kLn2), Ns);
-  // Taylor form for a < 1/16: a^2 (c2 + c3 a + ... + c7 a^5), truncation < 1e-7 relative; evaluated unconditionally
-  float2 ts = f2fma(a, f2(-0.864299380613076709f), f2(0.847785884987040950f));
-  ts = f2fma(a, ts, f2(-0.829542204114695941f));
-  ts = f2fma(a, ts, f2(0.811742425283353644f));
-  ts = f2fma(a, ts, f2(-0.801371268773062857f));
-  ts = f2fma(a, ts, f2(0.822467033424113218f));
-  ts = f2mul(ts, f2mul(a, a));
-  float2 N;
-  N.x = a.x < kSmallA ? ts.x : fabsf(Ns.x);
-  N.y = a.y < kSmallA ? ts.y : fabsf(Ns.y);
-  // quadratic root, a-scaled and cancellation-free (see mm_update_element)
-  float2 g = f2add(psi1, f2(-psis_hi));
-  g = f2add(g, ny);
-  g = f2add(g, f2(-psis_lo));
-  const float2 bt = f2fma(a, g, f2mul(N, f2(-2.0f)));
-  const float2 Dt = f2fma(bt, bt, f2mul(N, f2(8.0f)));
+  float2 nsg2 = f2fma(z, f2(-2.0f / 1260.0f), f2(2.0f / 360.0f));  // -2 S_gam / rX = 2(-1/12 + z/360 - z^2/1260)
+  nsg2 = f2fma(z, nsg2, f2(-2.0f / 12.0f));
+  const float2 nE = f2fma(ndP, rP, f2fma(f2(-0.5f), rX, f2mul(nsp, z)));
+  const float2 psi1m = f2add(lnXs, nE);                            // psi(a+1) - k ln2
+  const float2 a2 = f2add(a, a);
+  float2 M = f2fma(nsg2, rX, f2(2.0f * (5.0f - kHalfLn2Pi)));
+  M = f2add(f2fma(a2, nE, M), a2);
+  M = f2fma(lnX, f2(-9.0f), M);
+  M = f2fma(LP, f2(2.0f * kLn2), M);
+#if defined(__CUDA_ARCH__)
+  const bool any_small = __any_sync(0xffffffffu, (a.x < kSmallA) | (a.y < kSmallA));
+#else
+  const bool any_small = (a.x < kSmallA) | (a.y < kSmallA);
+#endif
+  if (any_small) {
+    // Taylor form of 2N for a < 1/16: 2 a^2 (c2 + c3 a + ... + c7 a^5), truncation < 1e-7 relative (warp-uniform branch:
+    // with y >= log(1e-15) the fixed points sit above 1/35, so whole warps rarely come here)
+    float2 ts = f2fma(a, f2(2.0f * -0.864299380613076709f), f2(2.0f * 0.847785884987040950f));
+    ts = f2fma(a, ts, f2(2.0f * -0.829542204114695941f));
+    ts = f2fma(a, ts, f2(2.0f * 0.811742425283353644f));
+    ts = f2fma(a, ts, f2(2.0f * -0.801371268773062857f));
+    ts = f2fma(a, ts, f2(2.0f * 0.822467033424113218f));
+    ts = f2mul(ts, f2mul(a, a));
+    M.x = a.x < kSmallA ? ts.x : M.x;
+    M.y = a.y < kSmallA ? ts.y : M.y;
+  }
+  const float2 g = f2add(f2add(psi1m, f2(-rp.dpsi)), ny);          // psi(a+1) - psi(s) - y
+  const float2 nM = make_float2(-M.x, -M.y);
+  const float2 bt = f2fma(a, g, nM);
+  const float2 M4 = f2mul(M, f2(4.0f));
+  const float2 Dt = f2fma(bt, bt, M4);
   const float2 r = make_float2(fast_sqrt(Dt.x), fast_sqrt(Dt.y));
   const float2 q = make_float2(fabsf(bt.x) + r.x, fabsf(bt.y) + r.y);
-  const float2 aq = f2mul(a, q);
-  const float2 a2 = f2add(a, a);
-  const float2 N4 = f2mul(N, f2(4.0f));
   const bool px = bt.x >= 0.0f, py = bt.y >= 0.0f;
-  const float2 num = make_float2(px ? a2.x : aq.x, py ? a2.y : aq.y);
-  const float2 den = make_float2(px ? q.x : N4.x, py ? q.y : N4.y);
+  const float2 num = f2mul(a2, make_float2(px ? 1.0f : q.x, py ? 1.0f : q.y));
+  const float2 den = make_float2(px ? q.x : M4.x, py ? q.y : M4.y);
   return f2mul(num, make_float2(fast_rcp(den.x), fast_rcp(den.y)));
 }
 
-// psi(s) in float64, s > 0.  Used once per row and MM iteration (and by the host tests).
-TCLIP_HD double digamma_f64(double s) {
-  double acc = 0.0;
-  while (s < 10.0) {  // only rows with a tiny total mass take this path
-    acc -= 1.0 / s;
-    s += 1.0;
+// psi(s) for the row total, s > 0, to ~1e-10 absolute: ln s from the (m-1)/(m+1) series in float64, reciprocals from a
+// MUFU seed + two Newton steps (no division subroutine, no libm call).  It enters the update as a (hi, lo) float pair.
+TCLIP_HD double rcp_f64(double x) {
+  double r = (double)fast_rcp((float)x);
+  r = r * fma(-x, r, 2.0);
+  r = r * fma(-x, r, 2.0);
+  return r;
+}
+
+// ln(s) = e ln2 + lnm with s = 2^e m, m in [sqrt(1/2), sqrt(2)); lnm from the (m-1)/(m+1) series (float64, ~1e-11).
+struct LogParts {
+  int e;
+  double lnm;
+};
+
+TCLIP_HD LogParts log_parts_f64(double s) {
+#if defined(__CUDA_ARCH__)
+  int hi = __double2hiint(s);
+  const int lo = __double2loint(s);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  double m = __hiloint2double(hi, lo);   // [1, 2)
+#else
+  int e;
+  double m = std::frexp(s, &e) * 2.0;    // [1, 2)
+  e -= 1;
+#endif
+  if (m > 1.4142135623730951) {
+    m *= 0.5;
+    e += 1;
   }
-  const double r = 1.0 / s;
+  const double t = (m - 1.0) * rcp_f64(m + 1.0);
+  const double t2 = t * t;                // <= 0.0295
+  double p = fma(t2, 1.0 / 13.0, 1.0 / 11.0);
+  p = fma(t2, p, 1.0 / 9.0);
+  p = fma(t2, p, 1.0 / 7.0);
+  p = fma(t2, p, 1.0 / 5.0);
+  p = fma(t2, p, 1.0 / 3.0);
+  p = fma(t2, p, 1.0);
+  LogParts out;
+  out.e = e;
+  out.lnm = 2.0 * t * p;
+  return out;
+}
+
+// psi(s) for the row total s > 0 (normal float64), split as k ln2 + dpsi with 2^k ~ s.
+TCLIP_HD RowPsi row_psi(double s) {
+  const LogParts ls = log_parts_f64(s);   // exponent of the *row total*, also when the series below shifts s
+  double acc = 0.0;
+  double x = s;
+  while (x < 10.0) {  // only rows with a tiny total mass take this path
+    acc -= rcp_f64(x);
+    x += 1.0;
+  }
+  const double r = rcp_f64(x);
   const double r2 = r * r;
-  double ser = fma(r2, -1.0 / 12.0, 691.0 / 32760.0);
-  ser = fma(r2, ser, -1.0 / 132.0);
-  ser = fma(r2, ser, 1.0 / 240.0);
-  ser = fma(r2, ser, -1.0 / 252.0);
+  double ser = fma(r2, 1.0 / 240.0, -1.0 / 252.0);   // next term 1/(132 x^10) < 1e-12
   ser = fma(r2, ser, 1.0 / 120.0);
   ser = fma(r2, ser, -1.0 / 12.0);
-  return log(s) + fma(r2, ser, -0.5 * r) + acc;
+  const double tail = fma(r2, ser, -0.5 * r) + acc;   // psi(x) - ln x + acc
+  double lnx_minus_kln2 = ls.lnm;                      // x == s: ln s - k ln2
+  if (x != s) {
+    const LogParts lx = log_parts_f64(x);
+    lnx_minus_kln2 = fma((double)(lx.e - ls.e), 0.693147180559945309417, lx.lnm);
+  }
+  RowPsi out;
+  out.dpsi = (float)(lnx_minus_kln2 + tail);
+  int k = ls.e;
+  k = k < -120 ? -120 : (k > 120 ? 120 : k);           // s is a sum of float32 values; keeps k * 2^23 exact
+  if (k != ls.e) out.dpsi = (float)(lnx_minus_kln2 + tail + (double)(ls.e - k) * 0.693147180559945309417);
+  out.k23 = (float)k * 8388608.0f;
+  return out;
+}
+
+// psi(s) itself in float64 (host tests)
+TCLIP_HD double digamma_row(double s) {
+  const RowPsi rp = row_psi(s);
+  return (double)rp.dpsi + (double)rp.k23 / 8388608.0 * 0.693147180559945309417;
 }
 
 }  // namespace tclip

@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtclip_b200.so")
+LIB_PATH = os.environ.get("TCLIP_LIB") or os.path.join(_HERE, "libtclip_b200.so")   # TCLIP_LIB: diagnostic builds only
 
 TCLIP_OK = 0
 TCLIP_MM_DENSE = 0
