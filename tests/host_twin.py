@@ -25,7 +25,7 @@ def shim():
             subprocess.run(["bash", os.path.join(HERE, "build_host_shim.sh")], check=True)
         _lib = ctypes.CDLL(SHIM)
         f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
-        _lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        _lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return _lib
 
 
@@ -47,11 +47,9 @@ def mm_update_alpha_twin(alpha0, y_cst, iter_mm, check_every=R.MM_CHECK_EVERY, t
         end, has_check = (cand, True) if cand <= iter_mm - 1 else (iter_mm - 1, False)
         n = end - start + 1
         if n > 1:
-            _pad_sum_fix(a, D)
-            lib.tclip_host_mm_rows(a, y, rows, Dp, n - 1)
+            lib.tclip_host_mm_rows(a, y, rows, Dp, D, n - 1)
         prev = a.copy()
-        _pad_sum_fix(a, D)
-        lib.tclip_host_mm_rows(a, y, rows, Dp, 1)
+        lib.tclip_host_mm_rows(a, y, rows, Dp, D, 1)
         start = end + 1
         if has_check:
             num = float(((a[:, :D].astype(np.float64) - prev[:, :D]) ** 2).sum())
@@ -59,13 +57,6 @@ def mm_update_alpha_twin(alpha0, y_cst, iter_mm, check_every=R.MM_CHECK_EVERY, t
             if np.float32(num) / np.float32(den) < tol:
                 break
     return torch.from_numpy(a[:, :D].copy()).reshape(shape), start
-
-
-def _pad_sum_fix(a, D):
-    """The padding column must not enter the row sum: the shim sums all Dp columns, so keep it at 0 (its own update
-    is then meaningless and discarded)."""
-    if a.shape[1] != D:
-        a[:, D:] = 0.0
 
 
 class patched_oracle:

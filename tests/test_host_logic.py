@@ -1,0 +1,145 @@
+"""CPU: host-side logic of the product package — synthetic task generator layout, batch sharding (gloo, world_size 2),
+label matching vs the oracle's, the drop-in module names, and the refusal to run without a B200."""
+from __future__ import annotations
+
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restated as R
+from oracle.ref_loader import make_args
+from tclip_b200 import matching, tasks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_zero_shot_batch_layout():
+    td, txt = tasks.make_zero_shot_batch(4, 50, seed=3)
+    assert td["x_q"].shape == (4, 75, 50) and td["x_q"].dtype == torch.float32 and td["x_q"].is_contiguous()
+    assert td["y_q"].shape == (4, 75, 1) and td["y_q"].dtype == torch.int64
+    assert torch.allclose(td["x_q"].sum(-1), torch.ones(4, 75), atol=1e-5)       # softmax features
+    assert txt.shape == (50, 1024)
+    for t in range(4):
+        assert 3 <= td["y_q"][t].unique().numel() <= 10                           # k_eff ~ U{3..10}
+    td2, _ = tasks.make_zero_shot_batch(4, 50, seed=3)
+    assert torch.equal(td["x_q"], td2["x_q"]) and torch.equal(td["y_q"], td2["y_q"])
+    td3, _ = tasks.make_zero_shot_batch(4, 50, seed=3, batch_index=1)
+    assert not torch.equal(td["x_q"], td3["x_q"])
+
+
+def test_few_shot_batch_layout():
+    td, _ = tasks.make_few_shot_batch(2, 20, shots=4, seed=1)
+    assert td["x_s"].shape == (2, 80, 20) and td["y_s"].shape == (2, 80, 1)
+    for t in range(2):
+        assert torch.equal(td["y_s"][t].flatten().bincount(minlength=20), torch.full((20,), 4))
+        assert td["y_q"][t].unique().numel() <= 5
+
+
+def test_shard_batches_partition():
+    for n, w in ((13, 1), (13, 2), (1333, 8), (3, 8)):
+        parts = [tasks.shard_batches(n, r, w) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_matching_equals_oracle_matching():
+    g = torch.Generator().manual_seed(0)
+    T, n, K = 5, 75, 40
+    feats = torch.softmax(3 * torch.randn(T, n, K, generator=g), -1)
+    labels = torch.randint(0, 9, (T, n), generator=g) * 4
+    # what tclip_cluster_prototypes delivers: clusters in first-appearance order, their mean raw feature
+    proto = np.zeros((T, n, K), dtype=np.float32)
+    n_clusters = np.zeros(T, dtype=np.int32)
+    sample_cluster = np.zeros((T, n), dtype=np.int32)
+    for t in range(T):
+        order = []
+        for i in range(n):
+            lab = int(labels[t, i])
+            if lab not in order:
+                order.append(lab)
+            sample_cluster[t, i] = order.index(lab)
+        n_clusters[t] = len(order)
+        for c, lab in enumerate(order):
+            proto[t, c] = feats[t][labels[t] == lab].mean(0).numpy()
+    onehot = torch.nn.functional.one_hot(labels, K).float()
+    _, protos = R.cluster_prototypes(onehot, feats, K, "einsum")
+    assert (matching.graph_matching(proto, n_clusters, sample_cluster) == R.graph_matching(labels, protos, K).numpy()).all()
+    assert (matching.basic_matching(proto, n_clusters, sample_cluster) == R.basic_matching(labels, protos).numpy()).all()
+
+
+def test_drop_in_module_names():
+    """The evaluators import these dotted names (src/eval_zero_shot.py:12-13, src/eval_few_shot.py:12-13)."""
+    code = textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {os.path.join(ROOT, 'transductive-clip_b200')!r})
+        from src.methods.zero_shot.em_dirichlet import EM_DIRICHLET as A, BASE
+        from src.methods.zero_shot.hard_em_dirichlet import HARD_EM_DIRICHLET as B
+        from src.methods.few_shot.em_dirichlet import EM_DIRICHLET as C
+        from src.methods.few_shot.hard_em_dirichlet import HARD_EM_DIRICHLET as D
+        import inspect
+        for cls in (A, B, C, D):
+            assert list(inspect.signature(cls.__init__).parameters)[1:] == ['model', 'device', 'log_file', 'args']
+        assert list(inspect.signature(A.run_task).parameters)[1:] == ['task_dic']
+        assert list(inspect.signature(C.run_task).parameters)[1:] == ['task_dic', 'shot']
+        print('ok')
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_no_cpu_fallback():
+    from tclip_b200 import ops
+    from tclip_b200.methods.dirichlet import EM_DIRICHLET, FEW_SHOT_EM_DIRICHLET
+    m = EM_DIRICHLET(model=None, device=torch.device("cpu"), log_file=None, args=make_args(20, iters=2))
+    assert m.lambd == int(20 / 5) * 75
+    td, _ = tasks.make_zero_shot_batch(2, 20, seed=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.run_task(td)
+    f = FEW_SHOT_EM_DIRICHLET(model=None, device=torch.device("cpu"), log_file=None, args=make_args(20, iters=2, k_eff=4))
+    assert f.lambd == int(20 / 4) * 75
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        ops.log_features(torch.ones(4))
+    with pytest.raises(ValueError, match="mm_mode"):
+        EM_DIRICHLET(model=None, device=torch.device("cpu"), log_file=None, args=make_args(20, mm_mode="bogus"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_sharded_gather_gloo_world2(tmp_path):
+    """The N > 1 host path of bench.py on CPU: batches by rank, one gather of accuracies, max-over-ranks timing."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {os.path.join(ROOT, 'transductive-clip_b200')!r})
+        import torch, torch.distributed as dist
+        from tclip_b200 import tasks
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        mine = tasks.shard_batches(7, rank, world)
+        acc = torch.tensor([float(sum(mine))])                    # stands in for the per-rank accuracy
+        gathered = [torch.zeros(1) for _ in range(world)] if rank == 0 else None
+        dist.gather(acc, gathered, dst=0)
+        t = torch.tensor([1.0 + rank], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert sorted(sum([tasks.shard_batches(7, r, world) for r in range(world)], [])) == list(range(7))
+            assert float(torch.cat(gathered).sum()) == 21.0 and float(t) == float(world)
+            print("gather ok")
+        dist.destroy_process_group()
+    """))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "gather ok" in out.stdout, out.stderr[-2000:]

@@ -28,7 +28,7 @@ def shim():
     lib.tclip_host_mm_update_pair.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
     lib.tclip_host_digamma.argtypes = [ctypes.c_double]
     lib.tclip_host_digamma.restype = ctypes.c_double
-    lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
 
 
@@ -54,8 +54,13 @@ def test_psi_and_curvature_numerator(shim):
 
 
 def test_digamma_f64(shim):
+    """row_psi: psi(s) = k ln2 + dpsi with dpsi carried as ONE float32 (|dpsi| < 0.4 + 1/(2s) for s >= 10), so the
+    reconstruction is good to a float32 ulp of dpsi, i.e. ~3e-8 absolute where it matters (large row totals)."""
     for s in (1e-3, 0.5, 1.0, 9.99, 10.0, 123.4, 1e5, 3e8):
-        assert abs(shim.tclip_host_digamma(s) - special.digamma(s)) <= 1e-12 * max(1.0, abs(special.digamma(s)))
+        ref = special.digamma(s)
+        got = shim.tclip_host_digamma(s)
+        k = np.floor(np.log2(s) + 0.5)
+        assert abs(got - ref) <= 1.2e-7 * max(abs(ref - k * np.log(2)), 0.25), (s, got, ref)
 
 
 def test_one_mm_update_matches_the_reference_formula(shim):
@@ -70,15 +75,20 @@ def test_one_mm_update_matches_the_reference_formula(shim):
     a = a[: a.size // 2 * 2]
     y, out, out2 = y[: a.size], out[: a.size], out2[: a.size]
     shim.tclip_host_mm_update(a, y, out, a.size, float(special.digamma(s)))
-    shim.tclip_host_mm_update_pair(a, y, out2, a.size, float(special.digamma(s)))   # the kernel's packed shift-4 form
+    shim.tclip_host_mm_update_pair(a, y, out2, a.size, s)   # the kernel's packed shift-4 form (takes the row total)
     a64, y64 = torch.from_numpy(a).double(), torch.from_numpy(y).double()
     psi1 = torch.polygamma(0, a64 + 1)
     c = torch.where(a64 > 1e-11, (2 * (-torch.lgamma(a64 + 1) + psi1 * a64) / a64 ** 2).abs(),
                     torch.polygamma(1, torch.ones(1, dtype=torch.float64)))
     b = psi1 - special.digamma(s) - c * a64 - y64
     ref = ((-b + torch.sqrt(b * b + 4 * c)) / (2 * c)).numpy()
-    assert np.max(np.abs(out - ref) / ref) < 3e-6
-    assert np.max(np.abs(out2 - ref) / ref) < 3e-6
+    # away from the fixed point one step inherits the relative error of the curvature c = 2N/a^2, which is ~1e-4 just
+    # above the Taylor/Stirling switch (cancellation in N, see test_psi_and_curvature_numerator) and ~1e-6 elsewhere;
+    # the fixed point itself does not depend on c
+    for got in (out, out2):
+        err = np.abs(got - ref) / ref
+        assert err.max() < 3e-4
+        assert err[(a < 0.05) | (a > 1.0)].max() < 5e-6
 
 
 def test_mm_rows_track_the_oracle(shim):
@@ -86,7 +96,7 @@ def test_mm_rows_track_the_oracle(shim):
     rows, D, iters = 6, 40, 120
     y = torch.log(torch.softmax(2 * torch.randn(rows, 6, D, generator=g), -1)).mean(1).contiguous()
     a = np.ones((rows, D), dtype=np.float32)
-    shim.tclip_host_mm_rows(a, y.numpy(), rows, D, iters)
+    shim.tclip_host_mm_rows(a, y.numpy(), rows, D, D, iters)
     ref, done = R.mm_update_alpha(torch.ones(rows, D, dtype=torch.float64), y.double(), iters, check_every=0 or 10 ** 9)
     assert done == iters
     assert np.max(np.abs(a - ref.numpy()) / ref.numpy()) < 2e-5

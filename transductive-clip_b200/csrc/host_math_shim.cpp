@@ -31,13 +31,14 @@ void tclip_host_mm_update_pair(const float* a, const float* y, float* out, int n
   }
 }
 // rows x D MM iterations on the host: the CPU twin of the kernel's inner loop (row sum in double).
-void tclip_host_mm_rows(float* alpha, const float* y, int rows, int D, int iters) {
+// D = padded (even) row length, n_valid = real row length: like the kernel, padding never enters the row total.
+void tclip_host_mm_rows(float* alpha, const float* y, int rows, int D, int n_valid, int iters) {
   for (int r = 0; r < rows; ++r) {
     float* a = alpha + (long)r * D;
     const float* yy = y + (long)r * D;
     for (int it = 0; it < iters; ++it) {
       double s = 0.0;
-      for (int d = 0; d < D; ++d) s += (double)a[d];
+      for (int d = 0; d < n_valid; ++d) s += (double)a[d];
       const tclip::RowPsi rp = tclip::row_psi(s);
       for (int d = 0; d + 1 < D; d += 2) {  // the kernel's packed form (D even here)
         tclip::float2 r = tclip::mm_update_pair(tclip::make_float2(a[d], a[d + 1]), tclip::make_float2(-yy[d], -yy[d + 1]), rp);

@@ -14,7 +14,10 @@ inline void note_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_r
 // ---- Dirichlet MM M-step (dirichlet_mm.cu) --------------------------------------------------------------------
 constexpr int kMMThreads = 128;    // 4 warps = 4 rows per CTA
 constexpr int kMMMaxSlots = 32;    // register slots per lane => D <= 1024
-constexpr int kMMMinBlocks = 6;    // CTAs per SM the M-step kernel is compiled for (<= 80 registers per thread)
+#ifndef TCLIP_MM_MIN_BLOCKS
+#define TCLIP_MM_MIN_BLOCKS 6
+#endif
+constexpr int kMMMinBlocks = TCLIP_MM_MIN_BLOCKS;    // CTAs per SM the M-step kernel is compiled for (<= 80 registers per thread)
 
 struct MMState {          // lives in device memory; written only by the reset / decide kernels
   int done;               // 1 once the batch-global criterion fell below tol
