@@ -92,9 +92,12 @@ struct EmWorkspace {
   int* cache_valid;
   double2* cache;       // [rows, n_checks]
   double2* extra;       // [n_checks] sum of the cached terms over all dead rows
+  int* frozen;          // [rows] dead rows proven periodic (mm_chunk_kernel)
+  float* snap;          // [rows, D] periodicity snapshots
   int* list_live;
   int* list_new;
   int* counts;          // [0] = live rows, [1] = newly dead rows
+  unsigned long long* work_ctr;  // row-iterations executed by the free-running pass of this outer iteration
   size_t bytes;
 };
 
@@ -129,9 +132,12 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
     w.cache_valid = c.take<int>(rows);
     w.cache = c.take<double2>(rows * (nc ? nc : 1));
     w.extra = c.take<double2>(nc ? nc : 1);
+    w.frozen = c.take<int>(rows);
+    w.snap = c.take<float>(rows * D);
     w.list_live = c.take<int>(rows);
     w.list_new = c.take<int>(rows);
     w.counts = c.take<int>(4);
+    w.work_ctr = c.take<unsigned long long>(1);
   }
   w.bytes = c.off;
   return w;
@@ -167,8 +173,10 @@ __global__ void zero_int_kernel(int* p, long n) {
 //   live rows                      -> list_live   (iterated in the main loop)
 //   dead rows without a valid cache -> list_new    (full trajectory once, terms cached)
 __global__ void __launch_bounds__(1024)
-classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ list_live,
-                     int* __restrict__ list_new, int* __restrict__ counts, int rows) {
+classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ frozen,
+                     int* __restrict__ list_live, int* __restrict__ list_new, int* __restrict__ counts,
+                     unsigned long long* __restrict__ work_ctr, int rows) {
+  if (threadIdx.x == 0) *work_ctr = 0ull;
   __shared__ int s_live[1024], s_new[1024];
   const int per = (rows + 1023) / 1024;
   const int lo = threadIdx.x * per, hi = min(rows, lo + per);
@@ -196,6 +204,7 @@ classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid
     } else if (!cache_valid[r]) {
       list_new[pn++] = r;
       cache_valid[r] = 1;
+      frozen[r] = 0;
     }
   }
   if (threadIdx.x == 1023) {
@@ -243,13 +252,14 @@ __global__ void __launch_bounds__(256) count_live_kernel(const int* __restrict__
   if (threadIdx.x == 0) *out = red[0];
 }
 
-__global__ void record_work_kernel(const tclip::MMState* state, const int* counts, const int* n_live_dev, int rows,
-                                   int iter_mm, int* mm_iters, int* n_live, long long* mm_rows) {
+__global__ void record_work_kernel(const tclip::MMState* state, const int* counts, const unsigned long long* work_ctr,
+                                   const int* n_live_dev, int rows, int iter_mm, int* mm_iters, int* n_live,
+                                   long long* mm_rows) {
   const int done = state->iters_done;
   *mm_iters = done;
   *n_live = n_live_dev ? *n_live_dev : rows;
   if (mm_rows) {
-    if (counts) *mm_rows = (long long)counts[0] * done + (long long)counts[1] * iter_mm;
+    if (counts) *mm_rows = (long long)counts[0] * done + (long long)*work_ctr;  // live rows + free-running dead rows
     else *mm_rows = (long long)rows * done;
   }
 }
@@ -456,7 +466,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       l.n_blocks = tclip::mm_num_blocks(rows);
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nullptr, st));
     } else {
-      classify_rows_kernel<<<1, 1024, 0, st>>>(w.live, w.cache_valid, w.list_live, w.list_new, w.counts, rows);
+      classify_rows_kernel<<<1, 1024, 0, st>>>(w.live, w.cache_valid, w.frozen, w.list_live, w.list_new, w.counts, w.work_ctr, rows);
       tclip::note_launch();
       // newly dead rows: full trajectory from their kept row with y = -10, criterion terms cached per check
       tclip::MMLaunch d = l;
@@ -467,6 +477,9 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       d.state = w.state_free;
       d.row_cache = w.cache;
       d.n_checks = nc;
+      d.frozen = w.frozen;
+      d.snap = w.snap;
+      d.work_ctr = w.work_ctr;
       TCLIP_CUDA(tclip::mm_run(d, p->iter_mm, p->check_every, p->tol, nullptr, st));
       if (nc > 0) {
         sum_cache_kernel<<<nc, 256, 0, st>>>(w.live, w.cache, w.extra, rows, nc);
@@ -486,7 +499,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       tclip::note_launch();
       n_live_dev = p->n_live + it;
     }
-    record_work_kernel<<<1, 1, 0, st>>>(w.state, skip ? w.counts : nullptr, n_live_dev, rows, p->iter_mm,
+    record_work_kernel<<<1, 1, 0, st>>>(w.state, skip ? w.counts : nullptr, w.work_ctr, n_live_dev, rows, p->iter_mm,
                                          p->mm_iters + it, p->n_live + it, p->mm_rows ? p->mm_rows + it : nullptr);
     tclip::note_launch();
     // empty clusters keep their previous row; logged criterion (em_dirichlet.py:224-226,236-238)

@@ -55,19 +55,24 @@ __global__ void __launch_bounds__(kMMThreads, kMMMinBlocks)
 mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict__ y,
                 const int* __restrict__ row_list, const int* __restrict__ n_rows_dev, int n_rows_host, int D,
                 int n_iters, int emit_check, double2* __restrict__ partials, const MMState* __restrict__ state,
-                double2* __restrict__ row_cache, int n_checks, int check_idx) {
+                double2* __restrict__ row_cache, int n_checks, int check_idx, int* __restrict__ frozen,
+                float* __restrict__ snap, int snap_age, int snap_write, unsigned long long* __restrict__ work_ctr) {
   if (state->done) return;  // an earlier chunk met the batch-global criterion: the M-step is over
   extern __shared__ float2 ny_smem[];  // [warps per CTA][NP][32] pairs of -y
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int n_rows = n_rows_dev ? *n_rows_dev : n_rows_host;
   const int slot = blockIdx.x * (kMMThreads / 32) + warp;
-  const bool active = slot < n_rows;
+  bool active = slot < n_rows;
   double dsq = 0.0, asq = 0.0;
   long row = 0;
+  int period = 0;  // free-running rows: > 0 once this chunk proved the row's trajectory periodic (in chunks)
 
   if (active) {
     row = row_list ? row_list[slot] : slot;
+    if (frozen && frozen[row]) active = false;  // proven periodic earlier: its remaining check terms are already cached
+  }
+  if (active) {
     const float* ain = alpha_in + row * D;
     const float* yin = y + row * D;
     float* aout = alpha_out + row * D;
@@ -122,12 +127,51 @@ mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict
     }
     if (ok_x) aout[dx] = a[NP - 1].x;
     if (ok_y) aout[dy] = a[NP - 1].y;
+
+    if (work_ctr && lane == 0) atomicAdd(work_ctr, (unsigned long long)n_iters);  // row-iterations actually executed
+    if (frozen) {
+      // Free-running (dead-cluster) rows: the map "state at a chunk end -> state at the next chunk end" is a fixed
+      // deterministic function of the row (y = const, 50 iterations), so a chunk-end state that equals, bit for bit, the
+      // snapshot taken `snap_age` chunks ago proves the trajectory periodic with that period: every later check term
+      // repeats and the row need not be iterated again.  (fp32 MM trajectories settle on such orbits after ~50-200
+      // iterations; the reference would keep recomputing the same numbers.)
+      float* sn = snap + row * D;
+      bool same = snap_age > 0;
+      if (snap_age > 0) {
+#pragma unroll
+        for (int j = 0; j < NP - 1; ++j) {
+          same &= (sn[(2 * j) * 32 + lane] == a[j].x) & (sn[(2 * j + 1) * 32 + lane] == a[j].y);
+        }
+        if (ok_x) same &= sn[dx] == a[NP - 1].x;
+        if (ok_y) same &= sn[dy] == a[NP - 1].y;
+        same = __all_sync(0xffffffffu, same);
+      }
+      if (same) {
+        period = snap_age;
+      } else if (snap_write) {
+#pragma unroll
+        for (int j = 0; j < NP - 1; ++j) {
+          sn[(2 * j) * 32 + lane] = a[j].x;
+          sn[(2 * j + 1) * 32 + lane] = a[j].y;
+        }
+        if (ok_x) sn[dx] = a[NP - 1].x;
+        if (ok_y) sn[dy] = a[NP - 1].y;
+      }
+    }
   }
 
   if (emit_check == 2) {  // free-running rows: each row keeps its own terms
     dsq = warp_sum_f64(dsq);
     asq = warp_sum_f64(asq);
-    if (active && lane == 0) row_cache[row * n_checks + check_idx] = make_double2(dsq, asq);
+    if (active && lane == 0) {
+      double2* rc = row_cache + row * n_checks;
+      rc[check_idx] = make_double2(dsq, asq);
+      if (period > 0) {
+        // state_end(c) == state_end(c - period)  =>  terms(j) == terms(j - period) for every later check j
+        for (int j = check_idx + 1; j < n_checks; ++j) rc[j] = rc[j - period];
+        frozen[row] = period;
+      }
+    }
   } else if (emit_check) {
     __shared__ double2 red[kMMThreads / 32];
     dsq = warp_sum_f64(dsq);
@@ -195,13 +239,17 @@ __global__ void mm_reset_kernel(MMState* state) {
 }
 
 template <int NP>
-void launch_chunk(const MMLaunch& p, int n_iters, int emit_check, int check_idx, cudaStream_t st) {
+void launch_chunk(const MMLaunch& p, int n_iters, int emit_check, int check_idx, int snap_age, int snap_write,
+                  cudaStream_t st) {
   mm_chunk_kernel<NP><<<p.n_blocks, kMMThreads, (size_t)(kMMThreads / 32) * NP * 32 * sizeof(float2), st>>>(p.alpha_in, p.alpha_out, p.y, p.row_list, p.n_rows_dev,
                                                          p.n_rows, p.D, n_iters, emit_check, p.partials, p.state,
-                                                         p.row_cache, p.n_checks, check_idx);
+                                                         p.row_cache, p.n_checks, check_idx, p.frozen, p.snap,
+                                                         snap_age, snap_write, p.work_ctr);
 }
 
-using ChunkFn = void (*)(const MMLaunch&, int, int, int, cudaStream_t);
+constexpr int kSnapEvery = 3;  // detects chunk-periods 1..3, i.e. iteration periods dividing 50, 100 or 150
+
+using ChunkFn = void (*)(const MMLaunch&, int, int, int, int, int, cudaStream_t);
 
 template <int... I>
 constexpr auto make_table(std::integer_sequence<int, I...>) {
@@ -239,7 +287,11 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
     MMLaunch q = p;
     q.alpha_in = (start == 0) ? first_in : p.alpha_out;
     const bool free_run = p.row_cache != nullptr;
-    fn(q, end - start + 1, has_check ? (free_run ? 2 : 1) : 0, check_idx, st);
+    if (free_run && !has_check) break;  // dead rows: alpha is discarded, only check terms matter -> no tail chunk
+    // periodicity snapshots of free-running rows every kSnapEvery chunks, compared at every chunk end in between
+    const int snap_age = (free_run && p.frozen) ? (check_idx == 0 ? 0 : ((check_idx - 1) % kSnapEvery) + 1) : 0;
+    const int snap_write = (free_run && p.frozen && check_idx % kSnapEvery == 0) ? 1 : 0;
+    fn(q, end - start + 1, has_check ? (free_run ? 2 : 1) : 0, check_idx, snap_age, snap_write, st);
     const double2* extra = (has_check && extra_checks) ? extra_checks + check_idx : nullptr;
     mm_decide_kernel<<<1, 256, 0, st>>>(p.partials, p.n_blocks, extra, free_run ? 0 : has_check, end + 1, tol,
                                         p.state);

@@ -41,6 +41,9 @@ struct MMLaunch {
   // each row's own criterion terms per check point: row_cache[row * n_checks + check] = (||da||^2, ||a||^2)
   double2* row_cache;
   int n_checks;
+  int* frozen;            // free-running mode, optional: [rows_total] period (in chunks) of rows proven periodic, 0 = still iterating
+  float* snap;            // free-running mode: [rows_total, D] chunk-end snapshots used for the periodicity proof
+  unsigned long long* work_ctr;  // optional: += row-iterations executed (work accounting for the roofline)
 };
 
 int mm_max_dim();
