@@ -71,6 +71,7 @@ struct Carver {
   }
 };
 
+constexpr int kSparseCap = 4096; // row-wise E-step kernels handle up to this many live + newly dead rows
 constexpr int kMaxChecks = 64;  // cached criterion terms per dead row (iter_mm / check_every must stay below)
 
 struct EmWorkspace {
@@ -90,8 +91,11 @@ struct EmWorkspace {
   float* support_count;
   // skip-dead mode
   int* cache_valid;
-  double2* cache;       // [rows, n_checks]
+  double2* cache;       // [n_checks, rows]
   double2* extra;       // [n_checks] sum of the cached terms over all dead rows
+  float* l3;            // [T,n,K] persistent contraction log z . (alpha-1)^T (only live columns are recomputed)
+  int* dead_age;        // [rows] consecutive outer iterations the cluster has been empty
+  int* gate;            // {n_live, row cap}: device-side choice between dense and row-wise E-step kernels
   int* frozen;          // [rows] dead rows proven periodic (mm_chunk_kernel)
   float* snap;          // [rows, D] periodicity snapshots
   int* list_live;
@@ -132,6 +136,9 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
     w.cache_valid = c.take<int>(rows);
     w.cache = c.take<double2>(rows * (nc ? nc : 1));
     w.extra = c.take<double2>(nc ? nc : 1);
+    w.l3 = c.take<float>(T * n * K);
+    w.dead_age = c.take<int>(rows);
+    w.gate = c.take<int>(2);
     w.frozen = c.take<int>(rows);
     w.snap = c.take<float>(rows * D);
     w.list_live = c.take<int>(rows);
@@ -174,8 +181,9 @@ __global__ void zero_int_kernel(int* p, long n) {
 //   dead rows without a valid cache -> list_new    (full trajectory once, terms cached)
 __global__ void __launch_bounds__(1024)
 classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ frozen,
-                     int* __restrict__ list_live, int* __restrict__ list_new, int* __restrict__ counts,
-                     unsigned long long* __restrict__ work_ctr, int rows) {
+                     int* __restrict__ dead_age, int* __restrict__ list_live, int* __restrict__ list_new,
+                     int* __restrict__ counts, int* __restrict__ gate, int cap, unsigned long long* __restrict__ work_ctr,
+                     int rows) {
   if (threadIdx.x == 0) *work_ctr = 0ull;
   __shared__ int s_live[1024], s_new[1024];
   const int per = (rows + 1023) / 1024;
@@ -198,6 +206,7 @@ classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid
   }
   int pl = s_live[threadIdx.x] - nl, pn = s_new[threadIdx.x] - nn;
   for (int r = lo; r < hi; ++r) {
+    dead_age[r] = live[r] ? 0 : dead_age[r] + 1;
     if (live[r]) {
       list_live[pl++] = r;
       cache_valid[r] = 0;
@@ -210,6 +219,8 @@ classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid
   if (threadIdx.x == 1023) {
     counts[0] = s_live[1023];
     counts[1] = s_new[1023];
+    gate[0] = s_live[1023] + s_new[1023];  // rows the row-wise kernels would have to touch
+    gate[1] = cap;
   }
 }
 
@@ -222,7 +233,7 @@ sum_cache_kernel(const int* __restrict__ live, const double2* __restrict__ cache
   double2 acc = make_double2(0.0, 0.0);
   for (int r = threadIdx.x; r < rows; r += 256) {
     if (!live[r]) {
-      const double2 v = cache[(long)r * n_checks + c];
+      const double2 v = cache[(long)c * rows + r];
       acc.x += v.x;
       acc.y += v.y;
     }
@@ -332,7 +343,7 @@ int tclip_dirichlet_moments(const float* u, const float* logz, const float* cols
   if ((support_sum == nullptr) != (support_count == nullptr))
     return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_moments: support_sum and support_count go together");
   if (int rc = current_device_ok()) return rc;
-  TCLIP_CUDA(tclip::moments(u, logz, colsum, support_sum, support_count, y, T, n, K, D, (cudaStream_t)stream));
+  TCLIP_CUDA(tclip::moments(u, logz, colsum, support_sum, support_count, y, T, n, K, D, nullptr, (cudaStream_t)stream));
   return TCLIP_OK;
 }
 
@@ -383,7 +394,7 @@ int tclip_dirichlet_commit(float* alpha, const float* work, const int* live, voi
   if (!alpha || !work || !rowstat || !criterion || T < 1 || K < 1 || D < 1)
     return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_commit: bad arguments");
   if (int rc = current_device_ok()) return rc;
-  TCLIP_CUDA(tclip::commit(alpha, work, live, (double2*)rowstat, task_criterion, criterion, T, K, D,
+  TCLIP_CUDA(tclip::commit(alpha, work, live, nullptr, (double2*)rowstat, task_criterion, criterion, T, K, D,
                            (cudaStream_t)stream));
   return TCLIP_OK;
 }
@@ -393,7 +404,8 @@ int tclip_dirichlet_estep(const float* alpha, const float* logz, const float* v,
   if (!alpha || !logz || !v || !norm || !u || T < 1 || n < 1 || K < 1 || D < 1)
     return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_estep: bad arguments");
   if (int rc = current_device_ok()) return rc;
-  TCLIP_CUDA(tclip::estep(alpha, logz, v, lambd, (double*)norm, u, labels, T, n, K, D, hard, (cudaStream_t)stream));
+  TCLIP_CUDA(tclip::estep(alpha, logz, v, lambd, (double*)norm, nullptr, u, labels, T, n, K, D, hard, nullptr, nullptr,
+                          (cudaStream_t)stream));
   return TCLIP_OK;
 }
 
@@ -444,14 +456,31 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
   }
   if (skip) {
     zero_int_kernel<<<(rows + 255) / 256, 256, 0, st>>>(w.cache_valid, rows);
-    tclip::note_launch();
+    zero_int_kernel<<<(rows + 255) / 256, 256, 0, st>>>(w.dead_age, rows);
+    tclip::note_launch(2);
     TCLIP_CUDA(cudaMemsetAsync(w.state_free, 0, sizeof(tclip::MMState), st));
   }
 
   for (int it = 0; it < p->iters; ++it) {
     // cluster sizes of the current u, live mask, and v (v_update uses the same u, em_dirichlet.py:230)
     TCLIP_CUDA(tclip::colsum_v(p->u, w.colsum, p->v, few ? nullptr : w.live, T, n, K, st));
-    TCLIP_CUDA(tclip::moments(p->u, w.logz, w.colsum, w.support_sum, w.support_count, w.y, T, n, K, D, st));
+    // skip-dead: row lists first (moments, M-step and E-step all work from them); from the second outer iteration on the
+    // E-step side touches live / newly dead rows only, everything of an empty cluster carries over unchanged
+    tclip::SparseRows sp{};
+    const bool sparse = skip && it > 0;
+    if (skip) {
+      classify_rows_kernel<<<1, 1024, 0, st>>>(w.live, w.cache_valid, w.frozen, w.dead_age, w.list_live, w.list_new,
+                                               w.counts, w.gate, kSparseCap, w.work_ctr, rows);
+      tclip::note_launch();
+      sp.rows_live = w.list_live;
+      sp.n_live = w.counts;
+      sp.rows_new = w.list_new;
+      sp.n_new = w.counts + 1;
+      sp.gate = w.gate;
+      sp.cap = kSparseCap;
+    }
+    TCLIP_CUDA(tclip::moments(p->u, w.logz, w.colsum, w.support_sum, w.support_count, w.y, T, n, K, D,
+                              sparse ? &sp : nullptr, st));
 
     if (p->mm_events && p->mm_events[2 * it]) TCLIP_CUDA(cudaEventRecord((cudaEvent_t)p->mm_events[2 * it], st));
     tclip::MMLaunch l{};
@@ -466,8 +495,6 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       l.n_blocks = tclip::mm_num_blocks(rows);
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nullptr, st));
     } else {
-      classify_rows_kernel<<<1, 1024, 0, st>>>(w.live, w.cache_valid, w.frozen, w.list_live, w.list_new, w.counts, w.work_ctr, rows);
-      tclip::note_launch();
       // newly dead rows: full trajectory from their kept row with y = -10, criterion terms cached per check
       tclip::MMLaunch d = l;
       d.row_list = w.list_new;
@@ -477,6 +504,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       d.state = w.state_free;
       d.row_cache = w.cache;
       d.n_checks = nc;
+      d.rows_total = rows;
       d.frozen = w.frozen;
       d.snap = w.snap;
       d.work_ctr = w.work_ctr;
@@ -503,10 +531,11 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
                                          p->mm_iters + it, p->n_live + it, p->mm_rows ? p->mm_rows + it : nullptr);
     tclip::note_launch();
     // empty clusters keep their previous row; logged criterion (em_dirichlet.py:224-226,236-238)
-    TCLIP_CUDA(tclip::commit(p->alpha, w.work, few ? nullptr : w.live, w.rowstat, w.task_crit, p->criterions + it, T,
-                             K, D, st));
+    TCLIP_CUDA(tclip::commit(p->alpha, w.work, few ? nullptr : w.live, skip ? w.dead_age : nullptr, w.rowstat,
+                             w.task_crit, p->criterions + it, T, K, D, st));
     // u <- softmax(logits + lambda v / n) [-> one-hot]
-    TCLIP_CUDA(tclip::estep(p->alpha, w.logz, p->v, p->lambd, w.norm, p->u, p->labels, T, n, K, D, p->hard, st));
+    TCLIP_CUDA(tclip::estep(p->alpha, w.logz, p->v, p->lambd, w.norm, skip ? w.l3 : nullptr, p->u, p->labels, T, n, K, D,
+                            p->hard, sparse ? w.live : nullptr, sparse ? &sp : nullptr, st));
     if (p->iter_events && p->iter_events[it]) TCLIP_CUDA(cudaEventRecord((cudaEvent_t)p->iter_events[it], st));
   }
   TCLIP_CUDA(cudaGetLastError());

@@ -63,10 +63,15 @@ __global__ void colsum_v_kernel(const float* __restrict__ u, float* __restrict__
 constexpr int kMomTile = 64;
 constexpr int kMomStage = 16;
 
+// `gate` (optional, device): {n_live, row cap}; the dense kernel runs iff n_live > cap, the row-wise one otherwise, so
+// the host can enqueue both without knowing how many clusters are alive.
+__device__ __forceinline__ bool dense_selected(const int* gate) { return gate == nullptr || gate[0] > gate[1]; }
+
 __global__ void __launch_bounds__(256)
 moments_kernel(const float* __restrict__ u, const float* __restrict__ logz, const float* __restrict__ colsum,
                const float* __restrict__ support_sum, const float* __restrict__ support_count,
-               float* __restrict__ y, int n, int K, int D, int few_shot) {
+               float* __restrict__ y, int n, int K, int D, int few_shot, const int* __restrict__ gate) {
+  if (!dense_selected(gate)) return;
   __shared__ float us[kMomStage][kMomTile + 4];
   __shared__ float ls[kMomStage][kMomTile + 4];
   const int t = blockIdx.z;
@@ -123,6 +128,34 @@ moments_kernel(const float* __restrict__ u, const float* __restrict__ logz, cons
   }
 }
 
+// Row-wise form for the skip-dead schedule: one CTA per row of `rows` (live rows: the moments; newly dead rows: the -10
+// fill they start their trajectory from).  Each output is the same sequential fma chain over n as in moments_kernel, so
+// both forms give bit-identical y.
+__global__ void __launch_bounds__(256)
+moments_rows_kernel(const float* __restrict__ u, const float* __restrict__ logz, const float* __restrict__ colsum,
+                    float* __restrict__ y, const int* __restrict__ rows, const int* __restrict__ n_rows, int fill_only,
+                    int n, int K, int D, const int* __restrict__ gate) {
+  if (dense_selected(gate)) return;
+  if ((int)blockIdx.x >= *n_rows) return;
+  const int row = rows[blockIdx.x];
+  float* out = y + (long)row * D;
+  if (fill_only) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = -10.0f;
+    return;
+  }
+  extern __shared__ float ucol[];  // [n] responsibilities of this cluster
+  const int t = row / K, k = row % K;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ucol[i] = u[((long)t * n + i) * K + k];
+  __syncthreads();
+  const float cs = colsum[row];
+  const float* lb = logz + (long)t * n * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.0f;
+    for (int i = 0; i < n; ++i) acc = fmaf(ucol[i], lb[(long)i * D + d], acc);
+    out[d] = cs > kEps ? acc / fmaxf(cs, kEps) : -10.0f;
+  }
+}
+
 // ---- few-shot support statistics (iteration invariant): per-class count and per-class sum of log-features -------
 __global__ void support_stats_kernel(const float* __restrict__ log_support, const long long* __restrict__ y_s,
                                      float* __restrict__ support_sum, float* __restrict__ support_count, int S,
@@ -158,10 +191,13 @@ __global__ void support_stats_kernel(const float* __restrict__ log_support, cons
 // rowstat[row] = (||old - new||^2, ||old||^2) over the row; alpha[row] <- work[row] when the cluster is live.
 __global__ void __launch_bounds__(128)
 commit_kernel(float* __restrict__ alpha, const float* __restrict__ work, const int* __restrict__ live,
-              double2* __restrict__ rowstat, int rows, int D) {
+              const int* __restrict__ dead_age, double2* __restrict__ rowstat, int rows, int D) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  // a cluster that was already empty in the previous outer iteration has the same alpha row as then: its
+  // (0, ||alpha||^2) entry written by that commit is still right
+  if (dead_age && dead_age[row] >= 2) return;
   const bool lv = live ? live[row] != 0 : true;
   float* a = alpha + (long)row * D;
   const float* w = work + (long)row * D;
@@ -178,48 +214,50 @@ commit_kernel(float* __restrict__ alpha, const float* __restrict__ work, const i
   if (lane == 0) rowstat[row] = make_double2(ds, os);
 }
 
-// criterion[t] = ||alpha_old - alpha||_F / ||alpha_old||_F per task, then the mean over tasks (one CTA, fixed order)
+// criterion[t] = ||alpha_old - alpha||_F / ||alpha_old||_F: one CTA per task (fixed reduction tree), then the mean over
+// tasks accumulated in task order by one thread
 __global__ void __launch_bounds__(256)
-criterion_kernel(const double2* __restrict__ rowstat, float* __restrict__ task_crit, float* __restrict__ crit_out,
-                 int T, int K) {
+criterion_task_kernel(const double2* __restrict__ rowstat, float* __restrict__ task_crit, int K) {
   __shared__ double red[256];
-  double total = 0.0;
-  for (int t = 0; t < T; ++t) {
-    double dx = 0.0, dy = 0.0;
-    for (int k = threadIdx.x; k < K; k += 256) {
-      const double2 r = rowstat[(long)t * K + k];
-      dx += r.x;
-      dy += r.y;
-    }
-    red[threadIdx.x] = dx;
-    __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-      if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
-      __syncthreads();
-    }
-    const double num = red[0];
-    __syncthreads();
-    red[threadIdx.x] = dy;
-    __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-      if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
-      __syncthreads();
-    }
-    const double den = red[0];
-    __syncthreads();
-    const float c = sqrtf((float)num) / sqrtf((float)den);
-    if (threadIdx.x == 0 && task_crit) task_crit[t] = c;
-    total += (double)c;
+  const int t = blockIdx.x;
+  double dx = 0.0, dy = 0.0;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const double2 r = rowstat[(long)t * K + k];
+    dx += r.x;
+    dy += r.y;
   }
-  if (threadIdx.x == 0) *crit_out = (float)(total / (double)T);
+  red[threadIdx.x] = dx;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  const double num = red[0];
+  __syncthreads();
+  red[threadIdx.x] = dy;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  const double den = red[0];
+  if (threadIdx.x == 0) task_crit[t] = sqrtf((float)num) / sqrtf((float)den);
+}
+
+__global__ void criterion_mean_kernel(const float* __restrict__ task_crit, float* __restrict__ crit_out, int T) {
+  double total = 0.0;
+  for (int t = 0; t < T; ++t) total += (double)task_crit[t];
+  *crit_out = (float)(total / (double)T);
 }
 
 // ---- Dirichlet log-normaliser: norm[t,k] = lnGamma(sum_d a) - sum_d lnGamma(a), float64, one warp per row --------
 __global__ void __launch_bounds__(128)
-lognorm_kernel(const float* __restrict__ alpha, double* __restrict__ norm, int rows, int D) {
+lognorm_kernel(const float* __restrict__ alpha, double* __restrict__ norm, const int* __restrict__ live, int rows,
+               int D) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (live && !live[row]) return;  // empty cluster: alpha row unchanged, norm[row] of the previous E-step still holds
   const float* a = alpha + (long)row * D;
   double s = 0.0, lg = 0.0;
   for (int d = lane; d < D; d += 32) {
@@ -240,7 +278,8 @@ constexpr int kLgBK = 16;
 
 __global__ void __launch_bounds__(256)
 logits_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, float* __restrict__ l3, int n, int K,
-              int D) {
+              int D, const int* __restrict__ gate) {
+  if (!dense_selected(gate)) return;
   __shared__ float as[kLgBK][kLgTile + 4];  // logz tile, transposed: [d][n]
   __shared__ float bs[kLgBK][kLgTile + 4];  // (alpha-1) tile, transposed: [d][k]
   const int t = blockIdx.z;
@@ -287,6 +326,38 @@ logits_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, f
       const int k = k0 + tx * 4 + j;
       if (k < K) l3[((long)t * n + nn) * K + k] = acc[i][j];
     }
+  }
+}
+
+// Row-wise form for the skip-dead schedule: only the columns of live clusters change between E-steps (an empty cluster
+// keeps its alpha row, hence its column of l3), so one CTA per live row recomputes l3[t, :, k]; thread = query n, with the
+// same blocked fma order as logits_kernel => bit-identical values.
+__global__ void __launch_bounds__(128)
+logits_rows_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, float* __restrict__ l3,
+                   const int* __restrict__ rows, const int* __restrict__ n_rows, int n, int K, int D,
+                   const int* __restrict__ gate) {
+  if (dense_selected(gate)) return;
+  if ((int)blockIdx.x >= *n_rows) return;
+  extern __shared__ float am1[];  // [D rounded up to kLgBK] alpha - 1, zero padded
+  const int row = rows[blockIdx.x];
+  const int t = row / K, k = row % K;
+  const int Dp = (D + kLgBK - 1) / kLgBK * kLgBK;
+  const float* a = alpha + (long)row * D;
+  for (int d = threadIdx.x; d < Dp; d += blockDim.x) am1[d] = d < D ? a[d] - 1.0f : 0.0f;
+  __syncthreads();
+  for (int nn = threadIdx.x; nn < n; nn += blockDim.x) {
+    const float* z = logz + ((long)t * n + nn) * D;
+    float acc = 0.0f;
+    for (int d0 = 0; d0 < Dp; d0 += kLgBK) {
+      float part = 0.0f;
+#pragma unroll
+      for (int c = 0; c < kLgBK; ++c) {
+        const int d = d0 + c;
+        part = fmaf(d < D ? z[d] : 0.0f, am1[d], part);
+      }
+      acc += part;
+    }
+    l3[((long)t * n + nn) * K + k] = acc;
   }
 }
 
@@ -431,11 +502,19 @@ cudaError_t colsum_v(const float* u, float* colsum, float* v, int* live, int T, 
 }
 
 cudaError_t moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
-                    const float* support_count, float* y, int T, int n, int K, int D, cudaStream_t st) {
+                    const float* support_count, float* y, int T, int n, int K, int D, const SparseRows* sp,
+                    cudaStream_t st) {
   const int few = support_sum != nullptr;
+  const int* gate = sp ? sp->gate : nullptr;
   moments_kernel<<<dim3((D + kMomTile - 1) / kMomTile, (K + kMomTile - 1) / kMomTile, T), 256, 0, st>>>(
-      u, logz, colsum, support_sum, support_count, y, n, K, D, few);
+      u, logz, colsum, support_sum, support_count, y, n, K, D, few, gate);
   note_launch(1);
+  if (sp) {
+    moments_rows_kernel<<<sp->cap, 256, n * sizeof(float), st>>>(u, logz, colsum, y, sp->rows_live, sp->n_live, 0, n, K, D,
+                                                               gate);
+    moments_rows_kernel<<<sp->cap, 256, 0, st>>>(u, logz, colsum, y, sp->rows_new, sp->n_new, 1, n, K, D, gate);
+    note_launch(2);
+  }
   return cudaGetLastError();
 }
 
@@ -446,24 +525,37 @@ cudaError_t support_stats(const float* log_support, const long long* y_s, float*
   return cudaGetLastError();
 }
 
-cudaError_t commit(float* alpha, const float* work, const int* live, double2* rowstat, float* task_crit,
-                   float* crit_out, int T, int K, int D, cudaStream_t st) {
+cudaError_t commit(float* alpha, const float* work, const int* live, const int* dead_age, double2* rowstat,
+                   float* task_crit, float* crit_out, int T, int K, int D, cudaStream_t st) {
   const int rows = T * K;
-  commit_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, work, live, rowstat, rows, D);
-  criterion_kernel<<<1, 256, 0, st>>>(rowstat, task_crit, crit_out, T, K);
-  note_launch(2);
+  commit_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, work, live, dead_age, rowstat, rows, D);
+  criterion_task_kernel<<<T, 256, 0, st>>>(rowstat, task_crit, K);
+  criterion_mean_kernel<<<1, 1, 0, st>>>(task_crit, crit_out, T);
+  note_launch(3);
   return cudaGetLastError();
 }
 
-cudaError_t estep(const float* alpha, const float* logz, const float* v, float lambd, double* norm, float* u,
-                  int* labels, int T, int n, int K, int D, int hard, cudaStream_t st) {
+// l3 == nullptr: the contraction is written into u and soft-maxed in place (stage entry point).  With a persistent l3
+// buffer and `sp`, only live clusters are recomputed (norm and l3 of empty clusters carry over from the last E-step).
+cudaError_t estep(const float* alpha, const float* logz, const float* v, float lambd, double* norm, float* l3, float* u,
+                  int* labels, int T, int n, int K, int D, int hard, const int* live, const SparseRows* sp,
+                  cudaStream_t st) {
   const int rows = T * K;
-  lognorm_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, norm, rows, D);
-  logits_kernel<<<dim3((K + kLgTile - 1) / kLgTile, (n + kLgTile - 1) / kLgTile, T), 256, 0, st>>>(logz, alpha, u, n,
-                                                                                                  K, D);
+  float* dst = l3 ? l3 : u;
+  const int* gate = (sp && l3) ? sp->gate : nullptr;
+  lognorm_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, norm, l3 ? live : nullptr, rows, D);
+  logits_kernel<<<dim3((K + kLgTile - 1) / kLgTile, (n + kLgTile - 1) / kLgTile, T), 256, 0, st>>>(logz, alpha, dst, n,
+                                                                                                  K, D, gate);
+  note_launch(2);
+  if (gate) {
+    const int Dp = (D + kLgBK - 1) / kLgBK * kLgBK;
+    logits_rows_kernel<<<sp->cap, 128, Dp * sizeof(float), st>>>(logz, alpha, dst, sp->rows_live, sp->n_live, n, K, D,
+                                                                gate);
+    note_launch(1);
+  }
   const int qrows = T * n;
-  softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(u, norm, v, lambd, u, labels, qrows, n, K, hard);
-  note_launch(3);
+  softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard);
+  note_launch(1);
   return cudaGetLastError();
 }
 

@@ -56,7 +56,8 @@ mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict
                 const int* __restrict__ row_list, const int* __restrict__ n_rows_dev, int n_rows_host, int D,
                 int n_iters, int emit_check, double2* __restrict__ partials, const MMState* __restrict__ state,
                 double2* __restrict__ row_cache, int n_checks, int check_idx, int* __restrict__ frozen,
-                float* __restrict__ snap, int snap_age, int snap_write, unsigned long long* __restrict__ work_ctr) {
+                float* __restrict__ snap, int snap_age, int snap_write, unsigned long long* __restrict__ work_ctr,
+                long cache_stride) {
   if (state->done) return;  // an earlier chunk met the batch-global criterion: the M-step is over
   extern __shared__ float2 ny_smem[];  // [warps per CTA][NP][32] pairs of -y
   const int lane = threadIdx.x & 31;
@@ -164,11 +165,12 @@ mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict
     dsq = warp_sum_f64(dsq);
     asq = warp_sum_f64(asq);
     if (active && lane == 0) {
-      double2* rc = row_cache + row * n_checks;
-      rc[check_idx] = make_double2(dsq, asq);
+      double2* rc = row_cache + row;  // [n_checks][rows_total] so that the per-check sums read coalesced
+      const long rs = cache_stride;
+      rc[check_idx * rs] = make_double2(dsq, asq);
       if (period > 0) {
         // state_end(c) == state_end(c - period)  =>  terms(j) == terms(j - period) for every later check j
-        for (int j = check_idx + 1; j < n_checks; ++j) rc[j] = rc[j - period];
+        for (int j = check_idx + 1; j < n_checks; ++j) rc[j * rs] = rc[(j - period) * rs];
         frozen[row] = period;
       }
     }
@@ -244,7 +246,7 @@ void launch_chunk(const MMLaunch& p, int n_iters, int emit_check, int check_idx,
   mm_chunk_kernel<NP><<<p.n_blocks, kMMThreads, (size_t)(kMMThreads / 32) * NP * 32 * sizeof(float2), st>>>(p.alpha_in, p.alpha_out, p.y, p.row_list, p.n_rows_dev,
                                                          p.n_rows, p.D, n_iters, emit_check, p.partials, p.state,
                                                          p.row_cache, p.n_checks, check_idx, p.frozen, p.snap,
-                                                         snap_age, snap_write, p.work_ctr);
+                                                         snap_age, snap_write, p.work_ctr, (long)p.rows_total);
 }
 
 constexpr int kSnapEvery = 3;  // detects chunk-periods 1..3, i.e. iteration periods dividing 50, 100 or 150

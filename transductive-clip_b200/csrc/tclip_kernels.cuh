@@ -38,9 +38,10 @@ struct MMLaunch {
   double2* partials;      // [n_blocks] scratch for the criterion
   MMState* state;
   // "free-running" mode (row_cache != nullptr): ignore the batch-global exit, run all iter_mm iterations and store
-  // each row's own criterion terms per check point: row_cache[row * n_checks + check] = (||da||^2, ||a||^2)
+  // each row's own criterion terms per check point: row_cache[check * rows_total + row] = (||da||^2, ||a||^2)
   double2* row_cache;
   int n_checks;
+  int rows_total;         // free-running mode: leading dimension of row_cache ([n_checks][rows_total])
   int* frozen;            // free-running mode, optional: [rows_total] period (in chunks) of rows proven periodic, 0 = still iterating
   float* snap;            // free-running mode: [rows_total, D] chunk-end snapshots used for the periodicity proof
   unsigned long long* work_ctr;  // optional: += row-iterations executed (work accounting for the roofline)
@@ -53,14 +54,26 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
 // ---- the rest of the Dirichlet EM loop (dirichlet_estep.cu) ---------------------------------------------------------
 cudaError_t log_features(const float* x, float* out, long count, cudaStream_t st);
 cudaError_t colsum_v(const float* u, float* colsum, float* v, int* live, int T, int n, int K, cudaStream_t st);
+// Skip-dead schedule: row lists built on the device by classify_rows_kernel (capi.cu).  gate = {n_live, cap}: kernels
+// take the row-wise form iff n_live <= cap, decided on the device.
+struct SparseRows {
+  const int* rows_live;
+  const int* n_live;
+  const int* rows_new;
+  const int* n_new;
+  const int* gate;
+  int cap;
+};
 cudaError_t moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
-                    const float* support_count, float* y, int T, int n, int K, int D, cudaStream_t st);
+                    const float* support_count, float* y, int T, int n, int K, int D, const SparseRows* sp,
+                    cudaStream_t st);
 cudaError_t support_stats(const float* log_support, const long long* y_s, float* support_sum, float* support_count,
                           int T, int S, int K, int D, cudaStream_t st);
-cudaError_t commit(float* alpha, const float* work, const int* live, double2* rowstat, float* task_crit,
-                   float* crit_out, int T, int K, int D, cudaStream_t st);
-cudaError_t estep(const float* alpha, const float* logz, const float* v, float lambd, double* norm, float* u,
-                  int* labels, int T, int n, int K, int D, int hard, cudaStream_t st);
+cudaError_t commit(float* alpha, const float* work, const int* live, const int* dead_age, double2* rowstat,
+                   float* task_crit, float* crit_out, int T, int K, int D, cudaStream_t st);
+cudaError_t estep(const float* alpha, const float* logz, const float* v, float lambd, double* norm, float* l3, float* u,
+                  int* labels, int T, int n, int K, int D, int hard, const int* live, const SparseRows* sp,
+                  cudaStream_t st);
 cudaError_t cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
                                int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
                                cudaStream_t st);
