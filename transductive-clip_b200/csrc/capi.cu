@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <string>
 
 #include "../../include/tclip_b200.h"
@@ -71,6 +72,7 @@ struct Carver {
   }
 };
 
+constexpr int kSplitCap = 1480;   // the few-rows M-step kernel (one row per CTA) handles up to this many live rows
 constexpr int kSparseCap = 4096; // row-wise E-step kernels handle up to this many live + newly dead rows
 constexpr int kMaxChecks = 64;  // cached criterion terms per dead row (iter_mm / check_every must stay below)
 
@@ -96,6 +98,7 @@ struct EmWorkspace {
   float* l3;            // [T,n,K] persistent contraction log z . (alpha-1)^T (only live columns are recomputed)
   int* dead_age;        // [rows] consecutive outer iterations the cluster has been empty
   int* gate;            // {n_live, row cap}: device-side choice between dense and row-wise E-step kernels
+  int* split_gate;      // {n_live, kSplitCap}: device-side choice of the few-rows M-step kernel
   int* frozen;          // [rows] dead rows proven periodic (mm_chunk_kernel)
   float* snap;          // [rows, D] periodicity snapshots
   int* list_live;
@@ -122,7 +125,7 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
   w.live = c.take<int>(rows);
   w.norm = c.take<double>(rows);
   w.rowstat = c.take<double2>(rows);
-  w.partials = c.take<double2>(tclip::mm_num_blocks((int)rows));
+  w.partials = c.take<double2>(std::max(tclip::mm_num_blocks((int)rows), kSplitCap));
   w.state = c.take<tclip::MMState>(1);
   w.state_free = c.take<tclip::MMState>(1);
   w.task_crit = c.take<float>(T);
@@ -139,6 +142,7 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
     w.l3 = c.take<float>(T * n * K);
     w.dead_age = c.take<int>(rows);
     w.gate = c.take<int>(2);
+    w.split_gate = c.take<int>(2);
     w.frozen = c.take<int>(rows);
     w.snap = c.take<float>(rows * D);
     w.list_live = c.take<int>(rows);
@@ -182,8 +186,8 @@ __global__ void zero_int_kernel(int* p, long n) {
 __global__ void __launch_bounds__(1024)
 classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ frozen,
                      int* __restrict__ dead_age, int* __restrict__ list_live, int* __restrict__ list_new,
-                     int* __restrict__ counts, int* __restrict__ gate, int cap, unsigned long long* __restrict__ work_ctr,
-                     int rows) {
+                     int* __restrict__ counts, int* __restrict__ gate, int cap, int* __restrict__ split_gate,
+                     int split_cap, unsigned long long* __restrict__ work_ctr, int rows) {
   if (threadIdx.x == 0) *work_ctr = 0ull;
   __shared__ int s_live[1024], s_new[1024];
   const int per = (rows + 1023) / 1024;
@@ -221,6 +225,8 @@ classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid
     counts[1] = s_new[1023];
     gate[0] = s_live[1023] + s_new[1023];  // rows the row-wise kernels would have to touch
     gate[1] = cap;
+    split_gate[0] = s_live[1023];
+    split_gate[1] = split_cap;
   }
 }
 
@@ -470,7 +476,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     const bool sparse = skip && it > 0;
     if (skip) {
       classify_rows_kernel<<<1, 1024, 0, st>>>(w.live, w.cache_valid, w.frozen, w.dead_age, w.list_live, w.list_new,
-                                               w.counts, w.gate, kSparseCap, w.work_ctr, rows);
+                                               w.counts, w.gate, kSparseCap, w.split_gate, kSplitCap, w.work_ctr, rows);
       tclip::note_launch();
       sp.rows_live = w.list_live;
       sp.n_live = w.counts;
@@ -515,6 +521,8 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       }
       l.row_list = w.list_live;
       l.n_rows_dev = w.counts;
+      l.split_gate = w.split_gate;
+      l.split_cap = kSplitCap;
       l.n_rows = rows;
       l.n_blocks = tclip::mm_num_blocks(rows);
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nc > 0 ? w.extra : nullptr, st));

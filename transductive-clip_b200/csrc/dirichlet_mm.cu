@@ -5,15 +5,22 @@
 // of the reference's run time.
 //
 // Layout: alpha, y are [rows, D] float32 row-major, rows = n_task * n_class, D = feature dim (<= 1024).
-// One warp owns one row: element d lives in lane d % 32, register slot d / 32, so a row of D <= 1024 floats stays
-// in registers for a whole chunk of MM iterations; HBM sees 12 B per element per chunk (read alpha, read y, write
-// alpha), i.e. the kernel is FP32/MUFU-issue bound, not memory bound (DESIGN.md "MM kernel").
+// One warp owns one row: element d lives in lane d % 32, register pair (d / 32) / 2, so a row of D <= 1024 floats stays
+// in registers for a whole chunk of MM iterations (-y, read-only, in the warp's slice of shared memory); HBM sees 12 B
+// per element per chunk (read alpha, read y, write alpha): the kernel is bound by the SM issue rate, not by memory
+// (DESIGN.md §3.1).  The grid is persistent (<= kMMMinBlocks CTAs per SM), warps stride over the rows.
 //
 // The reference's early exit is *batch-global*: at l in {50, 100, ...} (l > 0) it stops iff
 // ||a_new - a||^2 / ||a||^2 < 1e-11 over the whole [n_task, K, D] tensor.  The iteration loop is therefore cut into
-// chunks that end exactly at those l: a chunk kernel emits per-block partial sums of the two norms for its last
-// iteration, a 1-block decide kernel folds them in a fixed order (deterministic) and raises a device-side `done`
-// flag that later chunk kernels test on entry.  No host synchronisation anywhere in the M-step.
+// chunks that end exactly at those l: a chunk kernel emits per-CTA partial sums of the two norms for its last
+// iteration, the last CTA to finish (atomic ticket) folds them in a fixed order (deterministic) and raises a
+// device-side `done` flag that later chunk kernels test on entry.  No host synchronisation anywhere in the M-step.
+//
+// Two more forms of the same arithmetic:
+//   * free-running rows (FR = true; the empty clusters of the skip-dead schedule): ignore the exit flag, store each
+//     row's own criterion terms per check point, and stop iterating a row as soon as its fp32 trajectory is *proven*
+//     periodic (bit-exact state comparison) — the remaining terms then follow by periodic extension;
+//   * mm_chunk_split_kernel: one row per CTA for the few live rows of that schedule.
 #include <cuda_runtime.h>
 
 #include <array>
@@ -47,44 +54,114 @@ __device__ __forceinline__ float lane_tree_sum(const float2 (&a)[NP], float2 tai
   return t[0].x + t[0].y;
 }
 
+// What a chunk kernel needs besides the row data.
+struct ChunkArgs {
+  const float* alpha_in;
+  float* alpha_out;
+  const float* y;
+  const int* row_list;     // optional indirection
+  const int* n_rows_dev;   // optional device-side row count
+  int n_rows_host;
+  int D;
+  int n_iters;             // MM iterations of this chunk
+  int has_check;           // the last iteration of this chunk is a check point
+  int iters_cum;           // iterations executed once this chunk is done
+  float tol;
+  double2* partials;       // [gridDim.x]
+  MMState* state;
+  const double2* extra;    // optional: criterion terms of rows that are not iterated (cached dead rows)
+  const int* split_gate;   // optional: {n_rows, cap}; n_rows <= cap => mm_chunk_split_kernel runs instead
+  // free-running rows only
+  double2* row_cache;      // [n_checks][rows_total]
+  int n_checks;
+  int check_idx;
+  long rows_total;
+  int* frozen;
+  float* snap;
+  int snap_age;
+  int snap_write;
+  unsigned long long* work_ctr;
+};
+
+// The last CTA of a chunk to finish folds the per-CTA partials (fixed order => reproducible), applies the reference's
+// test `criterion < tol` (false for NaN, so a NaN never stops the loop) and keeps the executed-iteration count.
+template <int THREADS>
+__device__ __forceinline__ void finish_chunk(const ChunkArgs& g, double2 cta_terms, double2* red /* [THREADS] smem */) {
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    if (g.has_check) g.partials[blockIdx.x] = cta_terms;
+    __threadfence();
+    const unsigned ticket = atomicAdd(&g.state->ticket, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double2 acc = make_double2(0.0, 0.0);
+  if (g.has_check) {
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) {
+      const double2 p = g.partials[i];
+      acc.x += p.x;
+      acc.y += p.y;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = THREADS / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      red[threadIdx.x].x += red[threadIdx.x + w].x;
+      red[threadIdx.x].y += red[threadIdx.x + w].y;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    g.state->ticket = 0u;
+    g.state->iters_done = g.iters_cum;
+    if (g.has_check) {
+      double num = red[0].x, den = red[0].y;
+      if (g.extra) {
+        num += g.extra->x;
+        den += g.extra->y;
+      }
+      g.state->last_num = num;
+      g.state->last_den = den;
+      // the reference forms the ratio of two float32 squared norms; do the comparison on the float32 ratio too
+      const float crit = (float)num / (float)den;
+      if (crit < g.tol) g.state->done = 1;
+    }
+  }
+}
+
 // NP = ceil(D / 64) register pairs per lane: pair j holds elements d = (2j) * 32 + lane and (2j + 1) * 32 + lane, so
 // every global access is a coalesced 128-byte row segment.  Only the last pair can hold padding (masked in the sums).
 // All add / mul / fma work is issued as packed FFMA2 / FMUL2 / FADD2 (tclip_math.cuh: mm_update_pair).
-template <int NP>
+template <int NP, bool FR>
 __global__ void __launch_bounds__(kMMThreads, kMMMinBlocks)
-mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict__ y,
-                const int* __restrict__ row_list, const int* __restrict__ n_rows_dev, int n_rows_host, int D,
-                int n_iters, int emit_check, double2* __restrict__ partials, const MMState* __restrict__ state,
-                double2* __restrict__ row_cache, int n_checks, int check_idx, int* __restrict__ frozen,
-                float* __restrict__ snap, int snap_age, int snap_write, unsigned long long* __restrict__ work_ctr,
-                long cache_stride) {
-  if (state->done) return;  // an earlier chunk met the batch-global criterion: the M-step is over
-  extern __shared__ float2 ny_smem[];  // [warps per CTA][NP][32] pairs of -y
+mm_chunk_kernel(const ChunkArgs g) {
+  if (!FR && g.state->done) return;  // an earlier chunk met the batch-global criterion: the M-step is over
+  if (g.split_gate && g.split_gate[0] <= g.split_gate[1]) return;  // few rows: mm_chunk_split_kernel takes this chunk
+  // [warps][NP][32] pairs of -y, and for free-running rows a second slice: the state six iterations before the chunk end
+  extern __shared__ float2 smem2[];
+  __shared__ double2 red[kMMThreads];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int n_rows = n_rows_dev ? *n_rows_dev : n_rows_host;
-  const int slot = blockIdx.x * (kMMThreads / 32) + warp;
-  bool active = slot < n_rows;
-  double dsq = 0.0, asq = 0.0;
-  long row = 0;
-  int period = 0;  // free-running rows: > 0 once this chunk proved the row's trajectory periodic (in chunks)
+  constexpr int kWarps = kMMThreads / 32;
+  const int n_rows = g.n_rows_dev ? *g.n_rows_dev : g.n_rows_host;
+  const int D = g.D;
+  float2* ny = smem2 + (size_t)warp * NP * 32 + lane;
+  float2* a0s = smem2 + (size_t)(kWarps + warp) * NP * 32 + lane;  // FR only
+  const int dx = (2 * NP - 2) * 32 + lane, dy = (2 * NP - 1) * 32 + lane;  // elements of the last pair
+  const bool ok_x = dx < D, ok_y = dy < D;
+  const float2 tail_mask = make_float2(ok_x ? 1.0f : 0.0f, ok_y ? 1.0f : 0.0f);
+  double dsq_cta = 0.0, asq_cta = 0.0;  // per-lane partial sums over the rows of this warp (non-FR)
 
-  if (active) {
-    row = row_list ? row_list[slot] : slot;
-    if (frozen && frozen[row]) active = false;  // proven periodic earlier: its remaining check terms are already cached
-  }
-  if (active) {
-    const float* ain = alpha_in + row * D;
-    const float* yin = y + row * D;
-    float* aout = alpha_out + row * D;
-    const int dx = (2 * NP - 2) * 32 + lane, dy = (2 * NP - 1) * 32 + lane;  // elements of the last pair
-    const bool ok_x = dx < D, ok_y = dy < D;
-    const float2 tail_mask = make_float2(ok_x ? 1.0f : 0.0f, ok_y ? 1.0f : 0.0f);
+  for (int slot = blockIdx.x * kWarps + warp; slot < n_rows; slot += gridDim.x * kWarps) {
+    const long row = g.row_list ? g.row_list[slot] : slot;
+    if (FR && g.frozen[row]) continue;  // proven periodic earlier: its remaining check terms are already cached
+    const float* ain = g.alpha_in + row * D;
+    const float* yin = g.y + row * D;
+    float* aout = g.alpha_out + row * D;
 
-    // alpha stays in registers; -y (read-only, one LDS.64 per pair and iteration) lives in this warp's slice of shared
-    // memory, which keeps the kernel at <= 80 registers, i.e. 6 instead of 4 warps per scheduler to overlap the FMA and
-    // MUFU pipes (ncu: math-pipe-throttle was the top stall at 4 warps, profiles/r1_mm_chunk_packed.md)
-    float2* ny = ny_smem + (size_t)warp * NP * 32 + lane;
     float2 a[NP];
 #pragma unroll
     for (int j = 0; j < NP - 1; ++j) {
@@ -95,16 +172,29 @@ mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict
     a[NP - 1] = make_float2(ok_x ? ain[dx] : 1.0f, ok_y ? ain[dy] : 1.0f);
     ny[(NP - 1) * 32] = make_float2(ok_x ? -__ldg(yin + dx) : 1.0f, ok_y ? -__ldg(yin + dy) : 1.0f);
 
+    // Free-running rows: the last six iterations of the chunk form a window W[0..6]; W[6] == W[0] (bit for bit) proves
+    // the trajectory periodic with a period dividing 6, and the terms of window updates 2, 4 and 6 are then the terms
+    // of every later check point (their distance to this one is a multiple of 50 == 2 mod 6 iterations).
+    const bool window = FR && g.n_iters >= 8;
+    const int n_plain = window ? g.n_iters - 6 : g.n_iters - 1;
     double s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
-    for (int it = 0; it < n_iters - 1; ++it) {
+    for (int it = 0; it < n_plain; ++it) {
       const RowPsi rp = row_psi(s);
 #pragma unroll
       for (int j = 0; j < NP; ++j) a[j] = mm_update_pair(a[j], ny[j * 32], rp);
       s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     }
-    {  // last iteration of the chunk: also the one the criterion is evaluated on
+    if (FR && window) {
+#pragma unroll
+      for (int j = 0; j < NP; ++j) a0s[j * 32] = a[j];
+    }
+    float2 d2 = make_float2(0.0f, 0.0f), a2 = make_float2(0.0f, 0.0f);  // terms of the last update
+    float2 d2_k2 = d2, a2_k2 = d2, d2_k4 = d2, a2_k4 = d2;               // FR: window updates 2 and 4
+    const int n_tail = window ? 6 : 1;
+    for (int k = 1; k <= n_tail; ++k) {
       const RowPsi rp = row_psi(s);
-      float2 d2 = make_float2(0.0f, 0.0f), a2 = make_float2(0.0f, 0.0f);
+      d2 = make_float2(0.0f, 0.0f);
+      a2 = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
         const float2 an = mm_update_pair(a[j], ny[j * 32], rp);
@@ -118,8 +208,15 @@ mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict
         a2 = f2fma(ao, ao, a2);
         a[j] = an;
       }
-      dsq = (double)(d2.x + d2.y);
-      asq = (double)(a2.x + a2.y);
+      if (FR && k == 2) {
+        d2_k2 = d2;
+        a2_k2 = a2;
+      }
+      if (FR && k == 4) {
+        d2_k4 = d2;
+        a2_k4 = a2;
+      }
+      if (k < n_tail) s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     }
 #pragma unroll
     for (int j = 0; j < NP - 1; ++j) {
@@ -129,150 +226,255 @@ mm_chunk_kernel(const float* alpha_in, float* alpha_out, const float* __restrict
     if (ok_x) aout[dx] = a[NP - 1].x;
     if (ok_y) aout[dy] = a[NP - 1].y;
 
-    if (work_ctr && lane == 0) atomicAdd(work_ctr, (unsigned long long)n_iters);  // row-iterations actually executed
-    if (frozen) {
-      // Free-running (dead-cluster) rows: the map "state at a chunk end -> state at the next chunk end" is a fixed
-      // deterministic function of the row (y = const, 50 iterations), so a chunk-end state that equals, bit for bit, the
-      // snapshot taken `snap_age` chunks ago proves the trajectory periodic with that period: every later check term
-      // repeats and the row need not be iterated again.  (fp32 MM trajectories settle on such orbits after ~50-200
-      // iterations; the reference would keep recomputing the same numbers.)
-      float* sn = snap + row * D;
-      bool same = snap_age > 0;
-      if (snap_age > 0) {
+    if (!FR) {
+      dsq_cta += (double)(d2.x + d2.y);
+      asq_cta += (double)(a2.x + a2.y);
+    } else {
+      if (g.work_ctr && lane == 0) atomicAdd(g.work_ctr, (unsigned long long)g.n_iters);  // row-iterations executed
+      // (a) period dividing 6 iterations, proven inside this chunk
+      bool same6 = window;
+      if (window) {
 #pragma unroll
-        for (int j = 0; j < NP - 1; ++j) {
-          same &= (sn[(2 * j) * 32 + lane] == a[j].x) & (sn[(2 * j + 1) * 32 + lane] == a[j].y);
+        for (int j = 0; j < NP; ++j) {
+          const float2 w0 = a0s[j * 32];
+          same6 &= (w0.x == a[j].x) & (w0.y == a[j].y);
         }
-        if (ok_x) same &= sn[dx] == a[NP - 1].x;
-        if (ok_y) same &= sn[dy] == a[NP - 1].y;
-        same = __all_sync(0xffffffffu, same);
+        same6 = __all_sync(0xffffffffu, same6);
       }
-      if (same) {
-        period = snap_age;
-      } else if (snap_write) {
+      // (b) otherwise: period of 1..3 chunks, proven against the snapshot taken `snap_age` chunks ago.  The map "state at a
+      // chunk end -> state at the next chunk end" is a fixed deterministic function of the row (y = const, 50 iterations).
+      int period_chunks = 0;
+      if (!same6) {
+        float* sn = g.snap + row * D;
+        bool same = g.snap_age > 0;
+        if (g.snap_age > 0) {
 #pragma unroll
-        for (int j = 0; j < NP - 1; ++j) {
-          sn[(2 * j) * 32 + lane] = a[j].x;
-          sn[(2 * j + 1) * 32 + lane] = a[j].y;
+          for (int j = 0; j < NP - 1; ++j)
+            same &= (sn[(2 * j) * 32 + lane] == a[j].x) & (sn[(2 * j + 1) * 32 + lane] == a[j].y);
+          if (ok_x) same &= sn[dx] == a[NP - 1].x;
+          if (ok_y) same &= sn[dy] == a[NP - 1].y;
+          same = __all_sync(0xffffffffu, same);
         }
-        if (ok_x) sn[dx] = a[NP - 1].x;
-        if (ok_y) sn[dy] = a[NP - 1].y;
+        if (same) {
+          period_chunks = g.snap_age;
+        } else if (g.snap_write) {
+#pragma unroll
+          for (int j = 0; j < NP - 1; ++j) {
+            sn[(2 * j) * 32 + lane] = a[j].x;
+            sn[(2 * j + 1) * 32 + lane] = a[j].y;
+          }
+          if (ok_x) sn[dx] = a[NP - 1].x;
+          if (ok_y) sn[dy] = a[NP - 1].y;
+        }
+      }
+      const double t6x = warp_sum_f64((double)(d2.x + d2.y)), t6y = warp_sum_f64((double)(a2.x + a2.y));
+      const double t2x = warp_sum_f64((double)(d2_k2.x + d2_k2.y)), t2y = warp_sum_f64((double)(a2_k2.x + a2_k2.y));
+      const double t4x = warp_sum_f64((double)(d2_k4.x + d2_k4.y)), t4y = warp_sum_f64((double)(a2_k4.x + a2_k4.y));
+      if (lane == 0) {
+        double2* rc = g.row_cache + row;  // [n_checks][rows_total] so that the per-check sums read coalesced
+        const long rs = g.rows_total;
+        rc[g.check_idx * rs] = make_double2(t6x, t6y);
+        if (same6) {
+          for (int j = g.check_idx + 1; j < g.n_checks; ++j) {
+            const int ph = (2 * (j - g.check_idx)) % 6;
+            rc[j * rs] = ph == 0 ? make_double2(t6x, t6y) : (ph == 2 ? make_double2(t2x, t2y) : make_double2(t4x, t4y));
+          }
+          g.frozen[row] = 6;
+        } else if (period_chunks > 0) {
+          // state_end(c) == state_end(c - period)  =>  terms(j) == terms(j - period) for every later check j
+          for (int j = g.check_idx + 1; j < g.n_checks; ++j) rc[j * rs] = rc[(j - period_chunks) * rs];
+          g.frozen[row] = period_chunks;
+        }
       }
     }
   }
 
-  if (emit_check == 2) {  // free-running rows: each row keeps its own terms
-    dsq = warp_sum_f64(dsq);
-    asq = warp_sum_f64(asq);
-    if (active && lane == 0) {
-      double2* rc = row_cache + row;  // [n_checks][rows_total] so that the per-check sums read coalesced
-      const long rs = cache_stride;
-      rc[check_idx * rs] = make_double2(dsq, asq);
-      if (period > 0) {
-        // state_end(c) == state_end(c - period)  =>  terms(j) == terms(j - period) for every later check j
-        for (int j = check_idx + 1; j < n_checks; ++j) rc[j * rs] = rc[(j - period) * rs];
-        frozen[row] = period;
-      }
-    }
-  } else if (emit_check) {
-    __shared__ double2 red[kMMThreads / 32];
-    dsq = warp_sum_f64(dsq);
-    asq = warp_sum_f64(asq);
-    if (lane == 0) red[warp] = make_double2(dsq, asq);
+  if (!FR) {
+    __shared__ double2 wred[kWarps];
+    const double ds = warp_sum_f64(dsq_cta), as = warp_sum_f64(asq_cta);
+    if (lane == 0) wred[warp] = make_double2(ds, as);
     __syncthreads();
+    double2 acc = make_double2(0.0, 0.0);
     if (threadIdx.x == 0) {
-      double2 acc = red[0];
 #pragma unroll
-      for (int w = 1; w < kMMThreads / 32; ++w) {
-        acc.x += red[w].x;
-        acc.y += red[w].y;
+      for (int w = 0; w < kWarps; ++w) {
+        acc.x += wred[w].x;
+        acc.y += wred[w].y;
       }
-      partials[blockIdx.x] = acc;
     }
+    finish_chunk<kMMThreads>(g, acc, red);
   }
 }
 
-// Folds the per-block partials of the chunk that just ran (fixed order => bit-reproducible), applies the reference's
-// test `criterion < tol` (false for NaN, so a NaN never stops the loop) and keeps the executed-iteration count.
-__global__ void __launch_bounds__(256)
-mm_decide_kernel(const double2* __restrict__ partials, int n_partials, const double2* __restrict__ extra,
-                 int has_check, int iters_cum, float tol, MMState* state) {
-  if (state->done) return;
-  __shared__ double2 red[256];
-  double2 acc = make_double2(0.0, 0.0);
-  if (has_check) {
-    for (int i = threadIdx.x; i < n_partials; i += 256) {
-      const double2 p = partials[i];
-      acc.x += p.x;
-      acc.y += p.y;
+// Few-rows form (the live clusters of the skip-dead schedule: a few hundred rows per batch): one row per CTA, its
+// pairs dealt out to W warps so that the serial chain of one MM iteration is NPW pairs long instead of D/64, and the
+// machine is filled W times better.  Row total: warp partials through shared memory (ping-pong slots, one
+// __syncthreads per iteration), summed in warp order by every thread.  Runs iff split_gate[0] <= split_gate[1].
+template <int W, int NPW>
+__global__ void __launch_bounds__(32 * W)
+mm_chunk_split_kernel(const ChunkArgs g) {
+  if (g.state->done) return;
+  if (!(g.split_gate[0] <= g.split_gate[1])) return;
+  __shared__ double part[2][W];
+  __shared__ double2 wred[W];
+  __shared__ double2 red[32 * W];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int D = g.D;
+  const bool active = (int)blockIdx.x < *g.n_rows_dev;  // CTA-uniform
+  double2 cta_terms = make_double2(0.0, 0.0);
+  if (active) {
+    const long row = g.row_list[blockIdx.x];
+    const float* ain = g.alpha_in + row * D;
+    const float* yin = g.y + row * D;
+    float* aout = g.alpha_out + row * D;
+
+    float2 a[NPW], ny[NPW], mask[NPW];
+    int dxs[NPW], dys[NPW];
+#pragma unroll
+    for (int j = 0; j < NPW; ++j) {
+      const int jp = warp * NPW + j;
+      dxs[j] = (2 * jp) * 32 + lane;
+      dys[j] = (2 * jp + 1) * 32 + lane;
+      const bool okx = dxs[j] < D, oky = dys[j] < D;
+      mask[j] = make_float2(okx ? 1.0f : 0.0f, oky ? 1.0f : 0.0f);
+      a[j] = make_float2(okx ? ain[dxs[j]] : 1.0f, oky ? ain[dys[j]] : 1.0f);
+      ny[j] = make_float2(okx ? -__ldg(yin + dxs[j]) : 1.0f, oky ? -__ldg(yin + dys[j]) : 1.0f);
     }
-  }
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (threadIdx.x < w) {
-      red[threadIdx.x].x += red[threadIdx.x + w].x;
-      red[threadIdx.x].y += red[threadIdx.x + w].y;
+    auto row_total = [&](int parity) -> double {
+      float2 t = f2mul(a[0], mask[0]);
+#pragma unroll
+      for (int j = 1; j < NPW; ++j) t = f2fma(a[j], mask[j], t);
+      const double ws = warp_sum_f64((double)(t.x + t.y));
+      if (lane == 0) part[parity][warp] = ws;
+      __syncthreads();
+      double s = part[parity][0];
+#pragma unroll
+      for (int w = 1; w < W; ++w) s += part[parity][w];
+      return s;
+    };
+    double s = row_total(0);
+    for (int it = 0; it < g.n_iters - 1; ++it) {
+      const RowPsi rp = row_psi(s);
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) a[j] = mm_update_pair(a[j], ny[j], rp);
+      s = row_total((it + 1) & 1);
     }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    state->iters_done = iters_cum;
-    if (has_check) {
-      double num = red[0].x, den = red[0].y;
-      if (extra) {  // norm contributions of rows that are not iterated in this launch (cached dead rows)
-        num += extra->x;
-        den += extra->y;
+    double dsq, asq;
+    {
+      const RowPsi rp = row_psi(s);
+      float2 d2 = make_float2(0.0f, 0.0f), a2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) {
+        const float2 an = mm_update_pair(a[j], ny[j], rp);
+        const float2 df = f2mul(f2add(an, make_float2(-a[j].x, -a[j].y)), mask[j]);
+        const float2 ao = f2mul(a[j], mask[j]);
+        d2 = f2fma(df, df, d2);
+        a2 = f2fma(ao, ao, a2);
+        a[j] = an;
       }
-      state->last_num = num;
-      state->last_den = den;
-      // the reference forms the ratio of two float32 squared norms; do the comparison on the float32 ratio too
-      const float crit = (float)num / (float)den;
-      if (crit < tol) state->done = 1;
+      dsq = (double)(d2.x + d2.y);
+      asq = (double)(a2.x + a2.y);
+    }
+#pragma unroll
+    for (int j = 0; j < NPW; ++j) {
+      if (dxs[j] < D) aout[dxs[j]] = a[j].x;
+      if (dys[j] < D) aout[dys[j]] = a[j].y;
+    }
+    dsq = warp_sum_f64(dsq);
+    asq = warp_sum_f64(asq);
+    if (lane == 0) wred[warp] = make_double2(dsq, asq);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        cta_terms.x += wred[w].x;
+        cta_terms.y += wred[w].y;
+      }
     }
   }
+  finish_chunk<32 * W>(g, cta_terms, red);
 }
 
 __global__ void mm_reset_kernel(MMState* state) {
   state->done = 0;
   state->iters_done = 0;
+  state->ticket = 0u;
   state->last_num = 0.0;
   state->last_den = 0.0;
 }
 
-template <int NP>
-void launch_chunk(const MMLaunch& p, int n_iters, int emit_check, int check_idx, int snap_age, int snap_write,
-                  cudaStream_t st) {
-  mm_chunk_kernel<NP><<<p.n_blocks, kMMThreads, (size_t)(kMMThreads / 32) * NP * 32 * sizeof(float2), st>>>(p.alpha_in, p.alpha_out, p.y, p.row_list, p.n_rows_dev,
-                                                         p.n_rows, p.D, n_iters, emit_check, p.partials, p.state,
-                                                         p.row_cache, p.n_checks, check_idx, p.frozen, p.snap,
-                                                         snap_age, snap_write, p.work_ctr, (long)p.rows_total);
+template <int NP, bool FR>
+void launch_chunk(const ChunkArgs& g, int n_blocks, cudaStream_t st) {
+  const size_t smem = (size_t)(kMMThreads / 32) * NP * 32 * sizeof(float2) * (FR ? 2 : 1);
+  mm_chunk_kernel<NP, FR><<<n_blocks, kMMThreads, smem, st>>>(g);
 }
 
-constexpr int kSnapEvery = 3;  // detects chunk-periods 1..3, i.e. iteration periods dividing 50, 100 or 150
+template <int W, int NPW>
+void launch_split(const ChunkArgs& g, int n_blocks, cudaStream_t st) {
+  mm_chunk_split_kernel<W, NPW><<<n_blocks, 32 * W, 0, st>>>(g);
+}
 
-using ChunkFn = void (*)(const MMLaunch&, int, int, int, int, int, cudaStream_t);
+using ChunkFn = void (*)(const ChunkArgs&, int, cudaStream_t);
 
-template <int... I>
+template <bool FR, int... I>
 constexpr auto make_table(std::integer_sequence<int, I...>) {
-  return std::array<ChunkFn, sizeof...(I)>{&launch_chunk<I + 1>...};
+  return std::array<ChunkFn, sizeof...(I)>{&launch_chunk<I + 1, FR>...};
+}
+
+// NP = ceil(D / 64) pairs dealt to W = min(8, NP) warps, NPW = ceil(NP / W) pairs each
+ChunkFn split_fn(int np) {
+  switch (np) {
+    case 1: return &launch_split<1, 1>;
+    case 2: return &launch_split<2, 1>;
+    case 3: return &launch_split<3, 1>;
+    case 4: return &launch_split<4, 1>;
+    case 5: return &launch_split<5, 1>;
+    case 6: return &launch_split<6, 1>;
+    case 7: return &launch_split<7, 1>;
+    case 8: return &launch_split<8, 1>;
+    default: return &launch_split<8, 2>;
+  }
+}
+
+constexpr int kSnapEvery = 3;  // snapshot fallback: detects chunk-periods 1..3 (iteration periods dividing 50, 100, 150)
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else
+      return 148;  // B200; do not cache a failure
+  }
+  return n;
 }
 
 }  // namespace
 
 int mm_max_dim() { return 32 * kMMMaxSlots; }
 
-int mm_num_blocks(int n_rows) { return (n_rows + (kMMThreads / 32) - 1) / (kMMThreads / 32); }
+// persistent grid: at most kMMMinBlocks CTAs per SM, warps stride over the rows
+int mm_num_blocks(int n_rows) {
+  const int need = (n_rows + (kMMThreads / 32) - 1) / (kMMThreads / 32);
+  const int cap = sm_count() * kMMMinBlocks;
+  return need < cap ? need : cap;
+}
 
 // Enqueue one full M-step (<= iter_mm MM iterations with the batch-global early exit) on `st`.
 cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const double2* extra_checks, cudaStream_t st) {
-  static constexpr auto table = make_table(std::make_integer_sequence<int, kMMMaxSlots / 2>{});
+  static constexpr auto table = make_table<false>(std::make_integer_sequence<int, kMMMaxSlots / 2>{});
+  static constexpr auto table_fr = make_table<true>(std::make_integer_sequence<int, kMMMaxSlots / 2>{});
   if (p.D < 1 || p.D > mm_max_dim()) return cudaErrorInvalidValue;
   const int np = (p.D + 63) / 64;
-  const ChunkFn fn = table[np - 1];
-  mm_reset_kernel<<<1, 1, 0, st>>>(p.state);
-  note_launch();
-  const float* first_in = p.alpha_in;
+  const bool free_run = p.row_cache != nullptr;
+  const ChunkFn fn = free_run ? table_fr[np - 1] : table[np - 1];
+  if (!free_run) {
+    mm_reset_kernel<<<1, 1, 0, st>>>(p.state);
+    note_launch();
+  }
   int start = 0, check_idx = 0;
   while (start < iter_mm) {
     // the chunk ends at the next l with l > 0, l % check_every == 0, or at the last iteration
@@ -286,18 +488,41 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
         has_check = 1;
       }
     }
-    MMLaunch q = p;
-    q.alpha_in = (start == 0) ? first_in : p.alpha_out;
-    const bool free_run = p.row_cache != nullptr;
     if (free_run && !has_check) break;  // dead rows: alpha is discarded, only check terms matter -> no tail chunk
-    // periodicity snapshots of free-running rows every kSnapEvery chunks, compared at every chunk end in between
-    const int snap_age = (free_run && p.frozen) ? (check_idx == 0 ? 0 : ((check_idx - 1) % kSnapEvery) + 1) : 0;
-    const int snap_write = (free_run && p.frozen && check_idx % kSnapEvery == 0) ? 1 : 0;
-    fn(q, end - start + 1, has_check ? (free_run ? 2 : 1) : 0, check_idx, snap_age, snap_write, st);
-    const double2* extra = (has_check && extra_checks) ? extra_checks + check_idx : nullptr;
-    mm_decide_kernel<<<1, 256, 0, st>>>(p.partials, p.n_blocks, extra, free_run ? 0 : has_check, end + 1, tol,
-                                        p.state);
-    note_launch(2);
+    ChunkArgs g{};
+    g.alpha_in = (start == 0) ? p.alpha_in : p.alpha_out;
+    g.alpha_out = p.alpha_out;
+    g.y = p.y;
+    g.row_list = p.row_list;
+    g.n_rows_dev = p.n_rows_dev;
+    g.n_rows_host = p.n_rows;
+    g.D = p.D;
+    g.n_iters = end - start + 1;
+    g.has_check = has_check;
+    g.iters_cum = end + 1;
+    g.tol = tol;
+    g.partials = p.partials;
+    g.state = p.state;
+    g.extra = (has_check && extra_checks) ? extra_checks + check_idx : nullptr;
+    g.split_gate = p.split_gate;
+    if (free_run) {
+      g.row_cache = p.row_cache;
+      g.n_checks = p.n_checks;
+      g.check_idx = check_idx;
+      g.rows_total = p.rows_total;
+      g.frozen = p.frozen;
+      g.snap = p.snap;
+      // periodicity snapshots every kSnapEvery chunks, compared at every chunk end in between
+      g.snap_age = check_idx == 0 ? 0 : ((check_idx - 1) % kSnapEvery) + 1;
+      g.snap_write = check_idx % kSnapEvery == 0 ? 1 : 0;
+      g.work_ctr = p.work_ctr;
+    }
+    fn(g, p.n_blocks, st);
+    note_launch();
+    if (p.split_gate) {
+      split_fn(np)(g, p.split_cap, st);
+      note_launch();
+    }
     if (has_check) ++check_idx;
     start = end + 1;
   }

@@ -22,6 +22,7 @@ constexpr int kMMMinBlocks = TCLIP_MM_MIN_BLOCKS;    // CTAs per SM the M-step k
 struct MMState {          // lives in device memory; written only by the reset / decide kernels
   int done;               // 1 once the batch-global criterion fell below tol
   int iters_done;         // MM iterations executed so far in this M-step
+  unsigned int ticket;    // CTAs of the running chunk that have finished (the last one folds the criterion)
   double last_num;        // ||a_new - a||^2 at the last check
   double last_den;        // ||a||^2      at the last check
 };
@@ -34,7 +35,7 @@ struct MMLaunch {
   const int* n_rows_dev;  // optional: device-side row count (overrides n_rows)
   int n_rows;             // rows to iterate (upper bound when n_rows_dev is given)
   int D;
-  int n_blocks;           // grid size = mm_num_blocks(n_rows)
+  int n_blocks;           // grid size = mm_num_blocks(n_rows) (persistent: <= kMMMinBlocks CTAs per SM)
   double2* partials;      // [n_blocks] scratch for the criterion
   MMState* state;
   // "free-running" mode (row_cache != nullptr): ignore the batch-global exit, run all iter_mm iterations and store
@@ -45,6 +46,10 @@ struct MMLaunch {
   int* frozen;            // free-running mode, optional: [rows_total] period (in chunks) of rows proven periodic, 0 = still iterating
   float* snap;            // free-running mode: [rows_total, D] chunk-end snapshots used for the periodicity proof
   unsigned long long* work_ctr;  // optional: += row-iterations executed (work accounting for the roofline)
+  // optional (needs row_list + n_rows_dev): device-side {n_rows, cap}; when n_rows <= cap the chunk is run by
+  // mm_chunk_split_kernel (one row per CTA) instead of the one-warp-per-row kernel.  split_cap CTAs are launched.
+  const int* split_gate;
+  int split_cap;
 };
 
 int mm_max_dim();
