@@ -245,3 +245,44 @@ def test_imagenet_shape_properties(dev):
     # a cluster that was empty at every M-step after the first has alpha from outer iteration 0 only: finite, positive
     assert torch.isfinite(md.alpha).all() and (md.alpha > 0).all()
     assert sizes.sum().item() == T * 75
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE shape against the frozen answers of the CPU oracle (oracle/make_k1000_fixture.py; ~35 CPU-minutes to make)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["em", "hard"])
+@pytest.mark.parametrize("mode", ["skip_dead", "dense"])
+def test_imagenet_shape_vs_frozen_oracle(dev, golden_dir, name, mode):
+    from tclip_b200 import tasks
+    path = os.path.join(golden_dir, f"oracle_k1000_{name}.npz")
+    if not os.path.isfile(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path, allow_pickle=True)
+    K, T, iters, hard = int(g["K"]), int(g["T"]), int(g["iters"]), bool(g["hard"])
+    td, _ = tasks.make_zero_shot_batch(T, K, seed=int(g["seed"]), batch_index=int(g["batch_index"]))
+    # same inputs as the fixture: the generator is a pure function of the seed (weighted checksum computed when the
+    # fixture was made; the labels below come from the same random stream)
+    x = td["x_q"].double()
+    w = torch.cos(torch.arange(x.numel(), dtype=torch.float64) * 0.001).reshape(x.shape)
+    assert abs(float((x * w).sum()) - (-0.7348859040829243)) < 1e-7
+    assert np.array_equal(td["y_q"].numpy(), g["y_q"])
+    cls = _classes()[("zero_shot", "HARD_EM_DIRICHLET" if hard else "EM_DIRICHLET")]
+    m = cls(model=None, device=dev, log_file=None, args=make_args(K, iters=iters, mm_mode=mode))
+    logs = m.run_task({k: v.clone() for k, v in td.items()})
+
+    assert m.mm_iters.cpu().tolist() == g["mm_iters32"].tolist()
+    assert m.n_live.cpu().tolist() == g["n_live32"].tolist()
+    assert (m.labels.cpu().numpy() == g["preds32"]).mean() >= LABEL_AGREE
+    assert abs(float(logs["acc"].mean()) - float(g["acc32"].mean())) <= ACC_TOL
+    np.testing.assert_allclose(logs["criterions"], g["criterions32"], rtol=5e-3, atol=1e-6)
+    # alpha: rows of the clusters alive at the end carry all of the mass; GPU no further from float64 than 2x the
+    # reference float32 (or 1e-4), and every row norm (alive or not) within 1e-4 of float64
+    a = m.alpha.cpu()
+    live = torch.from_numpy(g["live"])
+    rows64, rows32 = torch.from_numpy(g["live_rows64"]), torch.from_numpy(g["live_rows32"])
+    gpu_rows = a[live].double()
+    gpu_err = ((gpu_rows - rows64).norm() / rows64.norm()).item()
+    ref_err = ((rows32.double() - rows64).norm() / rows64.norm()).item()
+    assert gpu_err <= max(ALPHA_REL, 2.0 * ref_err), (gpu_err, ref_err)
+    norm_err = (a.double().norm(dim=2) - torch.from_numpy(g["row_norm64"])).abs() / torch.from_numpy(g["row_norm64"])
+    assert norm_err.max().item() <= max(2e-4, 2.0 * float(np.max(g["task_err32"]))), norm_err.max().item()

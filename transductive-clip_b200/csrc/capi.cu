@@ -125,7 +125,7 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
   w.live = c.take<int>(rows);
   w.norm = c.take<double>(rows);
   w.rowstat = c.take<double2>(rows);
-  w.partials = c.take<double2>(std::max(tclip::mm_num_blocks((int)rows), kSplitCap));
+  w.partials = c.take<double2>(std::max(tclip::mm_num_blocks((int)rows), kSplitCap));  // largest grid of any chunk kernel
   w.state = c.take<tclip::MMState>(1);
   w.state_free = c.take<tclip::MMState>(1);
   w.task_crit = c.take<float>(T);
@@ -524,7 +524,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       l.split_gate = w.split_gate;
       l.split_cap = kSplitCap;
       l.n_rows = rows;
-      l.n_blocks = tclip::mm_num_blocks(rows);
+      l.n_blocks = tclip::mm_num_blocks(rows, true);
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nc > 0 ? w.extra : nullptr, st));
     }
     if (p->mm_events && p->mm_events[2 * it + 1])

@@ -456,10 +456,13 @@ int sm_count() {
 
 int mm_max_dim() { return 32 * kMMMaxSlots; }
 
-// persistent grid: at most kMMMinBlocks CTAs per SM, warps stride over the rows
-int mm_num_blocks(int n_rows) {
+// One CTA per 4 rows, capped: warps stride over the rows.  `persistent` (the live-rows launch of the skip-dead schedule,
+// whose real row count is only known on the device and is usually tiny) caps at one wave so that an almost empty launch
+// costs nothing; otherwise 8 waves, which leaves the load balancing of a full batch to the hardware scheduler (a
+// single static wave measured 10 % slower on 75 000 rows).
+int mm_num_blocks(int n_rows, bool persistent) {
   const int need = (n_rows + (kMMThreads / 32) - 1) / (kMMThreads / 32);
-  const int cap = sm_count() * kMMMinBlocks;
+  const int cap = sm_count() * kMMMinBlocks * (persistent ? 1 : 8);
   return need < cap ? need : cap;
 }
 

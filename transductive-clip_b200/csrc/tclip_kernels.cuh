@@ -53,7 +53,7 @@ struct MMLaunch {
 };
 
 int mm_max_dim();
-int mm_num_blocks(int n_rows);
+int mm_num_blocks(int n_rows, bool persistent = false);
 cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const double2* extra_checks, cudaStream_t st);
 
 // ---- the rest of the Dirichlet EM loop (dirichlet_estep.cu) ---------------------------------------------------------

@@ -99,9 +99,11 @@ class _DirichletBase(object):
         if not self.args.use_softmax_feature:
             raise ValueError("The selected method is unable to handle query features that are not in the unit simplex")
         cl = ops.cluster_prototypes(self.labels, query)
-        proto = cl["proto"].cpu().numpy()
         n_clusters = cl["n_clusters"].cpu().numpy()
         sample_cluster = cl["sample_cluster"].cpu().numpy()
+        # only the rows of existing clusters cross PCIe (a task has <= n_query clusters, usually a handful)
+        max_c = max(int(n_clusters.max()), 1)
+        proto = cl["proto"][:, :max_c].contiguous().cpu().numpy()
         if self.args.graph_matching == True:  # noqa: E712  (same truthiness test as the reference)
             new_preds = matching.graph_matching(proto, n_clusters, sample_cluster)
         else:
