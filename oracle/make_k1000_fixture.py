@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — ImageNet-shape (K = D = 1000) answers of the restated CPU oracle, float32 and float64,
 frozen into tests/golden/oracle_k1000_*.npz so the GPU box can check the headline configuration without spending
-minutes of CPU time per task.  Inputs are regenerated from the seed (tclip_b200.tasks); run: python oracle/make_k1000_fixture.py"""
+minutes of CPU time per task.  The inputs are stored next to the answers (oracle_k1000_inputs.npz): the generator's
+matmul/softmax is not bit-reproducible across host CPUs.  Run: python oracle/make_k1000_fixture.py (~45 min on 8 cores)"""
 from __future__ import annotations
 
 import os
@@ -24,6 +25,7 @@ K, T, SEED = 1000, 3, 2020
 if __name__ == "__main__":
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     td, _ = tasks.make_zero_shot_batch(T, K, seed=SEED, batch_index=777)
+    np.savez_compressed(os.path.join(OUT, "oracle_k1000_inputs.npz"), x_q=td["x_q"].numpy(), y_q=td["y_q"].numpy())
     for name, hard, iters in (("em", False, 20), ("hard", True, 10)):
         t0 = time.time()
         r32 = restated.dirichlet_zero_shot(td["x_q"], td["y_q"], K, iters=iters, hard=hard)

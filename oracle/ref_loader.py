@@ -74,13 +74,14 @@ def load(module: str) -> types.ModuleType:
     if clash is not None and not str(getattr(clash, "__file__", "") or getattr(clash, "__path__", [""])[0]).startswith(root):
         for name in [n for n in sys.modules if n == "src" or n.startswith("src.")]:
             del sys.modules[name]
-    if root not in sys.path:
-        sys.path.insert(0, root)
+    # The reference's ``src`` has no __init__.py (a namespace package), so ANY regular package called ``src`` on sys.path
+    # (the product mirror has one) would win regardless of order: hide those path entries during the import.
+    saved = list(sys.path)
+    sys.path[:] = [root] + [p for p in saved if p != root and not os.path.isdir(os.path.join(p or ".", "src"))]
     try:
         mod = importlib.import_module("src." + module)
     finally:
-        if root in sys.path:
-            sys.path.remove(root)
+        sys.path[:] = saved
     _LOADED[module] = mod
     return mod
 

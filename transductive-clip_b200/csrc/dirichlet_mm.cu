@@ -348,10 +348,15 @@ mm_chunk_split_kernel(const ChunkArgs g) {
       const double ws = warp_sum_f64((double)(t.x + t.y));
       if (lane == 0) part[parity][warp] = ws;
       __syncthreads();
-      double s = part[parity][0];
+      double pw[W];  // balanced tree: the total is on the serial path of every iteration
 #pragma unroll
-      for (int w = 1; w < W; ++w) s += part[parity][w];
-      return s;
+      for (int w = 0; w < W; ++w) pw[w] = part[parity][w];
+#pragma unroll
+      for (int st = 1; st < W; st <<= 1) {
+#pragma unroll
+        for (int w = 0; w + st < W; w += 2 * st) pw[w] += pw[w + st];
+      }
+      return pw[0];
     };
     double s = row_total(0);
     for (int it = 0; it < g.n_iters - 1; ++it) {

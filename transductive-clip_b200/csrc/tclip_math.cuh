@@ -288,15 +288,15 @@ TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, RowPsi rp) {
 }
 
 // psi(s) for the row total, s > 0, to ~1e-10 absolute: ln s from the (m-1)/(m+1) series in float64, reciprocals from a
-// MUFU seed + two Newton steps (no division subroutine, no libm call).  It enters the update as a (hi, lo) float pair.
+// MUFU seed + one Newton step (no division subroutine, no libm call).
 TCLIP_HD double rcp_f64(double x) {
-  double r = (double)fast_rcp((float)x);
-  r = r * fma(-x, r, 2.0);
-  r = r * fma(-x, r, 2.0);
+  double r = (double)fast_rcp((float)x);   // 1e-7 relative (needs |x| inside the float32 range: row totals are)
+  r = r * fma(-x, r, 2.0);                 // one Newton step: ~1e-14
   return r;
 }
 
-// ln(s) = e ln2 + lnm with s = 2^e m, m in [sqrt(1/2), sqrt(2)); lnm from the (m-1)/(m+1) series (float64, ~1e-11).
+// ln(s) = e ln2 + lnm with s = 2^e m, m in [sqrt(1/2), sqrt(2)); lnm = 2 atanh((m-1)/(m+1)) from its series up to t^13
+// (t^2 <= 0.0295: truncation 5e-11), evaluated in Estrin form: this sits on the serial path of every MM iteration.
 struct LogParts {
   int e;
   double lnm;
@@ -314,49 +314,51 @@ TCLIP_HD LogParts log_parts_f64(double s) {
   double m = std::frexp(s, &e) * 2.0;    // [1, 2)
   e -= 1;
 #endif
-  if (m > 1.4142135623730951) {
-    m *= 0.5;
-    e += 1;
-  }
+  const bool up = m > 1.4142135623730951;
+  m = up ? m * 0.5 : m;
+  e = up ? e + 1 : e;
   const double t = (m - 1.0) * rcp_f64(m + 1.0);
-  const double t2 = t * t;                // <= 0.0295
-  double p = fma(t2, 1.0 / 13.0, 1.0 / 11.0);
-  p = fma(t2, p, 1.0 / 9.0);
-  p = fma(t2, p, 1.0 / 7.0);
-  p = fma(t2, p, 1.0 / 5.0);
-  p = fma(t2, p, 1.0 / 3.0);
-  p = fma(t2, p, 1.0);
+  const double t2 = t * t;
+  const double t4 = t2 * t2;
+  const double t8 = t4 * t4;
+  const double p01 = fma(t2, 1.0 / 3.0, 1.0);
+  const double p23 = fma(t2, 1.0 / 7.0, 1.0 / 5.0);
+  const double p45 = fma(t2, 1.0 / 11.0, 1.0 / 9.0);
+  const double p = fma(t8, fma(t4, 1.0 / 13.0, p45), fma(t4, p23, p01));
   LogParts out;
   out.e = e;
-  out.lnm = 2.0 * t * p;
+  out.lnm = (t + t) * p;
   return out;
 }
 
 // psi(s) for the row total s > 0 (normal float64), split as k ln2 + dpsi with 2^k ~ s.
 TCLIP_HD RowPsi row_psi(double s) {
-  const LogParts ls = log_parts_f64(s);   // exponent of the *row total*, also when the series below shifts s
   double acc = 0.0;
   double x = s;
   while (x < 10.0) {  // only rows with a tiny total mass take this path
     acc -= rcp_f64(x);
     x += 1.0;
   }
+  const LogParts lx = log_parts_f64(x);  // one logarithm only: it sits on the serial path of every MM iteration
+  int k = lx.e;                          // 2^k ~ s
+  if (x != s) {
+#if defined(__CUDA_ARCH__)
+    k = ((__double2hiint(s) >> 20) & 0x7ff) - 1023;
+#else
+    int e;
+    std::frexp(s, &e);
+    k = e - 1;
+#endif
+  }
+  k = k < -120 ? -120 : (k > 120 ? 120 : k);           // s is a sum of float32 values; keeps k * 2^23 exact
   const double r = rcp_f64(x);
   const double r2 = r * r;
   double ser = fma(r2, 1.0 / 240.0, -1.0 / 252.0);   // next term 1/(132 x^10) < 1e-12
   ser = fma(r2, ser, 1.0 / 120.0);
   ser = fma(r2, ser, -1.0 / 12.0);
   const double tail = fma(r2, ser, -0.5 * r) + acc;   // psi(x) - ln x + acc
-  double lnx_minus_kln2 = ls.lnm;                      // x == s: ln s - k ln2
-  if (x != s) {
-    const LogParts lx = log_parts_f64(x);
-    lnx_minus_kln2 = fma((double)(lx.e - ls.e), 0.693147180559945309417, lx.lnm);
-  }
   RowPsi out;
-  out.dpsi = (float)(lnx_minus_kln2 + tail);
-  int k = ls.e;
-  k = k < -120 ? -120 : (k > 120 ? 120 : k);           // s is a sum of float32 values; keeps k * 2^23 exact
-  if (k != ls.e) out.dpsi = (float)(lnx_minus_kln2 + tail + (double)(ls.e - k) * 0.693147180559945309417);
+  out.dpsi = (float)(fma((double)(lx.e - k), 0.693147180559945309417, lx.lnm) + tail);
   out.k23 = (float)k * 8388608.0f;
   return out;
 }
