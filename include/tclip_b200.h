@@ -102,6 +102,38 @@ int tclip_dirichlet_estep(const float* alpha, const float* logz, const float* v,
 int tclip_cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
                              int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D, void* stream);
 
+/* ---- soft k-means / hard k-means / EM-Gaussian (identity covariance): src/methods/zero_shot/{soft_kmeans,hard_kmeans,
+ * em_gaussian}.py.  x [T,n,D] features, u [T,n,K], w [T,K,D] centroids, v [T,K], text [K,D] unit text embeddings. ---------- */
+
+/* out[r,:] = x[r,:] / ||x[r,:]||.  Replaces `query[task] / query[task].norm(dim=-1, keepdim=True)`
+ * (soft_kmeans.py:192-193) and the prototype normalisation of compute_acc_clustering (soft_kmeans.py:53-54). */
+int tclip_normalize_rows(const float* x, float* out, long long rows, int D, void* stream);
+
+/* u[m,:] = softmax_k(scale * a[m,:] . text[k,:]), m < M (all tasks flattened).  Replaces the initial assignment on visual
+ * features `(T * image_features @ text_features.T).softmax(-1)` (soft_kmeans.py:194-197; hard_kmeans.py:180-183;
+ * em_gaussian.py:199-203) and the prototype probabilities of compute_acc_clustering (soft_kmeans.py:55-56). */
+int tclip_kmeans_similarity(const float* a, const float* text, float scale, float* u, long long M, int K, int D,
+                            void* stream);
+
+/* w[t,k,:] = sum_n u[t,n,k] x[t,n,:] / max(sum_n u, 1e-15) for clusters with sum_n u > 1e-15; empty clusters keep their
+ * row (keep_old != 0: soft_kmeans.py:150-166, em_gaussian.py:153-169) or are zeroed (keep_old == 0: hard_kmeans.py:138-151,
+ * and w_init, soft_kmeans.py:135-148). */
+int tclip_kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int keep_old,
+                           void* stream);
+
+#define TCLIP_KMEANS_SOFT 0   /* u = softmax(T * (-1/2 d2))                       soft_kmeans.py:105-125 */
+#define TCLIP_KMEANS_GAUSS 1  /* u = softmax(T * (-1/2 d2) + lambd v / n)         em_gaussian.py:106-128 */
+#define TCLIP_KMEANS_HARD 2   /* u = one-hot(argmin_k softmax(+d2))               hard_kmeans.py:26-35,127-136,197-199 */
+/* d2[t,n,k] = sum_d (w[t,k,d] - x[t,n,d])^2 (direct difference, as the reference), then the assignment of `mode`.
+ * labels [T,n] int32 (may be NULL) = arg-max of the final u (hard: the arg-min cluster). */
+int tclip_kmeans_assign(const float* x, const float* w, const float* v, float temperature, float lambd, int mode, float* u,
+                        int* labels, int T, int n, int K, int D, void* stream);
+
+/* task_norm[t] = ||a[t] - b[t]||_F over `per_task` elements, *mean_out = mean_t.  Replaces the logged criterion
+ * `(u_old - self.u).norm(dim=(1, 2)).mean(0)` (hard_kmeans.py:201). */
+int tclip_kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long long per_task,
+                       void* stream);
+
 /* ---- fused driver: the whole run_method loop, enqueued on one stream without host synchronisation -------------- */
 typedef struct tclip_dirichlet_problem {
   int n_task, n_query, n_class, dim; /* T, n, K, D (D == K: softmax features) */

@@ -55,7 +55,8 @@ class StubTextModel:
         self.text_matrix = text_matrix
 
     def encode_text(self, tokens: torch.Tensor) -> torch.Tensor:
-        return self.text_matrix[tokens.reshape(-1).long()].clone()
+        idx = tokens.reshape(-1).long()
+        return self.text_matrix[idx.cpu()].clone().to(idx.device)   # like a model living on the caller's device
 
 
 _LOADED: dict[str, types.ModuleType] = {}

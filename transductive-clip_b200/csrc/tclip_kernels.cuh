@@ -83,6 +83,18 @@ cudaError_t cluster_prototypes(const int* labels, const float* feats, int* clust
                                int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
                                cudaStream_t st);
 
+// ---- soft / hard k-means and EM-Gaussian (kmeans.cu) -----------------------------------------------------------------
+cudaError_t normalize_rows(const float* x, float* out, long rows, int D, cudaStream_t st);
+cudaError_t kmeans_similarity(const float* a, const float* text, float scale, float* u, long M, int K, int D,
+                              cudaStream_t st);
+cudaError_t kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int keep_old,
+                             cudaStream_t st);
+cudaError_t kmeans_sqdist(const float* x, const float* w, float* d2, int T, int n, int K, int D, cudaStream_t st);
+cudaError_t kmeans_assign(const float* d2, const float* v, float temperature, float lambd, float* u, int* labels, int T,
+                          int n, int K, int mode, cudaStream_t st);
+cudaError_t kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long per_task,
+                         cudaStream_t st);
+
 // ---- issue-rate microbenchmarks used as roofline denominators (probe.cu) ------------------------------------------
 cudaError_t probe_ffma(float* sink, int n_blocks, int iters, cudaStream_t st);   // 2 * 8 * 256 * iters * 64 flop / CTA... see probe.cu
 cudaError_t probe_mufu(float* sink, int n_blocks, int iters, cudaStream_t st);

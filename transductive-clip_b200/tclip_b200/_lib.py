@@ -69,6 +69,12 @@ SIGNATURES = {
                                       c_int, c_int, c_int, c_int, c_void_p]),
     "tclip_cluster_prototypes": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_int, c_int, c_int, c_void_p]),
+    "tclip_normalize_rows": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "tclip_kmeans_similarity": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "tclip_kmeans_centroids": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tclip_kmeans_assign": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_int,
+                                    c_int, c_int, c_int, c_void_p]),
+    "tclip_kmeans_udiff": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "tclip_dirichlet_em_workspace_bytes": (c_size_t, [POINTER(DirichletProblem)]),
     "tclip_dirichlet_em_run": (c_int, [POINTER(DirichletProblem), c_void_p, c_size_t, c_void_p]),
 }

@@ -1,0 +1,171 @@
+"""Soft k-means, hard k-means and EM-Gaussian (identity covariance) method classes on libtclip_b200.
+
+Drop-in for the reference classes (same constructor, ``run_task`` contract and logs):
+  ``src/methods/zero_shot/soft_kmeans.py`` (SOFT_KMEANS :96-220), ``src/methods/zero_shot/hard_kmeans.py``
+  (HARD_KMEANS :118-211), ``src/methods/zero_shot/em_gaussian.py`` (EM_GAUSSIAN :97-229); the caller is
+  ``src/eval_zero_shot.py:119-137,171-177``.
+
+The loop (w -> u [-> v]) is the reference's, every numeric step is a kernel of ``csrc/kmeans.cu`` reached through the C
+ABI; the Hungarian label matching runs on the host with the reference's own SciPy solver.  Both feature kinds are
+supported: softmax features (u starts from the features) and visual features (u starts from
+``softmax(T * normalize(x) @ text.T)``; ``text`` comes from ``model.encode_text`` exactly like ``clip_weights``,
+``src/utils.py:363-377``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import matching, ops
+from ..logger import Logger
+
+
+def clip_weights(model, classnames, template, device):
+    """Unit-norm text embeddings of the class prompts (``src/utils.py:363-377``).  Needs the ``clip`` package for its
+    tokenizer, like the reference."""
+    import clip  # noqa: PLC0415  (openai/CLIP; tests register a stub)
+    names = [c.replace('_', ' ') for c in classnames]
+    tokens = torch.cat([clip.tokenize([template.format(c) for c in names])]).to(device)
+    with torch.no_grad():
+        text = model.encode_text(tokens).float()
+    return ops.normalize_rows(text.to(device).contiguous())
+
+
+class _KMeansBase(object):
+    mode = ops.KMEANS_SOFT
+    _title = "SOFT K-MEANS"
+
+    def __init__(self, model, device, log_file, args):
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        self.iter = args.iter
+        self.model = model
+        self.log_file = log_file
+        self.logger = Logger(type(self).__module__, self.log_file)
+        self.init_info_lists()
+        self.args = args
+        self.eps = 1e-15
+        self.u = self.w = self.v = self.labels = None
+
+    def __del__(self):
+        try:
+            self.logger.del_logger()
+        except Exception:
+            pass
+
+    def init_info_lists(self):
+        self.timestamps = []
+        self.criterions = []
+        self.test_acc = []
+
+    def record_convergence(self, new_time, criterions):
+        self.criterions.append(criterions)
+        self.timestamps.append(new_time)
+
+    def get_logs(self):
+        self.criterions = torch.stack(self.criterions, dim=0).cpu().numpy()
+        self.test_acc = torch.cat(self.test_acc, dim=1).cpu().numpy()
+        return {'timestamps': np.array(self.timestamps).mean(), 'criterions': self.criterions,
+                'acc': self.test_acc}
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("tclip_b200 runs on B200 GPUs only: device must be a CUDA device (no CPU fallback)")
+        if self.device.index is not None:
+            torch.cuda.set_device(self.device)
+
+    def run_task(self, task_dic):
+        """task_dic: {'x_q': float [T, n, F], 'y_q': int64 [T, n, 1]} CPU tensors -> logs dict."""
+        self._require_cuda()
+        y_q = task_dic['y_q']
+        query = task_dic['x_q']
+        query = query.to(self.device, non_blocking=True).float().contiguous()
+        y_q = y_q.long().squeeze(2).to(self.device, non_blocking=True)
+        del task_dic
+        self.run_method(query=query, y_q=y_q)
+        return self.get_logs()
+
+    def _text(self):
+        return clip_weights(self.model, self.args.classnames, self.args.template, self.device)
+
+    def _initial_u(self, query):
+        if self.args.use_softmax_feature:
+            return query.clone()
+        self._text_features = self._text()
+        return ops.kmeans_similarity(ops.normalize_rows(query), self._text_features, float(self.args.T))
+
+    def compute_acc_clustering(self, query, y_q):
+        """Prototypes of the arg-max clusters on the device, matching on the host (soft_kmeans.py:33-66)."""
+        cl = ops.cluster_prototypes(self.labels, query)
+        n_clusters = cl["n_clusters"].cpu().numpy()
+        sample_cluster = cl["sample_cluster"].cpu().numpy()
+        max_c = max(int(n_clusters.max()), 1)
+        proto = cl["proto"][:, :max_c].contiguous()
+        if not self.args.use_softmax_feature:
+            # probs = softmax(T * normalize(prototype) @ text.T); rows of clusters that do not exist are never read
+            proto = ops.kmeans_similarity(ops.normalize_rows(proto), self._text_features, float(self.args.T))
+        proto = proto.cpu().numpy()
+        if self.args.graph_matching == True:  # noqa: E712  (same truthiness test as the reference)
+            new_preds = matching.graph_matching(proto, n_clusters, sample_cluster)
+        else:
+            new_preds = matching.basic_matching(proto, n_clusters, sample_cluster)
+        new_preds_q = torch.from_numpy(new_preds).to(self.device)
+        self.test_acc.append((new_preds_q == y_q).float().mean(1, keepdim=True))
+
+    # ------------------------------------------------------------------------------------------------------------
+    def run_method(self, query, y_q):
+        self.logger.info(" ==> Executing {} with T = {}".format(self._title, self.args.T))
+        n_task, n_class = query.shape[0], self.args.num_classes_test
+        temperature = float(self.args.T)
+        hard = self.mode == ops.KMEANS_HARD
+        self.u = self._initial_u(query)
+        if self.mode == ops.KMEANS_GAUSS:
+            self.v = torch.zeros(n_task, n_class, device=self.device)
+        # w_init (soft_kmeans.py:135-148; hard k-means has none: its first w_update zeroes empty clusters anyway)
+        self.w = None if hard else ops.kmeans_centroids(self.u, query, None, keep_old=False)
+        u_old = self.u.clone() if hard else None
+        zero = torch.zeros((), device=self.device)
+        for _ in range(self.iter):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            self.w = ops.kmeans_centroids(self.u, query, self.w, keep_old=not hard)
+            self.u, self.labels = ops.kmeans_assign(query, self.w, self.mode, temperature, v=self.v,
+                                                    lambd=getattr(self, "lambd", 0.0))
+            if self.mode == ops.KMEANS_GAUSS:
+                # v_update after u_update (em_gaussian.py:212-218)
+                _, self.v, _ = ops.colsum_v(self.u, want_v=True, want_live=False)
+            if hard:
+                crit = ops.kmeans_udiff(u_old, self.u)[0]
+                u_old = self.u.clone()
+            else:
+                crit = zero  # the reference copies u_old *after* the update: its logged criterion is identically 0
+            t1.record()
+            t1.synchronize()
+            dt = t0.elapsed_time(t1) / 1000.0
+            if hard:
+                self.record_convergence(new_time=dt, criterions=crit)      # hard_kmeans.py:203 (un-normalised) ...
+            self.record_convergence(new_time=dt / n_task, criterions=crit)  # ... and :208-209
+        self.compute_acc_clustering(query, y_q)
+
+
+class SOFT_KMEANS(_KMeansBase):
+    mode = ops.KMEANS_SOFT
+    _title = "SOFT K-MEANS"
+
+
+class HARD_KMEANS(_KMeansBase):
+    mode = ops.KMEANS_HARD
+    _title = "HARD_KMEANS"
+
+
+class EM_GAUSSIAN(_KMeansBase):
+    """lambda = int(K / 5) * n_query (em_gaussian.py:20)."""
+    mode = ops.KMEANS_GAUSS
+    _title = "EM-GAUSSIAN"
+
+    def __init__(self, model, device, log_file, args):
+        super().__init__(model, device, log_file, args)
+        self.lambd = int(args.num_classes_test / 5) * args.n_query
+
+
+BASE = _KMeansBase

@@ -11,7 +11,8 @@ from . import _lib
 from ._lib import DirichletProblem, TCLIP_MM_DENSE, TCLIP_MM_SKIP_DEAD, check
 
 __all__ = ["log_features", "colsum_v", "moments", "support_stats", "mm_update_alpha", "commit", "estep",
-           "cluster_prototypes", "dirichlet_em", "device_check", "launch_count", "probe_issue_rate", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
+           "cluster_prototypes", "dirichlet_em", "device_check", "launch_count", "probe_issue_rate", "normalize_rows", "kmeans_similarity",
+           "kmeans_centroids", "kmeans_assign", "kmeans_udiff", "KMEANS_SOFT", "KMEANS_GAUSS", "KMEANS_HARD", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -146,6 +147,73 @@ def cluster_prototypes(labels: torch.Tensor, feats: torch.Tensor):
     check(lib.tclip_cluster_prototypes(_ptr(labels), _ptr(feats), _ptr(out["cluster_label"]), _ptr(out["cluster_size"]),
                                        _ptr(out["sample_cluster"]), _ptr(out["n_clusters"]), _ptr(out["proto"]),
                                        T, n, D, _stream()))
+    return out
+
+
+# ---- k-means family ------------------------------------------------------------------------------------------------
+KMEANS_SOFT, KMEANS_GAUSS, KMEANS_HARD = 0, 1, 2
+
+
+def normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    """x / ||x|| along the last dimension."""
+    lib = _lib.load()
+    _need(x, torch.float32, "x")
+    out = torch.empty_like(x)
+    D = x.shape[-1]
+    check(lib.tclip_normalize_rows(_ptr(x), _ptr(out), x.numel() // D, D, _stream()))
+    return out
+
+
+def kmeans_similarity(a: torch.Tensor, text: torch.Tensor, scale: float) -> torch.Tensor:
+    """softmax_k(scale * a @ text.T) for a [..., D], text [K, D] -> [..., K]."""
+    lib = _lib.load()
+    _need(a, torch.float32, "a"), _need(text, torch.float32, "text")
+    K, D = text.shape
+    M = a.numel() // D
+    u = torch.empty(*a.shape[:-1], K, device=a.device, dtype=torch.float32)
+    check(lib.tclip_kmeans_similarity(_ptr(a), _ptr(text), float(scale), _ptr(u), M, K, D, _stream()))
+    return u
+
+
+def kmeans_centroids(u: torch.Tensor, x: torch.Tensor, w: torch.Tensor | None, keep_old: bool) -> torch.Tensor:
+    """Centroid update; ``w`` is updated in place (allocated when None: then empty clusters are zero)."""
+    lib = _lib.load()
+    _need(u, torch.float32, "u"), _need(x, torch.float32, "x")
+    T, n, K = u.shape
+    D = x.shape[2]
+    if w is None:
+        w = torch.empty(T, K, D, device=u.device, dtype=torch.float32)
+        keep_old = False
+    else:
+        _need(w, torch.float32, "w")
+    check(lib.tclip_kmeans_centroids(_ptr(u), _ptr(x), _ptr(w), T, n, K, D, int(bool(keep_old)), _stream()))
+    return w
+
+
+def kmeans_assign(x: torch.Tensor, w: torch.Tensor, mode: int, temperature: float, v: torch.Tensor | None = None,
+                  lambd: float = 0.0):
+    """(u [T,n,K], labels int32 [T,n]) from the squared distances to the centroids."""
+    lib = _lib.load()
+    _need(x, torch.float32, "x"), _need(w, torch.float32, "w")
+    if v is not None:
+        _need(v, torch.float32, "v")
+    T, n, D = x.shape
+    K = w.shape[1]
+    u = torch.empty(T, n, K, device=x.device, dtype=torch.float32)
+    labels = torch.empty(T, n, device=x.device, dtype=torch.int32)
+    check(lib.tclip_kmeans_assign(_ptr(x), _ptr(w), _ptr(v), float(temperature), float(lambd), int(mode), _ptr(u),
+                                  _ptr(labels), T, n, K, D, _stream()))
+    return u, labels
+
+
+def kmeans_udiff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """mean over tasks of ||a[t] - b[t]||_F  -> tensor [1]."""
+    lib = _lib.load()
+    _need(a, torch.float32, "a"), _need(b, torch.float32, "b")
+    T = a.shape[0]
+    task = torch.empty(T, device=a.device, dtype=torch.float32)
+    out = torch.empty(1, device=a.device, dtype=torch.float32)
+    check(lib.tclip_kmeans_udiff(_ptr(a), _ptr(b), _ptr(task), _ptr(out), T, a.numel() // T, _stream()))
     return out
 
 
