@@ -339,7 +339,9 @@ def main():
             "roofline": {
                 "bound": "fp32-issue", "kernel": "mm_chunk_kernel (Dirichlet MM M-step)",
                 "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one such launch (ncu --set full, profiles/r1_mm_chunk_kernel.md),
+                # valid for the default shape only
+                "traffic": 865.1e6 if (K == 1000 and T == 75) else None, "traffic_unit": "bytes per launch",
                 "peak_source": "measured in this run: libtclip_b200 register-only FFMA microbenchmark "
                                "(MEASURED_PEAKS.json has only HBM and bf16-tensor peaks; this kernel is bound by neither)",
                 "how": "mm_chunk_kernel alone on a full batch of rows (%d x %d), 2 launches = 101 MM iterations, median of "

@@ -12,7 +12,7 @@ for which, it in (("ffma", 4000), ("ffma2", 4000), ("mufu", 1000), ("mix", 2000)
     print(f"probe {which}: {n:.3e} ops in {ms:.3f} ms -> {n / ms / 1e9:.3f} T/s", flush=True)
 # M-step alone, dense, K = D = 1000, 75 tasks -> 75000 rows
 g = torch.Generator().manual_seed(0)
-for rows, D in ((14800, 1000), (3750, 1000), (20000, 100)):
+for rows, D in ((75000, 1000), (3750, 1000), (20000, 100)):
     y = torch.log(torch.softmax(3 * torch.randn(rows, 4, D, generator=g), -1)).mean(1).to(dev)
     a0 = torch.ones(rows, D, device=dev)
     for iter_mm in (50, 200):

@@ -283,3 +283,37 @@ def test_imagenet_shape_vs_frozen_oracle(dev, golden_dir, name, mode):
     assert gpu_err <= max(ALPHA_REL, 2.0 * ref_err), (gpu_err, ref_err)
     norm_err = (a.double().norm(dim=2) - torch.from_numpy(g["row_norm64"])).abs() / torch.from_numpy(g["row_norm64"])
     assert norm_err.max().item() <= max(2e-4, 2.0 * float(np.max(g["task_err32"]))), norm_err.max().item()
+
+
+@pytest.mark.parametrize("tag", ["em", "hard"])
+def test_few_shot_imagenet_shape_vs_frozen_oracle(dev, golden_dir, tag):
+    """BASELINE config 3: 4-shot EM-Dirichlet at K = D = 1000 (S = 4000 support samples with label clamping).  The live
+    reference cannot run this shape; the answers come from the restated oracle (oracle/make_k1000_fewshot_fixture.py)."""
+    from tclip_b200 import tasks
+    path = os.path.join(golden_dir, "oracle_k1000_fewshot.npz")
+    if not os.path.isfile(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path, allow_pickle=True)
+    K, T, shots, iters = int(g["K"]), int(g["T"]), int(g["shots"]), int(g["iters"])
+    td, _ = tasks.make_few_shot_batch(T, K, shots=shots, k_eff=int(g["k_eff"]), seed=int(g["seed"]),
+                                      batch_index=int(g["batch_index"]))
+    # the 32 MB support set is regenerated (float64 generator, bit-reproducible); make sure it is the fixture's
+    assert np.array_equal(td["y_q"].numpy(), g["y_q"]) and np.array_equal(td["y_s"].numpy(), g["y_s"])
+    for key in ("x_q", "x_s"):
+        if abs(R.weighted_checksum(td[key]) - float(g["checksum_" + key])) > 1e-9 * td[key].numel():
+            pytest.skip("the synthetic generator is not bit-reproducible on this host")
+    hard = tag == "hard"
+    cls = _classes()[("few_shot", "HARD_EM_DIRICHLET" if hard else "EM_DIRICHLET")]
+    m = cls(model=None, device=dev, log_file=None, args=make_args(K, iters=iters, k_eff=int(g["k_eff"])))
+    logs = m.run_task({k: v.clone() for k, v in td.items()}, shot=shots)
+    assert m.mm_iters.cpu().tolist() == g[f"mm_iters32_{tag}"].tolist()
+    assert (m.labels.cpu().numpy() == g[f"preds32_{tag}"]).mean() >= LABEL_AGREE
+    assert abs(float(logs["acc"].mean()) - float(g[f"acc32_{tag}"].mean())) <= ACC_TOL
+    a = m.alpha.cpu().double()
+    rows = torch.arange(0, K, 37)
+    ref64, ref32 = torch.from_numpy(g[f"rows64_{tag}"]), torch.from_numpy(g[f"rows32_{tag}"]).double()
+    gpu_err = ((a[:, rows] - ref64).norm() / ref64.norm()).item()
+    ref_err = ((ref32 - ref64).norm() / ref64.norm()).item()
+    assert gpu_err <= max(ALPHA_REL, 2.0 * ref_err), (gpu_err, ref_err)
+    norm_err = (a.norm(dim=2) - torch.from_numpy(g[f"row_norm64_{tag}"])).abs() / torch.from_numpy(g[f"row_norm64_{tag}"])
+    assert norm_err.max().item() <= max(ALPHA_REL, 2.0 * float(np.max(g[f"task_err32_{tag}"]))), norm_err.max().item()

@@ -82,8 +82,11 @@ def test_drop_in_module_names():
         from src.methods.zero_shot.hard_em_dirichlet import HARD_EM_DIRICHLET as B
         from src.methods.few_shot.em_dirichlet import EM_DIRICHLET as C
         from src.methods.few_shot.hard_em_dirichlet import HARD_EM_DIRICHLET as D
+        from src.methods.zero_shot.soft_kmeans import SOFT_KMEANS as E
+        from src.methods.zero_shot.hard_kmeans import HARD_KMEANS as F
+        from src.methods.zero_shot.em_gaussian import EM_GAUSSIAN as G
         import inspect
-        for cls in (A, B, C, D):
+        for cls in (A, B, C, D, E, F, G):
             assert list(inspect.signature(cls.__init__).parameters)[1:] == ['model', 'device', 'log_file', 'args']
         assert list(inspect.signature(A.run_task).parameters)[1:] == ['task_dic']
         assert list(inspect.signature(C.run_task).parameters)[1:] == ['task_dic', 'shot']

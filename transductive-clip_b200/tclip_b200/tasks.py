@@ -10,7 +10,10 @@ so benchmarks and parity tests use the calibrated generator of SURVEY.md §8(d):
                    y = classes[randint(k_eff, n)];  img = normalize(txt[y] + s * randn(n, E) / sqrt(E)),  s = 9
   softmax feature  z = softmax(T * img @ txt.T),  T = 30 (``src/utils.py:287-290``)
 
-Pure host code (torch CPU); everything is driven by one seeded ``torch.Generator``.
+Pure host code (torch CPU); everything is driven by one seeded ``torch.Generator``.  The random draws are float32,
+all arithmetic after them (normalisation, the E x K similarity product, the soft-max) runs in float64 and is rounded to
+float32 once at the end, so a batch is a bit-reproducible function of the seed across host CPUs (a float32 matmul is
+not: its summation order depends on the SIMD width and thread count).
 """
 from __future__ import annotations
 
@@ -25,20 +28,20 @@ NOISE_SCALE = 9.0
 def text_prototypes(K: int, seed: int, embed_dim: int = EMBED_DIM) -> torch.Tensor:
     """Unit-norm class prototypes [K, E]; a fixed function of (K, seed, E)."""
     g = torch.Generator().manual_seed(int(seed) * 7919 + 13)
-    t = torch.randn(K, embed_dim, generator=g)
-    return t / t.norm(dim=-1, keepdim=True)
+    t = torch.randn(K, embed_dim, generator=g).double()
+    return (t / t.norm(dim=-1, keepdim=True)).float()
 
 
 def _embed(txt: torch.Tensor, labels: torch.Tensor, g: torch.Generator, noise: float) -> torch.Tensor:
     e = txt.shape[1]
-    img = txt[labels] + noise * torch.randn(labels.shape[0], e, generator=g) / math.sqrt(e)
-    return img / img.norm(dim=-1, keepdim=True)
+    img = txt[labels].double() + noise * torch.randn(labels.shape[0], e, generator=g).double() / math.sqrt(e)
+    return img / img.norm(dim=-1, keepdim=True)      # float64
 
 
 def _features(img: torch.Tensor, txt: torch.Tensor, temperature: float, softmax_feature: bool) -> torch.Tensor:
     if softmax_feature:
-        return (temperature * img @ txt.T).softmax(dim=-1)
-    return img
+        return (temperature * img @ txt.double().T).softmax(dim=-1).float()
+    return img.float()
 
 
 def make_zero_shot_batch(n_task: int, K: int, n_query: int = 75, seed: int = 0, temperature: float = 30.0,
