@@ -227,10 +227,9 @@ TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, RowPsi rp) {
   const float2 w = f2fma(a, X, f2(5.0f));
   const float2 P = f2fma(w, w, f2(-1.0f));
   const float2 ndP = f2mul(w, f2fma(a, f2(-4.0f), f2(-10.0f)));   // -dP/da = -2w(2a + 5)
-  const float2 XP = f2mul(X, P);
-  const float2 R = make_float2(fast_rcp(XP.x), fast_rcp(XP.y));
-  const float2 rX = f2mul(P, R);
-  const float2 rP = f2mul(X, R);
+  // 1/X and 1/P from two MUFU.RCP: a MUFU costs one dispatch slot, the shared rcp(X P) cost one plus three FMULs
+  const float2 rX = make_float2(fast_rcp(X.x), fast_rcp(X.y));
+  const float2 rP = make_float2(fast_rcp(P.x), fast_rcp(P.y));
   float2 m, e23;
   split_exponent(X.x, m.x, e23.x);
   split_exponent(X.y, m.y, e23.y);
@@ -250,11 +249,11 @@ TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, RowPsi rp) {
   nsp = f2fma(z, nsp, f2(-1.0f / 12.0f));
   float2 nsg2 = f2fma(z, f2(-2.0f / 1260.0f), f2(2.0f / 360.0f));  // -2 S_gam / rX = 2(-1/12 + z/360 - z^2/1260)
   nsg2 = f2fma(z, nsg2, f2(-2.0f / 12.0f));
-  const float2 nE = f2fma(ndP, rP, f2fma(f2(-0.5f), rX, f2mul(nsp, z)));
-  const float2 psi1m = f2add(lnXs, nE);                            // psi(a+1) - k ln2
+  // nEd = -E - dpsi: the row constant rides along for free in the innermost fma
+  const float2 nEd = f2fma(ndP, rP, f2fma(f2(-0.5f), rX, f2fma(nsp, z, f2(-rp.dpsi))));
   const float2 a2 = f2add(a, a);
   float2 M = f2fma(nsg2, rX, f2(2.0f * (5.0f - kHalfLn2Pi)));
-  M = f2add(f2fma(a2, nE, M), a2);
+  M = f2fma(a2, f2(1.0f + rp.dpsi), f2fma(a2, nEd, M));            // 2a (-E) + 2a
   M = f2fma(lnX, f2(-9.0f), M);
   M = f2fma(LP, f2(2.0f * kLn2), M);
 #if defined(__CUDA_ARCH__)
@@ -274,7 +273,7 @@ TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, RowPsi rp) {
     M.x = a.x < kSmallA ? ts.x : M.x;
     M.y = a.y < kSmallA ? ts.y : M.y;
   }
-  const float2 g = f2add(f2add(psi1m, f2(-rp.dpsi)), ny);          // psi(a+1) - psi(s) - y
+  const float2 g = f2add(f2add(lnXs, nEd), ny);                    // psi(a+1) - psi(s) - y
   const float2 nM = make_float2(-M.x, -M.y);
   const float2 bt = f2fma(a, g, nM);
   const float2 M4 = f2mul(M, f2(4.0f));
