@@ -115,10 +115,26 @@ int tclip_normalize_rows(const float* x, float* out, long long rows, int D, void
 int tclip_kmeans_similarity(const float* a, const float* text, float scale, float* u, long long M, int K, int D,
                             void* stream);
 
-/* w[t,k,:] = sum_n u[t,n,k] x[t,n,:] / max(sum_n u, 1e-15) for clusters with sum_n u > 1e-15; empty clusters keep their
- * row (keep_old != 0: soft_kmeans.py:150-166, em_gaussian.py:153-169) or are zeroed (keep_old == 0: hard_kmeans.py:138-151,
- * and w_init, soft_kmeans.py:135-148). */
-int tclip_kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int keep_old,
+/* w[t,k,:] = sum_n u[t,n,k] x[t,n,:] / max(sum_n u, 1e-15) for clusters with sum_n u > 1e-15; empty clusters are zeroed
+ * (mode 0: hard_kmeans.py:138-151, and w_init, soft_kmeans.py:135-148) or keep their row (mode 1: soft_kmeans.py:150-166,
+ * em_gaussian.py:153-169, em_gaussian_cov.py:153-170).  mode 2 = KL k-means (kl_kmeans.py:166-171): divide by
+ * max(size, 1), zero iff size == 0. */
+int tclip_kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int mode,
+                           void* stream);
+
+/* Diagonal precisions s[t,k,d] = sum_n u / max(sum_n u (w - x)^2, 1e-15); with keep_old != 0 empty clusters keep their row
+ * (s_update, em_gaussian_cov.py:182-193), keep_old == 0 is s_init (:172-180). */
+int tclip_kmeans_precisions(const float* u, const float* x, const float* w, float* s, int T, int n, int K, int D,
+                            int keep_old, void* stream);
+
+/* EM-Gaussian with diagonal covariance: u = softmax_k(-1/2 sum_d s (w - x)^2 + 1/2 sum_d log(s + 1e-15) + lambd v / n)
+ * (em_gaussian_cov.py:106-130).  det is scratch of T*K floats. */
+int tclip_kmeans_assign_cov(const float* x, const float* w, const float* s, const float* v, float lambd, float* det,
+                            float* u, int* labels, int T, int n, int K, int D, void* stream);
+
+/* KL k-means: u = one-hot(argmin_k sum_d p log(p / q)), p = x + 1e-15, q = w + 1e-15; NaN counts as the minimum, lowest
+ * index on ties, like torch.argmin (kl_kmeans.py:123-127,173-177). */
+int tclip_kmeans_assign_kl(const float* x, const float* w, float* u, int* labels, int T, int n, int K, int D,
                            void* stream);
 
 #define TCLIP_KMEANS_SOFT 0   /* u = softmax(T * (-1/2 d2))                       soft_kmeans.py:105-125 */

@@ -42,8 +42,12 @@ CASES = [
     ("zs_soft_kmeans_visual_k20", "kmeans", "SOFT_KMEANS", "zero_shot", 20, 3, 4, {"softmax": False, "embed": 64}),
     ("zs_hard_kmeans_visual_k20", "kmeans", "HARD_KMEANS", "zero_shot", 20, 3, 3, {"softmax": False, "embed": 64}),
     ("zs_em_gaussian_visual_k20", "kmeans", "EM_GAUSSIAN", "zero_shot", 20, 3, 4, {"softmax": False, "embed": 64}),
+    ("zs_em_gaussian_cov_k20", "kmeans", "EM_GAUSSIAN_COV", "zero_shot", 20, 3, 4, {"softmax": True}),
+    ("zs_em_gaussian_cov_visual_k20", "kmeans", "EM_GAUSSIAN_COV", "zero_shot", 20, 3, 4, {"softmax": False, "embed": 64}),
+    ("zs_kl_kmeans_k20", "kmeans", "KL_KMEANS", "zero_shot", 20, 3, 3, {"softmax": True}),
+    ("zs_kl_kmeans_visual_k20", "kmeans", "KL_KMEANS", "zero_shot", 20, 3, 3, {"softmax": False, "embed": 64}),
 ]
-KM = {"SOFT_KMEANS": "soft", "HARD_KMEANS": "hard", "EM_GAUSSIAN": "gauss"}
+KM = {"SOFT_KMEANS": "soft", "HARD_KMEANS": "hard", "EM_GAUSSIAN": "gauss", "EM_GAUSSIAN_COV": "gauss_cov", "KL_KMEANS": "kl"}
 
 
 def build(case):
@@ -85,8 +89,11 @@ def build(case):
     else:
         assert torch.equal(inst.w, r.w), name
         save.update(w=inst.w.numpy())
-        if method == "EM_GAUSSIAN":
+        if method in ("EM_GAUSSIAN", "EM_GAUSSIAN_COV"):
             save.update(v=inst.v.numpy())
+        if method == "EM_GAUSSIAN_COV":
+            assert torch.equal(inst.s, r.s), name
+            save.update(s=inst.s.numpy())
     for k, t in td.items():
         save[k] = t.numpy()
     save.update(u=inst.u.numpy(), acc=logs["acc"], criterions=logs["criterions"], preds=r.preds.numpy())
@@ -99,5 +106,7 @@ if __name__ == "__main__":
     if not ref_loader.available():
         sys.exit("reference checkout not found; golden vectors can only be regenerated in the build container")
     torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    only = set(sys.argv[1:])          # optional: fixture names to (re)build; the committed ones are otherwise left alone
     for c in CASES:
-        build(c)
+        if not only or c[0] in only:
+            build(c)

@@ -113,7 +113,8 @@ def make_args(K: int, n_query: int = 75, iters: int = 20, iter_mm: int = 1000, k
 def run_reference(method: str, setting: str, task_dic: dict, args: Cfg, model=None, shot: int | None = None):
     """Run the unchanged reference class on CPU.  Returns (logs, instance)."""
     modname = {"EM_DIRICHLET": "em_dirichlet", "HARD_EM_DIRICHLET": "hard_em_dirichlet", "EM_GAUSSIAN": "em_gaussian",
-               "SOFT_KMEANS": "soft_kmeans", "HARD_KMEANS": "hard_kmeans"}[method]
+               "SOFT_KMEANS": "soft_kmeans", "HARD_KMEANS": "hard_kmeans", "EM_GAUSSIAN_COV": "em_gaussian_cov",
+               "KL_KMEANS": "kl_kmeans"}[method]
     mod = load(f"methods.{setting}.{modname}")
     cls = getattr(mod, method)
     log_file = os.path.join(tempfile.mkdtemp(prefix="tclip_ref_"), "ref.log")

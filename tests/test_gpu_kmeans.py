@@ -17,9 +17,9 @@ pytestmark = pytest.mark.gpu
 from oracle import ref_loader, restated as R  # noqa: E402  (test infrastructure: the checker)
 from oracle.ref_loader import make_args  # noqa: E402
 
-KM = {"SOFT_KMEANS": "soft", "HARD_KMEANS": "hard", "EM_GAUSSIAN": "gauss"}
+KM = {"SOFT_KMEANS": "soft", "HARD_KMEANS": "hard", "EM_GAUSSIAN": "gauss", "EM_GAUSSIAN_COV": "gauss_cov", "KL_KMEANS": "kl"}
 GOLDEN_KMEANS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                       if any(s in p for s in ("kmeans", "gaussian")))
+                       if any(s in p for s in ("kmeans", "gaussian")))   # incl. em_gaussian_cov and kl_kmeans
 
 
 @pytest.fixture(scope="module")
@@ -32,10 +32,11 @@ def dev():
 
 def _cls(method):
     from tclip_b200.methods import kmeans as M
-    return {"SOFT_KMEANS": M.SOFT_KMEANS, "HARD_KMEANS": M.HARD_KMEANS, "EM_GAUSSIAN": M.EM_GAUSSIAN}[method]
+    return {"SOFT_KMEANS": M.SOFT_KMEANS, "HARD_KMEANS": M.HARD_KMEANS, "EM_GAUSSIAN": M.EM_GAUSSIAN,
+            "EM_GAUSSIAN_COV": M.EM_GAUSSIAN_COV, "KL_KMEANS": M.KL_KMEANS}[method]
 
 
-def _check(m, logs, u, w, preds, acc, crit, v=None):
+def _check(m, logs, u, w, preds, acc, crit, v=None, s=None):
     assert logs["acc"].shape == acc.shape and logs["criterions"].shape == crit.shape
     got_preds = m.u.argmax(2).cpu().numpy()
     assert (got_preds == preds).mean() >= 0.999
@@ -54,6 +55,9 @@ def _check(m, logs, u, w, preds, acc, crit, v=None):
     np.testing.assert_allclose(logs["criterions"], crit, rtol=1e-4, atol=1e-6)
     if v is not None:
         np.testing.assert_allclose(m.v.cpu().numpy(), v, rtol=1e-4, atol=2e-3)
+    if s is not None:   # diagonal precisions of the clusters that carry mass (log scale: they span many decades)
+        got_s = m.s.cpu().numpy()
+        np.testing.assert_allclose(np.log(got_s[heavy] + 1e-30), np.log(s[heavy] + 1e-30), atol=2e-3)
 
 
 @pytest.mark.parametrize("name", GOLDEN_KMEANS)
@@ -65,10 +69,11 @@ def test_golden_kmeans(dev, golden_dir, name):
     args = make_args(K, iters=iters, use_softmax_feature=softmax)
     m = _cls(method)(model=ref_loader.StubTextModel(text), device=dev, log_file=None, args=args)
     logs = m.run_task({"x_q": torch.from_numpy(g["x_q"]), "y_q": torch.from_numpy(g["y_q"])})
-    _check(m, logs, g["u"], g["w"], g["preds"], g["acc"], g["criterions"], g["v"] if "v" in g.files else None)
+    _check(m, logs, g["u"], g["w"], g["preds"], g["acc"], g["criterions"], g["v"] if "v" in g.files else None,
+           g["s"] if "s" in g.files else None)
 
 
-@pytest.mark.parametrize("method", ["SOFT_KMEANS", "HARD_KMEANS", "EM_GAUSSIAN"])
+@pytest.mark.parametrize("method", ["SOFT_KMEANS", "HARD_KMEANS", "EM_GAUSSIAN", "EM_GAUSSIAN_COV", "KL_KMEANS"])
 @pytest.mark.parametrize("K,T,iters,softmax,embed,seed", [
     (37, 3, 5, True, 1024, 0),
     (100, 6, 6, True, 1024, 1),
@@ -82,7 +87,10 @@ def test_kmeans_vs_oracle(dev, method, K, T, iters, softmax, embed, seed):
     m = _cls(method)(model=ref_loader.StubTextModel(txt), device=dev, log_file=None, args=args)
     logs = m.run_task({k: v.clone() for k, v in td.items()})
     r = R.kmeans_family(td["x_q"], td["y_q"], K, method=KM[method], iters=iters, use_softmax_feature=softmax, text=txt)
-    _check(m, logs, r.u.numpy(), r.w.numpy(), r.preds.numpy(), r.acc, r.criterions, r.v.numpy() if r.v is not None else None)
+    if method == "KL_KMEANS" and not softmax:
+        pytest.skip("KL divergence of signed embeddings is NaN upstream; covered by the golden fixture only")
+    _check(m, logs, r.u.numpy(), r.w.numpy(), r.preds.numpy(), r.acc, r.criterions, r.v.numpy() if r.v is not None else None,
+           r.s.numpy() if getattr(r, "s", None) is not None else None)
 
 
 def test_kmeans_rn50_shape_properties(dev):

@@ -85,8 +85,10 @@ def test_drop_in_module_names():
         from src.methods.zero_shot.soft_kmeans import SOFT_KMEANS as E
         from src.methods.zero_shot.hard_kmeans import HARD_KMEANS as F
         from src.methods.zero_shot.em_gaussian import EM_GAUSSIAN as G
+        from src.methods.zero_shot.em_gaussian_cov import EM_GAUSSIAN_COV as H
+        from src.methods.zero_shot.kl_kmeans import KL_KMEANS as I
         import inspect
-        for cls in (A, B, C, D, E, F, G):
+        for cls in (A, B, C, D, E, F, G, H, I):
             assert list(inspect.signature(cls.__init__).parameters)[1:] == ['model', 'device', 'log_file', 'args']
         assert list(inspect.signature(A.run_task).parameters)[1:] == ['task_dic']
         assert list(inspect.signature(C.run_task).parameters)[1:] == ['task_dic', 'shot']

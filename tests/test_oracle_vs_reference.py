@@ -33,7 +33,8 @@ def test_few_shot_dirichlet_live(method, hard):
     assert np.array_equal(logs["acc"], r.acc) and np.array_equal(logs["criterions"], r.criterions)
 
 
-@pytest.mark.parametrize("method,km", [("SOFT_KMEANS", "soft"), ("HARD_KMEANS", "hard"), ("EM_GAUSSIAN", "gauss")])
+@pytest.mark.parametrize("method,km", [("SOFT_KMEANS", "soft"), ("HARD_KMEANS", "hard"), ("EM_GAUSSIAN", "gauss"),
+                                       ("EM_GAUSSIAN_COV", "gauss_cov"), ("KL_KMEANS", "kl")])
 @pytest.mark.parametrize("softmax", [True, False])
 def test_kmeans_family_live(method, km, softmax):
     K, T, iters = 12, 2, 3

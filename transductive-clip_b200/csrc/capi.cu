@@ -443,11 +443,41 @@ int tclip_kmeans_similarity(const float* a, const float* text, float scale, floa
   return TCLIP_OK;
 }
 
-int tclip_kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int keep_old,
+int tclip_kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int mode,
                            void* stream) {
-  if (!u || !x || !w || T < 1 || n < 1 || K < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_kmeans_centroids: bad arguments");
+  if (!u || !x || !w || T < 1 || n < 1 || K < 1 || D < 1 || mode < 0 || mode > 2)
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_centroids: bad arguments");
   if (int rc = current_device_ok()) return rc;
-  TCLIP_CUDA(tclip::kmeans_centroids(u, x, w, T, n, K, D, keep_old, (cudaStream_t)stream));
+  TCLIP_CUDA(tclip::kmeans_centroids(u, x, w, T, n, K, D, mode, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_kmeans_precisions(const float* u, const float* x, const float* w, float* s, int T, int n, int K, int D,
+                            int keep_old, void* stream) {
+  if (!u || !x || !w || !s || T < 1 || n < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_precisions: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_precisions(u, x, w, s, T, n, K, D, keep_old, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_kmeans_assign_cov(const float* x, const float* w, const float* s, const float* v, float lambd, float* det,
+                            float* u, int* labels, int T, int n, int K, int D, void* stream) {
+  if (!x || !w || !s || !v || !det || !u || T < 1 || n < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_assign_cov: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_sqdist_cov(x, w, s, u, det, T, n, K, D, (cudaStream_t)stream));
+  TCLIP_CUDA(tclip::kmeans_assign(u, v, det, 1.0f, lambd, u, labels, T, n, K, 4, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_kmeans_assign_kl(const float* x, const float* w, float* u, int* labels, int T, int n, int K, int D,
+                           void* stream) {
+  if (!x || !w || !u || T < 1 || n < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_assign_kl: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_kl_div(x, w, u, T, n, K, D, (cudaStream_t)stream));
+  TCLIP_CUDA(tclip::kmeans_assign(u, nullptr, nullptr, 1.0f, 0.0f, u, labels, T, n, K, 5, (cudaStream_t)stream));
   return TCLIP_OK;
 }
 
@@ -457,7 +487,7 @@ int tclip_kmeans_assign(const float* x, const float* w, const float* v, float te
     return fail(TCLIP_ERR_INVALID, "tclip_kmeans_assign: bad arguments");
   if (int rc = current_device_ok()) return rc;
   TCLIP_CUDA(tclip::kmeans_sqdist(x, w, u, T, n, K, D, (cudaStream_t)stream));
-  TCLIP_CUDA(tclip::kmeans_assign(u, v, temperature, lambd, u, labels, T, n, K, mode, (cudaStream_t)stream));
+  TCLIP_CUDA(tclip::kmeans_assign(u, v, nullptr, temperature, lambd, u, labels, T, n, K, mode, (cudaStream_t)stream));
   return TCLIP_OK;
 }
 

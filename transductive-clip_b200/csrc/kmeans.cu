@@ -12,6 +12,9 @@
 //                                           hard_kmeans.py:127-136,197-199  u = one-hot(argmin softmax(+d2))
 //                                                                                               -> assign_kernel
 //   logged criterion of hard k-means        hard_kmeans.py:201-203  mean_t ||u_old - u||_F      -> udiff_kernel
+//   EM-Gaussian, diagonal covariance        em_gaussian_cov.py:106-130 (E-step), :172-193 (s_init / s_update)
+//                                                                                               -> precisions_kernel, pair_kernel<2>
+//   KL k-means                              kl_kmeans.py:123-127,166-177                        -> centroids (mode 2), pair_kernel<3>
 //
 // Layouts: x [T,n,D], u / d2 [T,n,K], w [T,K,D], text [K,D], all float32 row-major.  In w-space the loop is bound by the
 // CUDA-core rate of the direct-difference distance (3 flop per (n,k,d), the reference's own formulation: no cancellation),
@@ -52,38 +55,50 @@ __global__ void __launch_bounds__(128) normalize_rows_kernel(const float* __rest
 }
 
 // Tiled [M x D] . [N x D]^T with 64 x 64 tiles, BK = 16, 256 threads, 4 x 4 outputs per thread.
-//   OP 0: sum_d a b          (similarity; B shared by all batches when b_batch_stride == 0)
-//   OP 1: sum_d (b - a)^2    (squared distance, the reference's direct form)
+//   OP 0: sum_d a b                      (similarity; B shared by all batches when b_batch_stride == 0)
+//   OP 1: sum_d (b - a)^2                (squared distance, the reference's direct form)
+//   OP 2: sum_d s (b - a)^2              (diagonal-precision distance, S laid out like B)
+//   OP 3: sum_d p log(p / q), p = a + eps, q = b + eps   (KL divergence of kl_kmeans.py:123-127, division first)
 constexpr int kTile = 64;
 constexpr int kBK = 16;
 
 template <int OP>
 __global__ void __launch_bounds__(256)
-pair_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int D,
-            long a_batch_stride, long b_batch_stride, long c_batch_stride) {
+pair_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ S, float* __restrict__ C,
+            int M, int N, int D, long a_batch_stride, long b_batch_stride, long c_batch_stride) {
   __shared__ float as[kBK][kTile + 4];
   __shared__ float bs[kBK][kTile + 4];
+  __shared__ float ss[OP == 2 ? kBK : 1][kTile + 4];
   const int t = blockIdx.z;
   const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const float* ab = A + (long)t * a_batch_stride;
   const float* bb = B + (long)t * b_batch_stride;
+  const float* sb = OP == 2 ? S + (long)t * b_batch_stride : nullptr;
   float acc[4][4] = {};
   for (int d0 = 0; d0 < D; d0 += kBK) {
     for (int i = threadIdx.x; i < kTile * kBK; i += 256) {
       const int r = i / kBK, c = i % kBK;
       const int d = d0 + c;
-      as[c][r] = (m0 + r < M && d < D) ? ab[(long)(m0 + r) * D + d] : 0.0f;
-      bs[c][r] = (n0 + r < N && d < D) ? bb[(long)(n0 + r) * D + d] : 0.0f;
+      const bool ina = m0 + r < M && d < D, inb = n0 + r < N && d < D;
+      // OP 3 pads with p = q = 1 (p log(p/q) = 0), the others with zeros
+      as[c][r] = ina ? ab[(long)(m0 + r) * D + d] : (OP == 3 ? 1.0f : 0.0f);
+      bs[c][r] = inb ? bb[(long)(n0 + r) * D + d] : (OP == 3 ? 1.0f : 0.0f);
+      if (OP == 2) ss[c][r] = inb ? sb[(long)(n0 + r) * D + d] : 0.0f;
     }
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < kBK; ++c) {
-      float av[4], bv[4];
+      float av[4], bv[4], sv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         av[i] = as[c][ty * 4 + i];
         bv[i] = bs[c][tx * 4 + i];
+        sv[i] = OP == 2 ? ss[c][tx * 4 + i] : 0.0f;
+        if (OP == 3) {
+          av[i] += kEps;
+          bv[i] += kEps;
+        }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -91,9 +106,14 @@ pair_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __r
         for (int j = 0; j < 4; ++j) {
           if (OP == 0) {
             acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-          } else {
+          } else if (OP == 1) {
             const float df = bv[j] - av[i];
             acc[i][j] = fmaf(df, df, acc[i][j]);
+          } else if (OP == 2) {
+            const float df = bv[j] - av[i];
+            acc[i][j] = fmaf(df * df, sv[j], acc[i][j]);
+          } else {
+            acc[i][j] = fmaf(av[i], logf(av[i] / bv[j]), acc[i][j]);
           }
         }
     }
@@ -112,13 +132,15 @@ pair_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __r
   }
 }
 
-// w[t,k,:] = sum_n u[t,n,k] x[t,n,:] / max(sum_n u, eps) for non-empty clusters; empty ones keep the previous row
-// (keep_old) or are zeroed.  64(k) x 64(d) tile per CTA, n staged through shared memory; the column sums of u come along.
+// w[t,k,:] = sum_n u[t,n,k] x[t,n,:] / max(sum_n u, eps) for non-empty clusters; empty ones are zeroed (mode 0) or keep
+// the previous row (mode 1).  mode 2 = KL k-means (kl_kmeans.py:166-171): divide by max(size, 1), zero iff size == 0.
+// 64(k) x 64(d) tile per CTA, n staged through shared memory; the column sums of u come along.
+// precisions_kernel (below) has the same shape for s[t,k,:] = sum_n u / max(sum_n u (w - x)^2, eps).
 constexpr int kStage = 16;
 
 __global__ void __launch_bounds__(256)
 centroids_kernel(const float* __restrict__ u, const float* __restrict__ x, float* __restrict__ w, int n, int K, int D,
-                 int keep_old) {
+                 int mode) {
   __shared__ float us[kStage][kTile + 4];
   __shared__ float xs[kStage][kTile + 4];
   __shared__ float csum[kTile];
@@ -168,10 +190,93 @@ centroids_kernel(const float* __restrict__ u, const float* __restrict__ x, float
       const int d = d0 + tx * 4 + j;
       if (d >= D) continue;
       const long o = ((long)t * K + k) * D + d;
-      if (cs > kEps) w[o] = acc[i][j] / fmaxf(cs, kEps);
-      else if (!keep_old) w[o] = 0.0f;
+      if (mode == 2) w[o] = cs > 0.0f ? acc[i][j] / fmaxf(cs, 1.0f) : 0.0f;
+      else if (cs > kEps) w[o] = acc[i][j] / fmaxf(cs, kEps);
+      else if (mode == 0) w[o] = 0.0f;
     }
   }
+}
+
+// s[t,k,d] = sum_n u[t,n,k] / max(sum_n u[t,n,k] (w[t,k,d] - x[t,n,d])^2, eps); empty clusters keep their row when
+// keep_old (s_update, em_gaussian_cov.py:182-193), s_init (:172-180) has no mask (0 / eps = 0 for an empty cluster).
+__global__ void __launch_bounds__(256)
+precisions_kernel(const float* __restrict__ u, const float* __restrict__ x, const float* __restrict__ w,
+                  float* __restrict__ s, int n, int K, int D, int keep_old) {
+  __shared__ float us[kStage][kTile + 4];
+  __shared__ float xs[kStage][kTile + 4];
+  __shared__ float csum[kTile];
+  const int t = blockIdx.z;
+  const int k0 = blockIdx.y * kTile, d0 = blockIdx.x * kTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* ub = u + (long)t * n * K;
+  const float* xb = x + (long)t * n * D;
+  if (threadIdx.x < kTile) {
+    float sum = 0.0f;
+    const int k = k0 + threadIdx.x;
+    if (k < K)
+      for (int i = 0; i < n; ++i) sum += ub[(long)i * K + k];
+    csum[threadIdx.x] = sum;
+  }
+  float wv[4][4], acc[4][4] = {};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + ty * 4 + i, d = d0 + tx * 4 + j;
+      wv[i][j] = (k < K && d < D) ? w[((long)t * K + k) * D + d] : 0.0f;
+    }
+  for (int n0 = 0; n0 < n; n0 += kStage) {
+    for (int i = threadIdx.x; i < kStage * kTile; i += 256) {
+      const int r = i / kTile, c = i % kTile;
+      const int nn = n0 + r;
+      us[r][c] = (nn < n && k0 + c < K) ? ub[(long)nn * K + k0 + c] : 0.0f;
+      xs[r][c] = (nn < n && d0 + c < D) ? xb[(long)nn * D + d0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kStage; ++r) {
+      float uu[4], xx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uu[i] = us[r][ty * 4 + i];
+        xx[i] = xs[r][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float df = wv[i][j] - xx[j];
+          acc[i][j] = fmaf(df * df, uu[i], acc[i][j]);   // padded n have u = 0
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+    const float cs = csum[ty * 4 + i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + tx * 4 + j;
+      if (d >= D) continue;
+      const long o = ((long)t * K + k) * D + d;
+      if (!keep_old || cs > kEps) s[o] = cs / fmaxf(acc[i][j], kEps);
+    }
+  }
+}
+
+// det[row] = 1/2 sum_d log(s[row,d] + eps)  (one warp per (task, class) row; em_gaussian_cov.py:127)
+__global__ void __launch_bounds__(128) half_logdet_kernel(const float* __restrict__ s, float* __restrict__ det, long rows,
+                                                          int D) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* p = s + row * D;
+  float acc = 0.0f;
+  for (int d = lane; d < D; d += 32) acc += logf(p[d] + kEps);
+  acc = warp_sum_f32(acc);
+  if (lane == 0) det[row] = 0.5f * acc;
 }
 
 // One warp per (task, query): logits from the squared distances, soft-max over the classes, optional one-hot.
@@ -179,22 +284,51 @@ centroids_kernel(const float* __restrict__ u, const float* __restrict__ x, float
 //   mode 1 (EM-Gaussian)   u = softmax(T * (-1/2 d2) + lambd * v / n)
 //   mode 2 (hard k-means)  u = one-hot(argmin_k softmax(+d2)), lowest index on ties, as torch.argmin of the soft-maxed values
 //   mode 3 (similarity)    u = softmax(T * s)   (initial assignment / prototype probabilities on visual features)
+//   mode 4 (EM-Gaussian, diagonal covariance)  u = softmax(-1/2 d2s + det + lambd * v / n)   (em_gaussian_cov.py:117-130)
+//   mode 5 (KL k-means)    u = one-hot(argmin_k div), NaN counts as the minimum like torch.argmin (kl_kmeans.py:174-177)
 // `u` may alias `d2`.  labels (optional) = argmax_k of the final u.
 __global__ void __launch_bounds__(128)
-assign_kernel(const float* d2, const float* __restrict__ v, float temperature, float lambd, float* u,
-              int* __restrict__ labels, int rows, int n, int K, int mode) {
+assign_kernel(const float* d2, const float* __restrict__ v, const float* __restrict__ bias, float temperature, float lambd,
+              float* u, int* __restrict__ labels, int rows, int n, int K, int mode) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int t = row / n;
   const float* x = d2 + (long)row * K;
   const float* vv = v ? v + (long)t * K : nullptr;
+  const float* bb = bias ? bias + (long)t * K : nullptr;
   float* out = u + (long)row * K;
+  if (mode == 5) {  // plain arg-min of the divergences, NaN first
+    float best = CUDART_INF_F;
+    int best_k = 0x7fffffff;
+    for (int k = lane; k < K; k += 32) {
+      float d = x[k];
+      d = (d != d) ? -CUDART_INF_F : d;
+      if (d < best) {
+        best = d;
+        best_k = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+      if (ob < best || (ob == best && ok < best_k)) {
+        best = ob;
+        best_k = ok;
+      }
+    }
+    if (best_k == 0x7fffffff) best_k = 0;  // every divergence +inf: torch.argmin returns the first index
+    for (int k = lane; k < K; k += 32) out[k] = (k == best_k) ? 1.0f : 0.0f;
+    if (lane == 0 && labels) labels[row] = best_k;
+    return;
+  }
   const float fn = (float)n;
   auto logit = [&](int k) -> float {
     const float d = x[k];
     if (mode == 2) return d;
     if (mode == 3) return temperature * d;
+    if (mode == 4) return (-0.5f * d + bb[k]) + (lambd * vv[k]) / fn;
     float l = temperature * (-0.5f * d);
     if (mode == 1) l += (lambd * vv[k]) / fn;
     return l;
@@ -273,30 +407,55 @@ cudaError_t kmeans_similarity(const float* a, const float* text, float scale, fl
   // batches of <= 64 * 65535 rows through blockIdx.y
   if (M > 64L * 65535) return cudaErrorInvalidValue;
   pair_kernel<0><<<dim3((K + kTile - 1) / kTile, (unsigned)((M + kTile - 1) / kTile), 1), 256, 0, st>>>(
-      a, text, u, (int)M, K, D, 0, 0, 0);
-  assign_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(u, nullptr, scale, 0.0f, u, nullptr, (int)M, 1, K, 3);
+      a, text, nullptr, u, (int)M, K, D, 0, 0, 0);
+  assign_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(u, nullptr, nullptr, scale, 0.0f, u, nullptr, (int)M, 1, K, 3);
   note_launch(2);
   return cudaGetLastError();
 }
 
-cudaError_t kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int keep_old,
+cudaError_t kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int mode,
                              cudaStream_t st) {
-  centroids_kernel<<<dim3((D + kTile - 1) / kTile, (K + kTile - 1) / kTile, T), 256, 0, st>>>(u, x, w, n, K, D, keep_old);
+  centroids_kernel<<<dim3((D + kTile - 1) / kTile, (K + kTile - 1) / kTile, T), 256, 0, st>>>(u, x, w, n, K, D, mode);
   note_launch();
   return cudaGetLastError();
 }
 
 cudaError_t kmeans_sqdist(const float* x, const float* w, float* d2, int T, int n, int K, int D, cudaStream_t st) {
   pair_kernel<1><<<dim3((K + kTile - 1) / kTile, (n + kTile - 1) / kTile, T), 256, 0, st>>>(
-      x, w, d2, n, K, D, (long)n * D, (long)K * D, (long)n * K);
+      x, w, nullptr, d2, n, K, D, (long)n * D, (long)K * D, (long)n * K);
   note_launch();
   return cudaGetLastError();
 }
 
-cudaError_t kmeans_assign(const float* d2, const float* v, float temperature, float lambd, float* u, int* labels, int T,
-                          int n, int K, int mode, cudaStream_t st) {
+cudaError_t kmeans_precisions(const float* u, const float* x, const float* w, float* s, int T, int n, int K, int D,
+                              int keep_old, cudaStream_t st) {
+  precisions_kernel<<<dim3((D + kTile - 1) / kTile, (K + kTile - 1) / kTile, T), 256, 0, st>>>(u, x, w, s, n, K, D,
+                                                                                              keep_old);
+  note_launch();
+  return cudaGetLastError();
+}
+
+// d2s[t,n,k] = sum_d s (w - x)^2 and det[t,k] = 1/2 sum_d log(s + eps)
+cudaError_t kmeans_sqdist_cov(const float* x, const float* w, const float* s, float* d2s, float* det, int T, int n, int K,
+                              int D, cudaStream_t st) {
+  pair_kernel<2><<<dim3((K + kTile - 1) / kTile, (n + kTile - 1) / kTile, T), 256, 0, st>>>(
+      x, w, s, d2s, n, K, D, (long)n * D, (long)K * D, (long)n * K);
+  half_logdet_kernel<<<(unsigned)(((long)T * K + 3) / 4), 128, 0, st>>>(s, det, (long)T * K, D);
+  note_launch(2);
+  return cudaGetLastError();
+}
+
+cudaError_t kmeans_kl_div(const float* x, const float* w, float* div, int T, int n, int K, int D, cudaStream_t st) {
+  pair_kernel<3><<<dim3((K + kTile - 1) / kTile, (n + kTile - 1) / kTile, T), 256, 0, st>>>(
+      x, w, nullptr, div, n, K, D, (long)n * D, (long)K * D, (long)n * K);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t kmeans_assign(const float* d2, const float* v, const float* bias, float temperature, float lambd, float* u,
+                          int* labels, int T, int n, int K, int mode, cudaStream_t st) {
   const int rows = T * n;
-  assign_kernel<<<(rows + 3) / 4, 128, 0, st>>>(d2, v, temperature, lambd, u, labels, rows, n, K, mode);
+  assign_kernel<<<(rows + 3) / 4, 128, 0, st>>>(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode);
   note_launch();
   return cudaGetLastError();
 }

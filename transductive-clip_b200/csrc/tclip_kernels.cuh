@@ -87,11 +87,16 @@ cudaError_t cluster_prototypes(const int* labels, const float* feats, int* clust
 cudaError_t normalize_rows(const float* x, float* out, long rows, int D, cudaStream_t st);
 cudaError_t kmeans_similarity(const float* a, const float* text, float scale, float* u, long M, int K, int D,
                               cudaStream_t st);
-cudaError_t kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int keep_old,
+cudaError_t kmeans_centroids(const float* u, const float* x, float* w, int T, int n, int K, int D, int mode,
                              cudaStream_t st);
+cudaError_t kmeans_precisions(const float* u, const float* x, const float* w, float* s, int T, int n, int K, int D,
+                              int keep_old, cudaStream_t st);
+cudaError_t kmeans_sqdist_cov(const float* x, const float* w, const float* s, float* d2s, float* det, int T, int n, int K,
+                              int D, cudaStream_t st);
+cudaError_t kmeans_kl_div(const float* x, const float* w, float* div, int T, int n, int K, int D, cudaStream_t st);
 cudaError_t kmeans_sqdist(const float* x, const float* w, float* d2, int T, int n, int K, int D, cudaStream_t st);
-cudaError_t kmeans_assign(const float* d2, const float* v, float temperature, float lambd, float* u, int* labels, int T,
-                          int n, int K, int mode, cudaStream_t st);
+cudaError_t kmeans_assign(const float* d2, const float* v, const float* bias, float temperature, float lambd, float* u,
+                          int* labels, int T, int n, int K, int mode, cudaStream_t st);
 cudaError_t kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long per_task,
                          cudaStream_t st);
 

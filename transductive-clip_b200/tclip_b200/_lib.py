@@ -72,6 +72,11 @@ SIGNATURES = {
     "tclip_normalize_rows": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "tclip_kmeans_similarity": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "tclip_kmeans_centroids": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tclip_kmeans_precisions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p]),
+    "tclip_kmeans_assign_cov": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                        c_int, c_int, c_int, c_int, c_void_p]),
+    "tclip_kmeans_assign_kl": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tclip_kmeans_assign": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_int,
                                     c_int, c_int, c_int, c_void_p]),
     "tclip_kmeans_udiff": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),

@@ -168,4 +168,62 @@ class EM_GAUSSIAN(_KMeansBase):
         self.lambd = int(args.num_classes_test / 5) * args.n_query
 
 
+class EM_GAUSSIAN_COV(_KMeansBase):
+    """EM-Gaussian with diagonal covariance (``src/methods/zero_shot/em_gaussian_cov.py:97-257``): centroids w, diagonal
+    precisions s, responsibilities u = softmax(-1/2 sum_d s (w - x)^2 + 1/2 sum_d log s + lambda v / n) — no temperature in
+    the E-step — and the class-proportion dual v."""
+    _title = "EM_GAUSSIAN_COV"
+
+    def __init__(self, model, device, log_file, args):
+        super().__init__(model, device, log_file, args)
+        self.lambd = int(args.num_classes_test / 5) * args.n_query
+        self.s = None
+
+    def run_method(self, query, y_q):
+        self.logger.info(" ==> Executing {} with T = {}".format(self._title, self.args.T))
+        n_task, n_class = query.shape[0], self.args.num_classes_test
+        self.v = torch.zeros(n_task, n_class, device=self.device)
+        self.u = self._initial_u(query)
+        self.w = ops.kmeans_centroids(self.u, query, None)                  # w_init
+        self.s = ops.kmeans_precisions(self.u, query, self.w, None)        # s_init
+        zero = torch.zeros((), device=self.device)
+        for _ in range(self.iter):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            self.w = ops.kmeans_centroids(self.u, query, self.w, keep_old=True)
+            self.s = ops.kmeans_precisions(self.u, query, self.w, self.s)
+            self.u, self.labels = ops.kmeans_assign_cov(query, self.w, self.s, self.v, float(self.lambd))
+            _, self.v, _ = ops.colsum_v(self.u, want_v=True, want_live=False)
+            t1.record()
+            t1.synchronize()
+            self.record_convergence(new_time=t0.elapsed_time(t1) / 1000.0 / n_task, criterions=zero)
+        self.compute_acc_clustering(query, y_q)
+
+
+class KL_KMEANS(_KMeansBase):
+    """KL k-means (``src/methods/zero_shot/kl_kmeans.py:114-189``): centroids = cluster means (size clamped at 1), hard
+    assignment to the centroid of minimum KL(x || w); the criterion is recorded twice per iteration as upstream."""
+    _title = "KL KMEANS"
+
+    def run_method(self, query, y_q):
+        self.logger.info(" ==> Executing {} with T = {}".format(self._title, self.args.T))
+        n_task = query.shape[0]
+        self.u = self._initial_u(query)
+        u_old = self.u.clone()
+        self.w = None
+        for _ in range(self.iter):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            self.w = ops.kmeans_centroids(self.u, query, self.w, mode=ops.CENTROIDS_KL)
+            self.u, self.labels = ops.kmeans_assign_kl(query, self.w)
+            crit = ops.kmeans_udiff(u_old, self.u)[0]
+            u_old = self.u.clone()
+            t1.record()
+            t1.synchronize()
+            dt = t0.elapsed_time(t1) / 1000.0
+            self.record_convergence(new_time=dt, criterions=crit)            # kl_kmeans.py:181 (un-normalised) ...
+            self.record_convergence(new_time=dt / n_task, criterions=crit)   # ... and :186-187
+        self.compute_acc_clustering(query, y_q)
+
+
 BASE = _KMeansBase

@@ -12,7 +12,7 @@ from ._lib import DirichletProblem, TCLIP_MM_DENSE, TCLIP_MM_SKIP_DEAD, check
 
 __all__ = ["log_features", "colsum_v", "moments", "support_stats", "mm_update_alpha", "commit", "estep",
            "cluster_prototypes", "dirichlet_em", "device_check", "launch_count", "probe_issue_rate", "normalize_rows", "kmeans_similarity",
-           "kmeans_centroids", "kmeans_assign", "kmeans_udiff", "KMEANS_SOFT", "KMEANS_GAUSS", "KMEANS_HARD", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
+           "kmeans_centroids", "kmeans_assign", "kmeans_udiff", "kmeans_precisions", "kmeans_assign_cov", "kmeans_assign_kl", "KMEANS_SOFT", "KMEANS_GAUSS", "KMEANS_HARD", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -175,19 +175,66 @@ def kmeans_similarity(a: torch.Tensor, text: torch.Tensor, scale: float) -> torc
     return u
 
 
-def kmeans_centroids(u: torch.Tensor, x: torch.Tensor, w: torch.Tensor | None, keep_old: bool) -> torch.Tensor:
+CENTROIDS_ZERO_EMPTY, CENTROIDS_KEEP_EMPTY, CENTROIDS_KL = 0, 1, 2
+
+
+def kmeans_centroids(u: torch.Tensor, x: torch.Tensor, w: torch.Tensor | None, keep_old: bool = False,
+                     mode: int | None = None) -> torch.Tensor:
     """Centroid update; ``w`` is updated in place (allocated when None: then empty clusters are zero)."""
     lib = _lib.load()
     _need(u, torch.float32, "u"), _need(x, torch.float32, "x")
     T, n, K = u.shape
     D = x.shape[2]
+    if mode is None:
+        mode = CENTROIDS_KEEP_EMPTY if (keep_old and w is not None) else CENTROIDS_ZERO_EMPTY
     if w is None:
         w = torch.empty(T, K, D, device=u.device, dtype=torch.float32)
-        keep_old = False
     else:
         _need(w, torch.float32, "w")
-    check(lib.tclip_kmeans_centroids(_ptr(u), _ptr(x), _ptr(w), T, n, K, D, int(bool(keep_old)), _stream()))
+    check(lib.tclip_kmeans_centroids(_ptr(u), _ptr(x), _ptr(w), T, n, K, D, int(mode), _stream()))
     return w
+
+
+def kmeans_precisions(u: torch.Tensor, x: torch.Tensor, w: torch.Tensor, s: torch.Tensor | None) -> torch.Tensor:
+    """Diagonal precisions; ``s`` is updated in place keeping the rows of empty clusters (allocated when None: s_init)."""
+    lib = _lib.load()
+    _need(u, torch.float32, "u"), _need(x, torch.float32, "x"), _need(w, torch.float32, "w")
+    T, n, K = u.shape
+    D = x.shape[2]
+    keep = s is not None
+    if s is None:
+        s = torch.empty(T, K, D, device=u.device, dtype=torch.float32)
+    else:
+        _need(s, torch.float32, "s")
+    check(lib.tclip_kmeans_precisions(_ptr(u), _ptr(x), _ptr(w), _ptr(s), T, n, K, D, int(keep), _stream()))
+    return s
+
+
+def kmeans_assign_cov(x: torch.Tensor, w: torch.Tensor, s: torch.Tensor, v: torch.Tensor, lambd: float):
+    """(u, labels) of EM-Gaussian with diagonal covariance."""
+    lib = _lib.load()
+    for t_, nm in ((x, "x"), (w, "w"), (s, "s"), (v, "v")):
+        _need(t_, torch.float32, nm)
+    T, n, D = x.shape
+    K = w.shape[1]
+    u = torch.empty(T, n, K, device=x.device, dtype=torch.float32)
+    det = torch.empty(T, K, device=x.device, dtype=torch.float32)
+    labels = torch.empty(T, n, device=x.device, dtype=torch.int32)
+    check(lib.tclip_kmeans_assign_cov(_ptr(x), _ptr(w), _ptr(s), _ptr(v), float(lambd), _ptr(det), _ptr(u), _ptr(labels),
+                                      T, n, K, D, _stream()))
+    return u, labels
+
+
+def kmeans_assign_kl(x: torch.Tensor, w: torch.Tensor):
+    """(one-hot u, labels) of KL k-means."""
+    lib = _lib.load()
+    _need(x, torch.float32, "x"), _need(w, torch.float32, "w")
+    T, n, D = x.shape
+    K = w.shape[1]
+    u = torch.empty(T, n, K, device=x.device, dtype=torch.float32)
+    labels = torch.empty(T, n, device=x.device, dtype=torch.int32)
+    check(lib.tclip_kmeans_assign_kl(_ptr(x), _ptr(w), _ptr(u), _ptr(labels), T, n, K, D, _stream()))
+    return u, labels
 
 
 def kmeans_assign(x: torch.Tensor, w: torch.Tensor, mode: int, temperature: float, v: torch.Tensor | None = None,
