@@ -13,12 +13,14 @@ MM early exit is batch-global); ``value`` = tasks of all ranks / max-over-ranks 
   value        inputs already resident in HBM (``run_method``), timed with CUDA events;
   e2e          the reference-facing call ``run_task(task_dic)`` with pinned HOST tensors: H2D + EM + D2H of the
                accuracies inside the timed region;
-  roofline     the dominant kernel (mm_chunk_kernel, the MM M-step): algorithmic flop (74 per element-update,
-               SURVEY.md §8(d)) of the element-updates actually executed / M-step device time from CUDA events
-               recorded on the launching stream inside the C driver; peak = FP32 FMA issue rate measured by the
-               library's register-only microbenchmark right after the timed steps (MEASURED_PEAKS.json has no FP32 line);
+  roofline     the dominant kernel (mm_chunk_kernel, the MM M-step) run alone on a full batch of rows (T*K rows x D, two
+               launches = the first 101 MM iterations of an M-step): algorithmic flop (74 per element-update, SURVEY.md
+               §8(d)) / launch time from CUDA events on the launching stream; peak = FP32 FMA issue rate measured by the
+               library's register-only microbenchmark in the same run (MEASURED_PEAKS.json has no FP32 line).
+               ``in_step`` carries the same counters of the M-steps inside the timed steps (CUDA events recorded by the
+               C driver around every M-step);
   cpu_baseline the restated oracle (a port of the reference's CPU path; the Python reference itself cannot travel to
-               the GPU box) on a bounded sample: 1 task, 2 outer iterations, extrapolated to ``iter`` iterations.
+               the GPU box) on a bounded sample: 1 task, 8 outer iterations, extrapolated to ``iter`` iterations.
 """
 from __future__ import annotations
 
@@ -41,6 +43,7 @@ TASKS_PER_BATCH = 75
 FLOP_PER_UPDATE = 74.0      # canonical FP32 flop (FMA = 2) of one MM element-update
 MUFU_PER_UPDATE = 4.0       # this kernel: rcp(X P), lg2 P, sqrt, rcp (tclip_math.cuh); ln X is a polynomial
 SEED = 2020                 # the reference's default seed (config/datasets_config/*.yaml:10)
+CPU_SAMPLE_ITERS = 8         # outer iterations of the bounded CPU sample (~10-20 s of CPU work at K=D=1000)
 
 
 def parse():
@@ -122,9 +125,9 @@ class ClockSampler(threading.Thread):
 # CPU arm: the oracle port on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
 def cpu_sample(a, iters_full: int, dense_updates_per_task: float | None = None):
-    """One bounded sample of the CPU path: the restated oracle on 1 task of the same workload, 2 outer iterations
-    (outer iteration 0 exits its MM loop early, every later one runs all 1000 MM iterations), timed per
-    outer iteration and extrapolated:  seconds/task = t_iter0 + (iter - 1) * t_iter1 + t_accuracy."""
+    """One bounded sample of the CPU path: the restated oracle on 1 task of the same workload, CPU_SAMPLE_ITERS outer
+    iterations (outer iteration 0 exits its MM loop early, every later one runs all 1000 MM iterations),
+    timed per outer iteration and extrapolated:  seconds/task = t_iter0 + (iter - 1) * mean(t_iter1..) + t_accuracy."""
     import torch
     from oracle import restated
     from tclip_b200 import tasks
@@ -132,18 +135,20 @@ def cpu_sample(a, iters_full: int, dense_updates_per_task: float | None = None):
     torch.set_num_threads(cores)
     td, _ = tasks.make_zero_shot_batch(1, a.classes, n_query=N_QUERY, seed=SEED, batch_index=10_000)
     t0 = time.time()
-    r = restated.dirichlet_zero_shot(td["x_q"], td["y_q"], a.classes, iters=2, hard=(a.method == "hard"))
+    n_it = min(CPU_SAMPLE_ITERS, iters_full)
+    r = restated.dirichlet_zero_shot(td["x_q"], td["y_q"], a.classes, iters=n_it, hard=(a.method == "hard"))
     wall = time.time() - t0
-    t_it0, t_it1 = r.iter_seconds[0], r.iter_seconds[1]
-    t_acc = max(wall - t_it0 - t_it1, 0.0)
+    t_it0 = r.iter_seconds[0]
+    t_it1 = sum(r.iter_seconds[1:]) / max(n_it - 1, 1)
+    t_acc = max(wall - sum(r.iter_seconds), 0.0)
     per_task = t_it0 + (iters_full - 1) * t_it1 + t_acc
     updates = float(sum(r.mm_iters)) * a.classes * a.classes
     return {
         "value": 1.0 / per_task, "unit": "tasks/s", "cores": cores, "kind": "port",
-        "sample": (f"oracle/restated.py (torch CPU fp32, {cores} threads) on 1 task K=D={a.classes}, 2 of {iters_full} outer "
-                   f"iterations measured ({r.mm_iters[0]} + {r.mm_iters[1]} MM iterations, {wall:.1f} s), extrapolated as "
-                   f"t_iter0 + {iters_full - 1} x t_iter1 + t_accuracy = {per_task:.1f} s/task"),
-        "element_updates_per_s": updates / (t_it0 + t_it1), "seconds_measured": wall,
+        "sample": (f"oracle/restated.py (torch CPU fp32, {cores} threads) on 1 task K=D={a.classes}, {n_it} of {iters_full} outer "
+                   f"iterations measured ({'+'.join(str(i) for i in r.mm_iters)} MM iterations, {wall:.1f} s), extrapolated as "
+                   f"t_iter0 + {iters_full - 1} x mean(t_iter1..) + t_accuracy = {per_task:.1f} s/task"),
+        "element_updates_per_s": updates / sum(r.iter_seconds), "seconds_measured": wall,
     }
 
 
@@ -169,8 +174,8 @@ def run_reference(a):
         "impl": "reference", "metric": "EM-Dirichlet tasks/sec (K=D=1000, N=75)", "value": v, "unit": "tasks/s",
         "n_gpus": a.gpus, "steps": len(vals), "warmup": a.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "note": "CPU arm: one step = one bounded sample (1 task, 2 outer iterations, "
-                   "extrapolated per task); host cores only, no GPU"},
+        "config": {"workload": name, "note": "CPU arm: one step = one bounded sample (1 task, %d outer iterations, "
+                   "extrapolated per task); host cores only, no GPU" % CPU_SAMPLE_ITERS},
         "cpu_baseline": last,
         "e2e": {"value": v, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -188,8 +193,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle.ref_loader import make_args   # attribute-dict config only (no oracle arithmetic on this arm)
     from tclip_b200 import ops, tasks
+    from tclip_b200.config import make_args
     from tclip_b200.methods.dirichlet import EM_DIRICHLET, HARD_EM_DIRICHLET
 
     rank = int(os.environ.get("RANK", "0"))

@@ -87,27 +87,17 @@ def load(module: str) -> types.ModuleType:
     return mod
 
 
-class Cfg(dict):
-    """Attribute-access dict, same surface as the reference's ``CfgNode`` (``src/utils.py:40-63``)."""
-
-    def __getattr__(self, name):
-        try:
-            return self[name]
-        except KeyError:
-            raise AttributeError(name)
-
-    def __setattr__(self, name, value):
-        self[name] = value
+def _product_config():
+    """``Cfg`` / ``make_args`` live in the product package (bench.py needs them without touching oracle/)."""
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "transductive-clip_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from tclip_b200 import config
+    return config
 
 
-def make_args(K: int, n_query: int = 75, iters: int = 20, iter_mm: int = 1000, k_eff: int = 5, T: float = 30,
-              use_softmax_feature: bool = True, graph_matching: bool = True, **extra) -> Cfg:
-    """The config keys the method classes read."""
-    cfg = Cfg(iter=iters, iter_mm=iter_mm, num_classes_test=K, n_class=K, n_query=n_query, k_eff=k_eff, T=T,
-              use_softmax_feature=use_softmax_feature, graph_matching=graph_matching,
-              classnames=[f"c{i}" for i in range(K)], template="a photo of a {}.")
-    cfg.update(extra)
-    return cfg
+Cfg = _product_config().Cfg
+make_args = _product_config().make_args
 
 
 def run_reference(method: str, setting: str, task_dic: dict, args: Cfg, model=None, shot: int | None = None):
