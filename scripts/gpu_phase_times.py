@@ -9,9 +9,10 @@ from tclip_b200.methods.dirichlet import EM_DIRICHLET, HARD_EM_DIRICHLET
 from oracle.ref_loader import make_args
 dev = torch.device("cuda:0")
 K, T = 1000, 75
+ONLY_SKIP = "--skip-only" in sys.argv
 for hard, iters in ((False, 20), (True, 10)):
     for mode in ("skip_dead", "dense"):
-        if mode == "dense" and hard: continue
+        if mode == "dense" and (hard or ONLY_SKIP): continue
         for rep in range(2):
             td, _ = tasks.make_zero_shot_batch(T, K, seed=2020, batch_index=rep)
             m = (HARD_EM_DIRICHLET if hard else EM_DIRICHLET)(model=None, device=dev, log_file=None, args=make_args(K, iters=iters, mm_mode=mode))

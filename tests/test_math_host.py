@@ -26,6 +26,7 @@ def shim():
     lib.tclip_host_psi1_N.argtypes = [f32p, f32p, f32p, ctypes.c_int]
     lib.tclip_host_mm_update.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
     lib.tclip_host_mm_update_pair.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
+    lib.tclip_host_mm_update_pair_split.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
     lib.tclip_host_digamma.argtypes = [ctypes.c_double]
     lib.tclip_host_digamma.restype = ctypes.c_double
     lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -89,6 +90,20 @@ def test_one_mm_update_matches_the_reference_formula(shim):
         err = np.abs(got - ref) / ref
         assert err.max() < 3e-4
         assert err[(a < 0.05) | (a > 1.0)].max() < 5e-6
+
+
+def test_two_phase_update_is_bit_identical(shim):
+    """mm_update_pre + mm_update_post (the software-pipelined form of mm_spec_kernel) == mm_update_pair, bit for bit,
+    on both sides of the small-a switch and for small and large row totals."""
+    g = np.random.default_rng(1)
+    a = np.concatenate([_grid(), g.uniform(0.01, 0.2, 400).astype(np.float32), g.uniform(0.5, 3e5, 400).astype(np.float32)])
+    a = np.ascontiguousarray(a[: a.size // 2 * 2])
+    y = -g.uniform(0.1, 35.0, a.size).astype(np.float32)
+    for s in (0.7, 12.5, 1000.0, 2.5e5):
+        out, out2 = np.empty_like(a), np.empty_like(a)
+        shim.tclip_host_mm_update_pair(a, y, out, a.size, s)
+        shim.tclip_host_mm_update_pair_split(a, y, out2, a.size, s)
+        assert np.array_equal(out.view(np.uint32), out2.view(np.uint32)), s
 
 
 def test_mm_rows_track_the_oracle(shim):

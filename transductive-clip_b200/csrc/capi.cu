@@ -99,6 +99,8 @@ struct EmWorkspace {
   int* dead_age;        // [rows] consecutive outer iterations the cluster has been empty
   int* gate;            // {n_live, row cap}: device-side choice between dense and row-wise E-step kernels
   int* split_gate;      // {n_live, kSplitCap}: device-side choice of the few-rows M-step kernel
+  double2* spec_terms;  // [n_checks][kSplitCap] criterion terms of the speculated rows
+  float* spec_snap;     // [n_checks][kSplitCap][D] their states right after every check iteration
   int* frozen;          // [rows] dead rows proven periodic (mm_chunk_kernel)
   float* snap;          // [rows, D] periodicity snapshots
   int* list_live;
@@ -143,6 +145,8 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
     w.dead_age = c.take<int>(rows);
     w.gate = c.take<int>(2);
     w.split_gate = c.take<int>(2);
+    w.spec_terms = c.take<double2>((nc ? nc : 1) * (size_t)kSplitCap);
+    w.spec_snap = c.take<float>((nc ? nc : 1) * (size_t)kSplitCap * D);
     w.frozen = c.take<int>(rows);
     w.snap = c.take<float>(rows * D);
     w.list_live = c.take<int>(rows);
@@ -596,6 +600,8 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       l.n_rows_dev = w.counts;
       l.split_gate = w.split_gate;
       l.split_cap = kSplitCap;
+      l.spec_terms = w.spec_terms;
+      l.spec_snap = w.spec_snap;
       l.n_rows = rows;
       l.n_blocks = tclip::mm_num_blocks(rows, true);
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nc > 0 ? w.extra : nullptr, st));

@@ -20,10 +20,11 @@
 //   * free-running rows (FR = true; the empty clusters of the skip-dead schedule): ignore the exit flag, store each
 //     row's own criterion terms per check point, and stop iterating a row as soon as its fp32 trajectory is *proven*
 //     periodic (bit-exact state comparison) — the remaining terms then follow by periodic extension;
-//   * mm_chunk_split_kernel: one row per CTA for the few live rows of that schedule.
+//   * mm_spec_kernel: one row per CTA and the whole M-step in one launch for the few live rows of that schedule.
 #include <cuda_runtime.h>
 
 #include <array>
+#include <cstdlib>
 #include <utility>
 
 #include "tclip_kernels.cuh"
@@ -70,7 +71,7 @@ struct ChunkArgs {
   double2* partials;       // [gridDim.x]
   MMState* state;
   const double2* extra;    // optional: criterion terms of rows that are not iterated (cached dead rows)
-  const int* split_gate;   // optional: {n_rows, cap}; n_rows <= cap => mm_chunk_split_kernel runs instead
+  const int* split_gate;   // optional: {n_rows, cap}; n_rows <= cap => mm_spec_kernel runs the M-step instead
   // free-running rows only
   double2* row_cache;      // [n_checks][rows_total]
   int n_checks;
@@ -139,7 +140,7 @@ template <int NP, bool FR>
 __global__ void __launch_bounds__(kMMThreads, kMMMinBlocks)
 mm_chunk_kernel(const ChunkArgs g) {
   if (!FR && g.state->done) return;  // an earlier chunk met the batch-global criterion: the M-step is over
-  if (g.split_gate && g.split_gate[0] <= g.split_gate[1]) return;  // few rows: mm_chunk_split_kernel takes this chunk
+  if (g.split_gate && g.split_gate[0] <= g.split_gate[1]) return;  // few rows: mm_spec_kernel runs this M-step
   // [warps][NP][32] pairs of -y, and for free-running rows a second slice: the state six iterations before the chunk end
   extern __shared__ float2 smem2[];
   __shared__ double2 red[kMMThreads];
@@ -307,104 +308,203 @@ mm_chunk_kernel(const ChunkArgs g) {
 }
 
 // Few-rows form (the live clusters of the skip-dead schedule: a few hundred rows per batch): one row per CTA, its
-// pairs dealt out to W warps so that the serial chain of one MM iteration is NPW pairs long instead of D/64, and the
-// machine is filled W times better.  Row total: warp partials through shared memory (ping-pong slots, one
-// __syncthreads per iteration), summed in warp order by every thread.  Runs iff split_gate[0] <= split_gate[1].
-template <int W, int NPW>
+// pairs dealt out to W warps so that the serial chain of one MM iteration is NPW pairs long instead of D/64.  Row total:
+// warp partials through shared memory (ping-pong slots, one __syncthreads per iteration), summed as a tree by every thread.
+//
+// The whole M-step runs in ONE launch, speculatively: rows are independent except through the batch-global exit test, so
+// every row simply iterates all iter_mm times and leaves, for each check point, its criterion terms and a snapshot of its
+// state right after the check iteration (the state the reference would return if it stopped there).
+// mm_spec_resolve_kernel then evaluates the checks in order with the terms of ALL rows (+ the cached dead rows) and, in
+// the rare case that one fires, mm_spec_apply_kernel restores the snapshot of that check.  Same arithmetic, same result,
+// no launch per 50 iterations.  Runs iff split_gate[0] <= split_gate[1].
+struct SpecArgs {
+  const float* alpha_in;
+  float* alpha_out;
+  const float* y;
+  const int* row_list;
+  const int* n_rows_dev;
+  const int* split_gate;
+  int D;
+  int iter_mm;
+  int check_every;
+  int n_checks;
+  int cap;              // rows the scratch is sized for (= grid size)
+  double2* terms;       // [n_checks][cap]
+  float* snap;          // [n_checks][cap][D]
+  const double2* extra; // optional [n_checks]
+  float tol;
+  MMState* state;       // iters_done out; `fired` check index in state->done_check
+};
+
+template <int W, int NPW, bool PIPE>
 __global__ void __launch_bounds__(32 * W)
-mm_chunk_split_kernel(const ChunkArgs g) {
-  if (g.state->done) return;
+mm_spec_kernel(const SpecArgs g) {
   if (!(g.split_gate[0] <= g.split_gate[1])) return;
+  if ((int)blockIdx.x >= *g.n_rows_dev) return;  // CTA-uniform
   __shared__ double part[2][W];
   __shared__ double2 wred[W];
-  __shared__ double2 red[32 * W];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int D = g.D;
-  const bool active = (int)blockIdx.x < *g.n_rows_dev;  // CTA-uniform
-  double2 cta_terms = make_double2(0.0, 0.0);
-  if (active) {
-    const long row = g.row_list[blockIdx.x];
-    const float* ain = g.alpha_in + row * D;
-    const float* yin = g.y + row * D;
-    float* aout = g.alpha_out + row * D;
+  const long row = g.row_list[blockIdx.x];
+  const float* ain = g.alpha_in + row * D;
+  const float* yin = g.y + row * D;
+  float* aout = g.alpha_out + row * D;
 
-    float2 a[NPW], ny[NPW], mask[NPW];
-    int dxs[NPW], dys[NPW];
+  float2 a[NPW], ny[NPW], mask[NPW];
+  int dxs[NPW], dys[NPW];
 #pragma unroll
-    for (int j = 0; j < NPW; ++j) {
-      const int jp = warp * NPW + j;
-      dxs[j] = (2 * jp) * 32 + lane;
-      dys[j] = (2 * jp + 1) * 32 + lane;
-      const bool okx = dxs[j] < D, oky = dys[j] < D;
-      mask[j] = make_float2(okx ? 1.0f : 0.0f, oky ? 1.0f : 0.0f);
-      a[j] = make_float2(okx ? ain[dxs[j]] : 1.0f, oky ? ain[dys[j]] : 1.0f);
-      ny[j] = make_float2(okx ? -__ldg(yin + dxs[j]) : 1.0f, oky ? -__ldg(yin + dys[j]) : 1.0f);
+  for (int j = 0; j < NPW; ++j) {
+    const int jp = warp * NPW + j;
+    dxs[j] = (2 * jp) * 32 + lane;
+    dys[j] = (2 * jp + 1) * 32 + lane;
+    const bool okx = dxs[j] < D, oky = dys[j] < D;
+    mask[j] = make_float2(okx ? 1.0f : 0.0f, oky ? 1.0f : 0.0f);
+    a[j] = make_float2(okx ? ain[dxs[j]] : 1.0f, oky ? ain[dys[j]] : 1.0f);
+    ny[j] = make_float2(okx ? -__ldg(yin + dxs[j]) : 1.0f, oky ? -__ldg(yin + dys[j]) : 1.0f);
+  }
+  // Software pipeline: the part of the next update that needs the pair only (mm_update_pre: both Stirling series, ln X,
+  // the reciprocals) is issued together with the row-total shuffles, so it runs in the shadow of the reduction, the CTA
+  // barrier and psi(s); what remains on the serial path after psi(s) is mm_update_post (~15 dependent operations).
+  PairPre pre[NPW];
+  auto row_total = [&](int parity) -> double {
+    float2 t = f2mul(a[0], mask[0]);
+#pragma unroll
+    for (int j = 1; j < NPW; ++j) t = f2fma(a[j], mask[j], t);
+    if (PIPE) {
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) pre[j] = mm_update_pre(a[j]);
     }
-    auto row_total = [&](int parity) -> double {
-      float2 t = f2mul(a[0], mask[0]);
+    const double ws = warp_sum_f64((double)(t.x + t.y));
+    if (lane == 0) part[parity][warp] = ws;
+    __syncthreads();
+    double pw[W];  // balanced tree: the total is on the serial path of every iteration
 #pragma unroll
-      for (int j = 1; j < NPW; ++j) t = f2fma(a[j], mask[j], t);
-      const double ws = warp_sum_f64((double)(t.x + t.y));
-      if (lane == 0) part[parity][warp] = ws;
-      __syncthreads();
-      double pw[W];  // balanced tree: the total is on the serial path of every iteration
+    for (int w = 0; w < W; ++w) pw[w] = part[parity][w];
 #pragma unroll
-      for (int w = 0; w < W; ++w) pw[w] = part[parity][w];
+    for (int st = 1; st < W; st <<= 1) {
 #pragma unroll
-      for (int st = 1; st < W; st <<= 1) {
-#pragma unroll
-        for (int w = 0; w + st < W; w += 2 * st) pw[w] += pw[w + st];
-      }
-      return pw[0];
-    };
-    double s = row_total(0);
-    for (int it = 0; it < g.n_iters - 1; ++it) {
-      const RowPsi rp = row_psi(s);
-#pragma unroll
-      for (int j = 0; j < NPW; ++j) a[j] = mm_update_pair(a[j], ny[j], rp);
-      s = row_total((it + 1) & 1);
+      for (int w = 0; w + st < W; w += 2 * st) pw[w] += pw[w + st];
     }
-    double dsq, asq;
-    {
-      const RowPsi rp = row_psi(s);
+    return pw[0];
+  };
+  double s = row_total(0);
+  int parity = 1;
+  int next_check = g.check_every > 0 ? g.check_every : 0x7fffffff, c = 0;
+  for (int l = 0; l < g.iter_mm; ++l) {
+    const RowPsi rp = row_psi(s);
+    float2 an[NPW];
+#pragma unroll
+    for (int j = 0; j < NPW; ++j) an[j] = PIPE ? mm_update_post(pre[j], a[j], ny[j], rp) : mm_update_pair(a[j], ny[j], rp);
+    if (l == next_check && c < g.n_checks) {
+      // check iteration: its criterion terms and a snapshot of the new state
       float2 d2 = make_float2(0.0f, 0.0f), a2 = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int j = 0; j < NPW; ++j) {
-        const float2 an = mm_update_pair(a[j], ny[j], rp);
-        const float2 df = f2mul(f2add(an, make_float2(-a[j].x, -a[j].y)), mask[j]);
+        const float2 df = f2mul(f2add(an[j], make_float2(-a[j].x, -a[j].y)), mask[j]);
         const float2 ao = f2mul(a[j], mask[j]);
         d2 = f2fma(df, df, d2);
         a2 = f2fma(ao, ao, a2);
-        a[j] = an;
       }
-      dsq = (double)(d2.x + d2.y);
-      asq = (double)(a2.x + a2.y);
+      const double dsq = warp_sum_f64((double)(d2.x + d2.y)), asq = warp_sum_f64((double)(a2.x + a2.y));
+      if (lane == 0) wred[warp] = make_double2(dsq, asq);
+      float* sn = g.snap + ((long)c * g.cap + blockIdx.x) * D;
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) {
+        if (dxs[j] < D) sn[dxs[j]] = an[j].x;
+        if (dys[j] < D) sn[dys[j]] = an[j].y;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          acc.x += wred[w].x;
+          acc.y += wred[w].y;
+        }
+        g.terms[(long)c * g.cap + blockIdx.x] = acc;
+      }
+      ++c;
+      next_check += g.check_every;
     }
 #pragma unroll
-    for (int j = 0; j < NPW; ++j) {
-      if (dxs[j] < D) aout[dxs[j]] = a[j].x;
-      if (dys[j] < D) aout[dys[j]] = a[j].y;
-    }
-    dsq = warp_sum_f64(dsq);
-    asq = warp_sum_f64(asq);
-    if (lane == 0) wred[warp] = make_double2(dsq, asq);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int w = 0; w < W; ++w) {
-        cta_terms.x += wred[w].x;
-        cta_terms.y += wred[w].y;
-      }
+    for (int j = 0; j < NPW; ++j) a[j] = an[j];
+    if (l + 1 < g.iter_mm) {
+      s = row_total(parity);
+      parity ^= 1;
     }
   }
-  finish_chunk<32 * W>(g, cta_terms, red);
+#pragma unroll
+  for (int j = 0; j < NPW; ++j) {
+    if (dxs[j] < D) aout[dxs[j]] = a[j].x;
+    if (dys[j] < D) aout[dys[j]] = a[j].y;
+  }
+}
+
+// One CTA: the checks in order, each over the terms of all speculated rows (fixed summation order) plus the cached dead
+// rows; the first one below tol fires.  state->iters_done and state->fired are what the reference would have ended with.
+__global__ void __launch_bounds__(256)
+mm_spec_resolve_kernel(const SpecArgs g) {
+  if (!(g.split_gate[0] <= g.split_gate[1])) return;
+  __shared__ double2 red[256];
+  __shared__ int fired;
+  if (threadIdx.x == 0) fired = -1;
+  __syncthreads();
+  const int n_rows = *g.n_rows_dev;
+  for (int c = 0; c < g.n_checks; ++c) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < n_rows; i += 256) {
+      const double2 p = g.terms[(long)c * g.cap + i];
+      acc.x += p.x;
+      acc.y += p.y;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if ((int)threadIdx.x < w) {
+        red[threadIdx.x].x += red[threadIdx.x + w].x;
+        red[threadIdx.x].y += red[threadIdx.x + w].y;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      double num = red[0].x, den = red[0].y;
+      if (g.extra) {
+        num += g.extra[c].x;
+        den += g.extra[c].y;
+      }
+      g.state->last_num = num;
+      g.state->last_den = den;
+      const float crit = (float)num / (float)den;
+      if (crit < g.tol) fired = c;
+    }
+    __syncthreads();
+    if (fired >= 0) break;
+  }
+  if (threadIdx.x == 0) {
+    g.state->fired = fired;
+    g.state->done = fired >= 0 ? 1 : 0;
+    g.state->iters_done = fired >= 0 ? (fired + 1) * g.check_every + 1 : g.iter_mm;
+  }
+}
+
+// Only if a check fired: every speculated row goes back to its state right after that check iteration.
+__global__ void __launch_bounds__(256)
+mm_spec_apply_kernel(const SpecArgs g) {
+  if (!(g.split_gate[0] <= g.split_gate[1])) return;
+  const int fired = g.state->fired;
+  if (fired < 0 || (int)blockIdx.x >= *g.n_rows_dev) return;
+  const long row = g.row_list[blockIdx.x];
+  const float* sn = g.snap + ((long)fired * g.cap + blockIdx.x) * g.D;
+  float* out = g.alpha_out + row * g.D;
+  for (int d = threadIdx.x; d < g.D; d += 256) out[d] = sn[d];
 }
 
 __global__ void mm_reset_kernel(MMState* state) {
   state->done = 0;
   state->iters_done = 0;
   state->ticket = 0u;
+  state->fired = -1;
   state->last_num = 0.0;
   state->last_den = 0.0;
 }
@@ -415,10 +515,12 @@ void launch_chunk(const ChunkArgs& g, int n_blocks, cudaStream_t st) {
   mm_chunk_kernel<NP, FR><<<n_blocks, kMMThreads, smem, st>>>(g);
 }
 
-template <int W, int NPW>
-void launch_split(const ChunkArgs& g, int n_blocks, cudaStream_t st) {
-  mm_chunk_split_kernel<W, NPW><<<n_blocks, 32 * W, 0, st>>>(g);
+template <int W, int NPW, bool PIPE = true>
+void launch_spec(const SpecArgs& g, cudaStream_t st) {
+  mm_spec_kernel<W, NPW, PIPE><<<g.cap, 32 * W, 0, st>>>(g);
 }
+
+using SpecFn = void (*)(const SpecArgs&, cudaStream_t);
 
 using ChunkFn = void (*)(const ChunkArgs&, int, cudaStream_t);
 
@@ -427,18 +529,29 @@ constexpr auto make_table(std::integer_sequence<int, I...>) {
   return std::array<ChunkFn, sizeof...(I)>{&launch_chunk<I + 1, FR>...};
 }
 
-// NP = ceil(D / 64) pairs dealt to W = min(8, NP) warps, NPW = ceil(NP / W) pairs each
-ChunkFn split_fn(int np) {
+// NP = ceil(D / 64) pairs dealt to W = min(4, NP) warps, NPW = ceil(NP / W) pairs each.  The kernel is issue-bound on the
+// SMs that hold two rows, and every warp repeats the row total and psi(s): 4 warps x 4 pairs measured 1.1 ms per
+// 1000-iteration M-step of 224 rows, 8 x 2 1.3 ms, 16 x 1 1.8 ms (profiles/r1_spec_kernel.md).
+SpecFn spec_fn(int np) {
+  static const int w = [] {
+    const char* e = std::getenv("TCLIP_SPEC_W");  // experiments only
+    return e ? std::atoi(e) : 4;
+  }();
+  static const int pipe = [] {
+    const char* e = std::getenv("TCLIP_SPEC_PIPE");  // experiments only
+    return e ? std::atoi(e) : 1;
+  }();
+  if (np > 8 && w == 2) return &launch_spec<2, 8, false>;
+  if (np > 8 && w == 8) return &launch_spec<8, 2>;
+  if (np > 12 && !pipe) return &launch_spec<4, 4, false>;
   switch (np) {
-    case 1: return &launch_split<1, 1>;
-    case 2: return &launch_split<2, 1>;
-    case 3: return &launch_split<3, 1>;
-    case 4: return &launch_split<4, 1>;
-    case 5: return &launch_split<5, 1>;
-    case 6: return &launch_split<6, 1>;
-    case 7: return &launch_split<7, 1>;
-    case 8: return &launch_split<8, 1>;
-    default: return &launch_split<8, 2>;
+    case 1: return &launch_spec<1, 1>;
+    case 2: return &launch_spec<2, 1>;
+    case 3: return &launch_spec<3, 1>;
+    case 4: return &launch_spec<4, 1>;
+    case 5: case 6: case 7: case 8: return &launch_spec<4, 2>;
+    case 9: case 10: case 11: case 12: return &launch_spec<4, 3>;
+    default: return &launch_spec<4, 4>;
   }
 }
 
@@ -527,12 +640,32 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
     }
     fn(g, p.n_blocks, st);
     note_launch();
-    if (p.split_gate) {
-      split_fn(np)(g, p.split_cap, st);
-      note_launch();
-    }
     if (has_check) ++check_idx;
     start = end + 1;
+  }
+  if (p.split_gate) {
+    // the few-rows alternative of the same M-step (the chunk kernels above returned at once if it is selected)
+    SpecArgs g{};
+    g.alpha_in = p.alpha_in;
+    g.alpha_out = p.alpha_out;
+    g.y = p.y;
+    g.row_list = p.row_list;
+    g.n_rows_dev = p.n_rows_dev;
+    g.split_gate = p.split_gate;
+    g.D = p.D;
+    g.iter_mm = iter_mm;
+    g.check_every = check_every;
+    g.n_checks = check_every > 0 ? (iter_mm - 1) / check_every : 0;
+    g.cap = p.split_cap;
+    g.terms = p.spec_terms;
+    g.snap = p.spec_snap;
+    g.extra = extra_checks;
+    g.tol = tol;
+    g.state = p.state;
+    spec_fn(np)(g, st);
+    mm_spec_resolve_kernel<<<1, 256, 0, st>>>(g);
+    mm_spec_apply_kernel<<<g.cap, 256, 0, st>>>(g);
+    note_launch(3);
   }
   return cudaGetLastError();
 }

@@ -30,6 +30,17 @@ void tclip_host_mm_update_pair(const float* a, const float* y, float* out, int n
     out[i + 1] = r.y;
   }
 }
+// the two-phase form used by mm_spec_kernel (must equal mm_update_pair bit for bit)
+void tclip_host_mm_update_pair_split(const float* a, const float* y, float* out, int n, double s) {
+  const tclip::RowPsi rp = tclip::row_psi(s);
+  for (int i = 0; i + 1 < n; i += 2) {
+    const tclip::float2 av = tclip::make_float2(a[i], a[i + 1]);
+    const tclip::PairPre pre = tclip::mm_update_pre(av);
+    tclip::float2 r = tclip::mm_update_post(pre, av, tclip::make_float2(-y[i], -y[i + 1]), rp);
+    out[i] = r.x;
+    out[i + 1] = r.y;
+  }
+}
 // rows x D MM iterations on the host: the CPU twin of the kernel's inner loop (row sum in double).
 // D = padded (even) row length, n_valid = real row length: like the kernel, padding never enters the row total.
 void tclip_host_mm_rows(float* alpha, const float* y, int rows, int D, int n_valid, int iters) {

@@ -23,6 +23,7 @@ struct MMState {          // lives in device memory; written only by the reset /
   int done;               // 1 once the batch-global criterion fell below tol
   int iters_done;         // MM iterations executed so far in this M-step
   unsigned int ticket;    // CTAs of the running chunk that have finished (the last one folds the criterion)
+  int fired;              // mm_spec path: index of the check point that met the criterion, -1 if none
   double last_num;        // ||a_new - a||^2 at the last check
   double last_den;        // ||a||^2      at the last check
 };
@@ -46,10 +47,12 @@ struct MMLaunch {
   int* frozen;            // free-running mode, optional: [rows_total] period (in chunks) of rows proven periodic, 0 = still iterating
   float* snap;            // free-running mode: [rows_total, D] chunk-end snapshots used for the periodicity proof
   unsigned long long* work_ctr;  // optional: += row-iterations executed (work accounting for the roofline)
-  // optional (needs row_list + n_rows_dev): device-side {n_rows, cap}; when n_rows <= cap the chunk is run by
-  // mm_chunk_split_kernel (one row per CTA) instead of the one-warp-per-row kernel.  split_cap CTAs are launched.
+  // optional (needs row_list + n_rows_dev): device-side {n_rows, cap}; when n_rows <= cap the whole M-step is run by
+  // mm_spec_kernel (one row per CTA, one launch) instead of the chunked one-warp-per-row kernel.
   const int* split_gate;
   int split_cap;
+  double2* spec_terms;    // [n_checks][split_cap]
+  float* spec_snap;       // [n_checks][split_cap][D]
 };
 
 int mm_max_dim();

@@ -286,6 +286,73 @@ TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, RowPsi rp) {
   return f2mul(num, make_float2(fast_rcp(den.x), fast_rcp(den.y)));
 }
 
+// The same update cut in two at the point where the row constant enters, for the latency-bound few-rows kernel
+// (mm_spec_kernel): mm_update_pre needs the pair only, so it is issued in the shadow of the row-total reduction and of
+// psi(s); mm_update_post is the short remainder.  Operation for operation the arithmetic of mm_update_pair (checked bit
+// for bit by tests/test_host_twin.py); the Taylor form for small a is evaluated unconditionally (no vote, no branch:
+// issue slots are free here).
+struct PairPre {
+  float2 ndP, rP, rX, z, nsp, M0, lnX, lnm, e23, LP, ts;
+};
+
+TCLIP_HD PairPre mm_update_pre(float2 a) {
+  PairPre p;
+  const float2 X = f2add(a, f2(5.0f));
+  const float2 w = f2fma(a, X, f2(5.0f));
+  const float2 P = f2fma(w, w, f2(-1.0f));
+  p.ndP = f2mul(w, f2fma(a, f2(-4.0f), f2(-10.0f)));
+  p.rX = make_float2(fast_rcp(X.x), fast_rcp(X.y));
+  p.rP = make_float2(fast_rcp(P.x), fast_rcp(P.y));
+  float2 m;
+  split_exponent(X.x, m.x, p.e23.x);
+  split_exponent(X.y, m.y, p.e23.y);
+  const float2 f = f2add(m, f2(-1.0f));
+  float2 lp = f2fma(f, f2(0.08671870082616806f), f2(-0.14378608763217926f));
+  lp = f2fma(f, lp, f2(0.14977926015853882f));
+  lp = f2fma(f, lp, f2(-0.16564473509788513f));
+  lp = f2fma(f, lp, f2(0.1995488703250885f));
+  lp = f2fma(f, lp, f2(-0.250016987323761f));
+  lp = f2fma(f, lp, f2(0.33334165811538696f));
+  p.lnm = f2fma(f2mul(f, f), f2fma(f, lp, f2(-0.5f)), f);
+  p.lnX = f2fma(p.e23, f2(kLn2 / 8388608.0f), p.lnm);
+  p.LP = make_float2(fast_lg2(P.x), fast_lg2(P.y));
+  p.z = f2mul(p.rX, p.rX);
+  float2 nsp = f2fma(p.z, f2(-1.0f / 252.0f), f2(1.0f / 120.0f));
+  p.nsp = f2fma(p.z, nsp, f2(-1.0f / 12.0f));
+  float2 nsg2 = f2fma(p.z, f2(-2.0f / 1260.0f), f2(2.0f / 360.0f));
+  nsg2 = f2fma(p.z, nsg2, f2(-2.0f / 12.0f));
+  p.M0 = f2fma(nsg2, p.rX, f2(2.0f * (5.0f - kHalfLn2Pi)));
+  float2 ts = f2fma(a, f2(2.0f * -0.864299380613076709f), f2(2.0f * 0.847785884987040950f));
+  ts = f2fma(a, ts, f2(2.0f * -0.829542204114695941f));
+  ts = f2fma(a, ts, f2(2.0f * 0.811742425283353644f));
+  ts = f2fma(a, ts, f2(2.0f * -0.801371268773062857f));
+  ts = f2fma(a, ts, f2(2.0f * 0.822467033424113218f));
+  p.ts = f2mul(ts, f2mul(a, a));
+  return p;
+}
+
+TCLIP_HD float2 mm_update_post(const PairPre& p, float2 a, float2 ny, RowPsi rp) {
+  const float2 nEd = f2fma(p.ndP, p.rP, f2fma(f2(-0.5f), p.rX, f2fma(p.nsp, p.z, f2(-rp.dpsi))));
+  const float2 a2 = f2add(a, a);
+  float2 M = f2fma(a2, f2(1.0f + rp.dpsi), f2fma(a2, nEd, p.M0));
+  M = f2fma(p.lnX, f2(-9.0f), M);
+  M = f2fma(p.LP, f2(2.0f * kLn2), M);
+  M.x = a.x < kSmallA ? p.ts.x : M.x;
+  M.y = a.y < kSmallA ? p.ts.y : M.y;
+  const float2 lnXs = f2fma(f2add(p.e23, f2(-rp.k23)), f2(kLn2 / 8388608.0f), p.lnm);
+  const float2 g = f2add(f2add(lnXs, nEd), ny);
+  const float2 nM = make_float2(-M.x, -M.y);
+  const float2 bt = f2fma(a, g, nM);
+  const float2 M4 = f2mul(M, f2(4.0f));
+  const float2 Dt = f2fma(bt, bt, M4);
+  const float2 r = make_float2(fast_sqrt(Dt.x), fast_sqrt(Dt.y));
+  const float2 q = make_float2(fabsf(bt.x) + r.x, fabsf(bt.y) + r.y);
+  const bool px = bt.x >= 0.0f, py = bt.y >= 0.0f;
+  const float2 num = f2mul(a2, make_float2(px ? 1.0f : q.x, py ? 1.0f : q.y));
+  const float2 den = make_float2(px ? q.x : M4.x, py ? q.y : M4.y);
+  return f2mul(num, make_float2(fast_rcp(den.x), fast_rcp(den.y)));
+}
+
 // psi(s) for the row total, s > 0, to ~1e-10 absolute: ln s from the (m-1)/(m+1) series in float64, reciprocals from a
 // MUFU seed + one Newton step (no division subroutine, no libm call).
 TCLIP_HD double rcp_f64(double x) {
