@@ -94,6 +94,15 @@ int tclip_dirichlet_commit(float* alpha, const float* work, const int* live, voi
 int tclip_dirichlet_estep(const float* alpha, const float* logz, const float* v, float lambd, void* norm, float* u,
                           int* labels, int T, int n, int K, int D, int hard, void* stream);
 
+/* The contraction inside the E-step on its own: l3[t,i,k] = sum_d logz[t,i,d] * (alpha[t,k,d] - 1), l3 [T,n,K].
+ * mode 0: tcgen05 tensor cores, 3 x TF32 split precision, running sum in round-to-nearest fp32 outside the tensor core
+ *         (what tclip_dirichlet_estep / tclip_dirichlet_em_run use; needs D % 4 == 0 and n <= 128, else TCLIP_ERR_INVALID);
+ * mode 1: the same with the sum left to the tensor core's accumulator (measurement of its truncation only);
+ * mode 2: the CUDA-core fp32 kernel (any shape).
+ * Replaces `(torch.log(query + eps) * (alpha - 1)).sum(-1)` of get_logits (zero_shot/em_dirichlet.py:37-38). */
+int tclip_dirichlet_contraction(const float* logz, const float* alpha, float* l3, int T, int n, int K, int D, int mode,
+                                void* stream);
+
 /* Inputs of the label matching: per task the clusters in order of first appearance among `labels`, their sizes, the
  * cluster index of every query, and proto[t,c,:] = mean raw feature of cluster c (rows c >= n_clusters[t] are 0).
  * All int outputs are int32; cluster_label/cluster_size/sample_cluster are [T,n], n_clusters [T], proto [T,n,D].

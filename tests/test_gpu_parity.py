@@ -196,6 +196,37 @@ def test_stage_estep_moments(dev):
             np.testing.assert_allclose(uu.cpu().numpy(), sm.numpy(), atol=2e-4)
 
 
+@pytest.mark.parametrize("T,n,K,D", [(2, 75, 20, 20), (3, 75, 100, 100), (2, 75, 136, 100), (2, 40, 1000, 1000),
+                                     (1, 128, 260, 64), (2, 75, 7, 1024)])
+def test_stage_contraction_tensor_cores(dev, T, n, K, D):
+    """tcgen05 3 x TF32 contraction (the E-step's GEMM) vs float64: as accurate as the CUDA-core fp32 kernel, on ragged
+    tiles too (K not a multiple of 128, D not a multiple of 32, n < 128); heavy-tailed alpha like a real EM state."""
+    from tclip_b200 import ops
+    g = torch.Generator().manual_seed(100 + K)
+    logz = torch.log(torch.softmax(5 * torch.randn(T, n, D, generator=g), -1) + 1e-15)
+    alpha = (0.03 + torch.exp(2.5 * torch.randn(T, K, D, generator=g))).clamp(max=3e5)
+    ref = torch.einsum("tnd,tkd->tnk", logz.double(), (alpha - 1.0).double())
+    scale = ref.abs().max().item()
+    out = {m: ops.contraction(logz.to(dev), alpha.to(dev), m).cpu().double() for m in ("tcgen05", "tcgen05_tmem_sum", "simt")}
+    rms = {m: (o - ref).pow(2).mean().sqrt().item() for m, o in out.items()}
+    mx = {m: (o - ref).abs().max().item() for m, o in out.items()}
+    assert mx["simt"] <= 2e-6 * scale, (mx, scale)
+    assert mx["tcgen05"] <= 2e-6 * scale, (mx, scale)
+    assert rms["tcgen05"] <= 2.0 * rms["simt"] + 1e-9 * scale, (rms, scale)
+    # the textbook loop (whole sum in the TMEM accumulator) is what the external fp32 sum protects against
+    assert mx["tcgen05_tmem_sum"] <= 1e-4 * scale, (mx, scale)
+
+
+def test_contraction_rejects_shapes_tma_cannot_address(dev):
+    from tclip_b200 import ops
+    from tclip_b200._lib import TclipError
+    logz = torch.zeros(1, 75, 50, device=dev)
+    alpha = torch.ones(1, 50, 50, device=dev)
+    with pytest.raises(TclipError):
+        ops.contraction(logz, alpha, "tcgen05")          # D % 4 != 0
+    assert torch.equal(ops.contraction(logz, alpha, "simt"), torch.zeros(1, 75, 50, device=dev))
+
+
 def test_stage_cluster_prototypes_and_matching(dev):
     from tclip_b200 import matching, ops
     g = torch.Generator().manual_seed(2)

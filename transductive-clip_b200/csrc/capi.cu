@@ -419,6 +419,20 @@ int tclip_dirichlet_estep(const float* alpha, const float* logz, const float* v,
   return TCLIP_OK;
 }
 
+int tclip_dirichlet_contraction(const float* logz, const float* alpha, float* l3, int T, int n, int K, int D, int mode,
+                                void* stream) {
+  if (!logz || !alpha || !l3 || T < 1 || n < 1 || K < 1 || D < 1 || mode < 0 || mode > 2)
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_contraction: bad arguments");
+  if (mode != 2 && !tclip::logits_tc_supported(n, K, D))
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_contraction: the tensor-core form needs D %% 4 == 0 and n <= 128 (n=%d, D=%d)", n, D);
+  if (int rc = current_device_ok()) return rc;
+  if (mode == 2)
+    TCLIP_CUDA(tclip::logits_simt(logz, alpha, l3, T, n, K, D, nullptr, (cudaStream_t)stream));
+  else
+    TCLIP_CUDA(tclip::logits_tc(logz, alpha, l3, T, n, K, D, nullptr, mode == 1, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
 int tclip_cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
                              int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D, void* stream) {
   if (!labels || !feats || !cluster_label || !cluster_size || !sample_cluster || !n_clusters || !proto || T < 1 ||

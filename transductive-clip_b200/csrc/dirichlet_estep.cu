@@ -13,6 +13,9 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+#include <string>
+
 #include "tclip_kernels.cuh"
 
 namespace tclip {
@@ -535,6 +538,24 @@ cudaError_t commit(float* alpha, const float* work, const int* live, const int* 
   return cudaGetLastError();
 }
 
+cudaError_t logits_simt(const float* logz, const float* alpha, float* l3, int T, int n, int K, int D, const int* gate,
+                        cudaStream_t st) {
+  logits_kernel<<<dim3((K + kLgTile - 1) / kLgTile, (n + kLgTile - 1) / kLgTile, T), 256, 0, st>>>(logz, alpha, l3, n, K,
+                                                                                                  D, gate);
+  note_launch(1);
+  return cudaGetLastError();
+}
+
+// The dense contraction runs on the tensor cores (contraction_tc.cu) whenever TMA can address the operands (D % 4 == 0,
+// n <= 128); other shapes take the CUDA-core kernel.  TCLIP_CONTRACTION=simt forces the latter (measurements).
+static bool use_tensor_cores(int n, int K, int D) {
+  static const bool forced_simt = [] {
+    const char* e = std::getenv("TCLIP_CONTRACTION");
+    return e && std::string(e) == "simt";
+  }();
+  return !forced_simt && logits_tc_supported(n, K, D);
+}
+
 // l3 == nullptr: the contraction is written into u and soft-maxed in place (stage entry point).  With a persistent l3
 // buffer and `sp`, only live clusters are recomputed (norm and l3 of empty clusters carry over from the last E-step).
 cudaError_t estep(const float* alpha, const float* logz, const float* v, float lambd, double* norm, float* l3, float* u,
@@ -544,9 +565,12 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
   float* dst = l3 ? l3 : u;
   const int* gate = (sp && l3) ? sp->gate : nullptr;
   lognorm_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, norm, l3 ? live : nullptr, rows, D);
-  logits_kernel<<<dim3((K + kLgTile - 1) / kLgTile, (n + kLgTile - 1) / kLgTile, T), 256, 0, st>>>(logz, alpha, dst, n,
-                                                                                                  K, D, gate);
-  note_launch(2);
+  note_launch(1);
+  if (use_tensor_cores(n, K, D)) {
+    if (cudaError_t e = logits_tc(logz, alpha, dst, T, n, K, D, gate, false, st)) return e;
+  } else {
+    if (cudaError_t e = logits_simt(logz, alpha, dst, T, n, K, D, gate, st)) return e;
+  }
   if (gate) {
     const int Dp = (D + kLgBK - 1) / kLgBK * kLgBK;
     logits_rows_kernel<<<sp->cap, 128, Dp * sizeof(float), st>>>(logz, alpha, dst, sp->rows_live, sp->n_live, n, K, D,

@@ -82,6 +82,13 @@ cudaError_t commit(float* alpha, const float* work, const int* live, const int* 
 cudaError_t estep(const float* alpha, const float* logz, const float* v, float lambd, double* norm, float* l3, float* u,
                   int* labels, int T, int n, int K, int D, int hard, const int* live, const SparseRows* sp,
                   cudaStream_t st);
+// contraction_tc.cu: l3 = logz . (alpha - 1)^T on tcgen05 (3 x TF32, fp32 round-to-nearest running sum outside the tensor
+// core); accumulate_in_tmem = true is the measurement-only variant that leaves the whole sum to the tensor core.
+bool logits_tc_supported(int n, int K, int D);
+cudaError_t logits_simt(const float* logz, const float* alpha, float* l3, int T, int n, int K, int D, const int* gate,
+                        cudaStream_t st);   // the CUDA-core form (dirichlet_estep.cu), any shape
+cudaError_t logits_tc(const float* logz, const float* alpha, float* l3, int T, int n, int K, int D, const int* gate,
+                      bool accumulate_in_tmem, cudaStream_t st);
 cudaError_t cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
                                int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
                                cudaStream_t st);

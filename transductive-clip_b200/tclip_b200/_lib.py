@@ -67,6 +67,7 @@ SIGNATURES = {
                                        c_int, c_void_p]),
     "tclip_dirichlet_estep": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int,
                                       c_int, c_int, c_int, c_int, c_void_p]),
+    "tclip_dirichlet_contraction": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tclip_cluster_prototypes": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_int, c_int, c_int, c_void_p]),
     "tclip_normalize_rows": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),

@@ -130,6 +130,21 @@ def estep(alpha: torch.Tensor, logz: torch.Tensor, v: torch.Tensor, lambd: float
     return u, labels
 
 
+CONTRACTION_MODES = {"tcgen05": 0, "tcgen05_tmem_sum": 1, "simt": 2}
+
+
+def contraction(logz: torch.Tensor, alpha: torch.Tensor, mode: str = "tcgen05") -> torch.Tensor:
+    """l3 [T,n,K] = sum_d logz[t,i,d] (alpha[t,k,d] - 1)  (get_logits, zero_shot/em_dirichlet.py:37-38)."""
+    lib = _lib.load()
+    _need(alpha, torch.float32, "alpha"), _need(logz, torch.float32, "logz")
+    T, K, D = alpha.shape
+    n = logz.shape[1]
+    l3 = torch.empty(T, n, K, device=alpha.device, dtype=torch.float32)
+    check(lib.tclip_dirichlet_contraction(_ptr(logz), _ptr(alpha), _ptr(l3), T, n, K, D, CONTRACTION_MODES[mode],
+                                          _stream()))
+    return l3
+
+
 def cluster_prototypes(labels: torch.Tensor, feats: torch.Tensor):
     """Inputs of the label matching: dict(cluster_label, cluster_size, sample_cluster [T,n] int32,
     n_clusters [T] int32, proto [T,n,D])."""
