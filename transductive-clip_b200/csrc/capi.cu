@@ -187,57 +187,82 @@ __global__ void zero_int_kernel(int* p, long n) {
 // Stable compaction of the row classes (single CTA so the order, hence every later summation order, is fixed):
 //   live rows                      -> list_live   (iterated in the main loop)
 //   dead rows without a valid cache -> list_new    (full trajectory once, terms cached)
+// Tiles of 1024 consecutive rows (coalesced), ballot + popc inside a warp, a 32-entry shuffle scan across the warps; one
+// barrier per tile (double-buffered warp totals).  counts = {n_live, n_new, changed}: `changed` says whether the set of
+// dead rows or any cached term differs from the previous outer iteration (else the cached sums stay valid).
 __global__ void __launch_bounds__(1024)
 classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ frozen,
                      int* __restrict__ dead_age, int* __restrict__ list_live, int* __restrict__ list_new,
                      int* __restrict__ counts, int* __restrict__ gate, int cap, int* __restrict__ split_gate,
                      int split_cap, unsigned long long* __restrict__ work_ctr, int rows) {
-  if (threadIdx.x == 0) *work_ctr = 0ull;
-  __shared__ int s_live[1024], s_new[1024];
-  const int per = (rows + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(rows, lo + per);
-  int nl = 0, nn = 0;
-  for (int r = lo; r < hi; ++r) {
-    if (live[r]) ++nl;
-    else if (!cache_valid[r]) ++nn;
+  __shared__ int wl[2][32], wn[2][32];
+  __shared__ int s_changed;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  if (threadIdx.x == 0) {
+    *work_ctr = 0ull;
+    s_changed = 0;
   }
-  s_live[threadIdx.x] = nl;
-  s_new[threadIdx.x] = nn;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-    const int a = threadIdx.x >= o ? s_live[threadIdx.x - o] : 0;
-    const int b = threadIdx.x >= o ? s_new[threadIdx.x - o] : 0;
-    __syncthreads();
-    s_live[threadIdx.x] += a;
-    s_new[threadIdx.x] += b;
-    __syncthreads();
-  }
-  int pl = s_live[threadIdx.x] - nl, pn = s_new[threadIdx.x] - nn;
-  for (int r = lo; r < hi; ++r) {
-    dead_age[r] = live[r] ? 0 : dead_age[r] + 1;
-    if (live[r]) {
-      list_live[pl++] = r;
-      cache_valid[r] = 0;
-    } else if (!cache_valid[r]) {
-      list_new[pn++] = r;
-      cache_valid[r] = 1;
-      frozen[r] = 0;
+  int base_l = 0, base_n = 0, changed = 0;
+  for (int r0 = 0, tile = 0; r0 < rows; r0 += 1024, ++tile) {
+    const int r = r0 + threadIdx.x;
+    const bool in = r < rows;
+    const bool l = in && live[r] != 0;
+    const int age = in ? dead_age[r] : 0;
+    const bool nw = in && !l && !cache_valid[r];
+    if (in && (l != (age == 0))) changed = 1;   // was live (age 0) and is not any more, or the reverse
+    const unsigned bl = __ballot_sync(0xffffffffu, l), bn = __ballot_sync(0xffffffffu, nw);
+    const int buf = tile & 1;
+    if (lane == 0) {
+      wl[buf][warp] = __popc(bl);
+      wn[buf][warp] = __popc(bn);
     }
+    __syncthreads();
+    const int vl = wl[buf][lane], vn = wn[buf][lane];  // lane i holds the totals of warp i
+    int sl = vl, sn = vn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, sl, o), b = __shfl_up_sync(0xffffffffu, sn, o);
+      if (lane >= o) {
+        sl += a;
+        sn += b;
+      }
+    }
+    const int tot_l = __shfl_sync(0xffffffffu, sl, 31), tot_n = __shfl_sync(0xffffffffu, sn, 31);
+    const int off_l = __shfl_sync(0xffffffffu, sl - vl, warp), off_n = __shfl_sync(0xffffffffu, sn - vn, warp);
+    if (in) {
+      dead_age[r] = l ? 0 : age + 1;
+      if (l) {
+        list_live[base_l + off_l + __popc(bl & lt)] = r;
+        cache_valid[r] = 0;
+      } else if (nw) {
+        list_new[base_n + off_n + __popc(bn & lt)] = r;
+        cache_valid[r] = 1;
+        frozen[r] = 0;
+      }
+    }
+    base_l += tot_l;
+    base_n += tot_n;
   }
-  if (threadIdx.x == 1023) {
-    counts[0] = s_live[1023];
-    counts[1] = s_new[1023];
-    gate[0] = s_live[1023] + s_new[1023];  // rows the row-wise kernels would have to touch
+  if (changed) s_changed = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    counts[0] = base_l;
+    counts[1] = base_n;
+    counts[2] = (s_changed || base_n > 0) ? 1 : 0;
+    gate[0] = base_l + base_n;  // rows the row-wise kernels would have to touch
     gate[1] = cap;
-    split_gate[0] = s_live[1023];
+    split_gate[0] = base_l;
     split_gate[1] = split_cap;
   }
 }
 
-// extra[c] = sum over dead rows of cache[row, c]  (one CTA per check, fixed order)
+// extra[c] = sum over dead rows of cache[row, c]  (one CTA per check, fixed order); kept from the previous outer iteration
+// when neither the set of dead rows nor any cached term changed (classify_rows_kernel)
 __global__ void __launch_bounds__(256)
 sum_cache_kernel(const int* __restrict__ live, const double2* __restrict__ cache, double2* __restrict__ extra, int rows,
-                 int n_checks) {
+                 int n_checks, const int* __restrict__ changed) {
+  if (!*changed) return;
   __shared__ double2 red[256];
   const int c = blockIdx.x;
   double2 acc = make_double2(0.0, 0.0);
@@ -556,6 +581,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     zero_int_kernel<<<(rows + 255) / 256, 256, 0, st>>>(w.dead_age, rows);
     tclip::note_launch(2);
     TCLIP_CUDA(cudaMemsetAsync(w.state_free, 0, sizeof(tclip::MMState), st));
+    TCLIP_CUDA(cudaMemsetAsync(w.extra, 0, sizeof(double2) * (size_t)(nc ? nc : 1), st));  // no dead rows yet
   }
 
   for (int it = 0; it < p->iters; ++it) {
@@ -607,7 +633,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       d.work_ctr = w.work_ctr;
       TCLIP_CUDA(tclip::mm_run(d, p->iter_mm, p->check_every, p->tol, nullptr, st));
       if (nc > 0) {
-        sum_cache_kernel<<<nc, 256, 0, st>>>(w.live, w.cache, w.extra, rows, nc);
+        sum_cache_kernel<<<nc, 256, 0, st>>>(w.live, w.cache, w.extra, rows, nc, w.counts + 2);
         tclip::note_launch();
       }
       l.row_list = w.list_live;
@@ -623,7 +649,9 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     if (p->mm_events && p->mm_events[2 * it + 1])
       TCLIP_CUDA(cudaEventRecord((cudaEvent_t)p->mm_events[2 * it + 1], st));
     int* n_live_dev = nullptr;
-    if (!few) {
+    if (skip) {
+      n_live_dev = w.counts;  // classify_rows_kernel counted them
+    } else if (!few) {
       count_live_kernel<<<1, 256, 0, st>>>(w.live, rows, p->n_live + it);
       tclip::note_launch();
       n_live_dev = p->n_live + it;

@@ -152,10 +152,20 @@ moments_rows_kernel(const float* __restrict__ u, const float* __restrict__ logz,
   __syncthreads();
   const float cs = colsum[row];
   const float* lb = logz + (long)t * n * D;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float acc = 0.0f;
-    for (int i = 0; i < n; ++i) acc = fmaf(ucol[i], lb[(long)i * D + d], acc);
-    out[d] = cs > kEps ? acc / fmaxf(cs, kEps) : -10.0f;
+  // four strided columns per thread at a time: the 75-step fma chain of a column is latency-bound, four of them overlap;
+  // every column still sums i = 0..n-1 in order (bit-identical to moments_kernel)
+  for (int d0 = threadIdx.x; d0 < D; d0 += 4 * blockDim.x) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int i = 0; i < n; ++i) {
+      const float ui = ucol[i];
+      const float* li = lb + (long)i * D + d0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (d0 + j * (int)blockDim.x < D) acc[j] = fmaf(ui, li[j * blockDim.x], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (d0 + j * (int)blockDim.x < D) out[d0 + j * blockDim.x] = cs > kEps ? acc[j] / fmaxf(cs, kEps) : -10.0f;
   }
 }
 
@@ -333,40 +343,107 @@ logits_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, f
 }
 
 // Row-wise form for the skip-dead schedule: only the columns of live clusters change between E-steps (an empty cluster
-// keeps its alpha row, hence its column of l3), so one CTA per live row recomputes l3[t, :, k]; thread = query n, with the
-// same blocked fma order as logits_kernel => bit-identical values.
+// keeps its alpha row, hence its column of l3), so one CTA per live row recomputes l3[t, :, k].
 __global__ void __launch_bounds__(128)
 logits_rows_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, float* __restrict__ l3,
                    const int* __restrict__ rows, const int* __restrict__ n_rows, int n, int K, int D,
                    const int* __restrict__ gate) {
   if (dense_selected(gate)) return;
   if ((int)blockIdx.x >= *n_rows) return;
-  extern __shared__ float am1[];  // [D rounded up to kLgBK] alpha - 1, zero padded
+  extern __shared__ float am1[];  // [D] alpha - 1
   const int row = rows[blockIdx.x];
   const int t = row / K, k = row % K;
-  const int Dp = (D + kLgBK - 1) / kLgBK * kLgBK;
   const float* a = alpha + (long)row * D;
-  for (int d = threadIdx.x; d < Dp; d += blockDim.x) am1[d] = d < D ? a[d] - 1.0f : 0.0f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) am1[d] = a[d] - 1.0f;
   __syncthreads();
-  for (int nn = threadIdx.x; nn < n; nn += blockDim.x) {
-    const float* z = logz + ((long)t * n + nn) * D;
-    float acc = 0.0f;
-    for (int d0 = 0; d0 < Dp; d0 += kLgBK) {
-      float part = 0.0f;
+  // a warp takes four queries at a time: lanes stride over d (coalesced 128-byte reads of log z), four independent
+  // accumulators, one shuffle tree each
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (int n0 = warp * 4; n0 < n; n0 += n_warps * 4) {
+    const float* z0 = logz + ((long)t * n + n0) * D;
+    const int nq = min(4, n - n0);
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) {
+      const float b = am1[d];
 #pragma unroll
-      for (int c = 0; c < kLgBK; ++c) {
-        const int d = d0 + c;
-        part = fmaf(d < D ? z[d] : 0.0f, am1[d], part);
-      }
-      acc += part;
+      for (int q = 0; q < 4; ++q)
+        if (q < nq) acc[q] = fmaf(z0[(long)q * D + d], b, acc[q]);
     }
-    l3[((long)t * n + nn) * K + k] = acc;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float tot = warp_sum_f32(acc[q]);
+      if (lane == 0 && q < nq) l3[((long)t * n + n0 + q) * K + k] = tot;
+    }
   }
 }
 
 // ---- responsibilities: u = softmax_k(norm + l3 + lambda v / n); optional argmax -> one-hot ------------------------
 // One warp per (task, query).  labels = argmax of the *softmaxed* float32 values, first index wins
 // (hard_em_dirichlet.py:256-258).  `u` may alias `l3` (each warp reads its row before overwriting it).
+// K <= 1024: the 32 logits of a lane stay in registers (one pass over l3 / norm / v, one expf per element); same
+// arithmetic and the same per-lane summation order as the general kernel below => identical results.
+__global__ void __launch_bounds__(128)
+softmax_reg_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
+                   float* u, int* __restrict__ labels, int rows, int n, int K, int hard) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int t = row / n;
+  const float* x = l3 + (long)row * K;
+  const double* nm = norm + (long)t * K;
+  const float* vv = v + (long)t * K;
+  float* out = u + (long)row * K;
+  const float fn = (float)n;
+  float lg[32];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int k = lane + 32 * j;
+    if (k < K) {
+      lg[j] = (float)(nm[k] + (double)x[k]) + (lambd * vv[k]) / fn;
+      mx = fmaxf(mx, lg[j]);
+    }
+  }
+  mx = warp_max_f32(mx);
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (lane + 32 * j < K) {
+      lg[j] = expf(lg[j] - mx);
+      sum += lg[j];
+    }
+  }
+  sum = warp_sum_f32(sum);
+  float best = -1.0f;
+  int best_k = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int k = lane + 32 * j;
+    if (k < K) {
+      const float p = lg[j] / sum;
+      if (p > best) {  // strict: the lowest k of this lane's stripe wins ties
+        best = p;
+        best_k = k;
+      }
+      if (!hard) out[k] = p;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    if (ob > best || (ob == best && ok < best_k)) {
+      best = ob;
+      best_k = ok;
+    }
+  }
+  if (hard) {
+    for (int k = lane; k < K; k += 32) out[k] = (k == best_k) ? 1.0f : 0.0f;
+  }
+  if (lane == 0 && labels) labels[row] = best_k;
+}
+
 __global__ void __launch_bounds__(128)
 softmax_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
                float* u, int* __restrict__ labels, int rows, int n, int K, int hard) {
@@ -572,13 +649,15 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
     if (cudaError_t e = logits_simt(logz, alpha, dst, T, n, K, D, gate, st)) return e;
   }
   if (gate) {
-    const int Dp = (D + kLgBK - 1) / kLgBK * kLgBK;
-    logits_rows_kernel<<<sp->cap, 128, Dp * sizeof(float), st>>>(logz, alpha, dst, sp->rows_live, sp->n_live, n, K, D,
+    logits_rows_kernel<<<sp->cap, 128, D * sizeof(float), st>>>(logz, alpha, dst, sp->rows_live, sp->n_live, n, K, D,
                                                                 gate);
     note_launch(1);
   }
   const int qrows = T * n;
-  softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard);
+  if (K <= 1024)
+    softmax_reg_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard);
+  else
+    softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard);
   note_launch(1);
   return cudaGetLastError();
 }

@@ -82,7 +82,11 @@ struct ChunkArgs {
   int snap_age;
   int snap_write;
   unsigned long long* work_ctr;
+  int fr_chunks;           // free-running rows: all chunks of the M-step in ONE launch (the state stays in registers);
+  int fr_chunk_iters;      // chunk 0 runs n_iters iterations, every later chunk fr_chunk_iters
 };
+
+constexpr int kSnapEvery = 3;  // snapshot fallback: detects chunk-periods 1..3 (iteration periods dividing 50, 100, 150)
 
 // The last CTA of a chunk to finish folds the per-CTA partials (fixed order => reproducible), applies the reference's
 // test `criterion < tol` (false for NaN, so a NaN never stops the loop) and keeps the executed-iteration count.
@@ -173,16 +177,43 @@ mm_chunk_kernel(const ChunkArgs g) {
     a[NP - 1] = make_float2(ok_x ? ain[dx] : 1.0f, ok_y ? ain[dy] : 1.0f);
     ny[(NP - 1) * 32] = make_float2(ok_x ? -__ldg(yin + dx) : 1.0f, ok_y ? -__ldg(yin + dy) : 1.0f);
 
+    // Free-running rows walk through all their chunks here (they never look at the batch-global exit flag, so nothing
+    // has to be decided between chunks); the other rows run the one chunk of this launch.
+    const int n_chunks = FR ? g.fr_chunks : 1;
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int n_iters = (FR && chunk > 0) ? g.fr_chunk_iters : g.n_iters;
+    const int check_idx = FR ? chunk : g.check_idx;
+    const int snap_age = FR ? (chunk == 0 ? 0 : ((chunk - 1) % kSnapEvery) + 1) : 0;
+    const bool snap_write = FR && (chunk % kSnapEvery == 0);
+    bool froze = false;
     // Free-running rows: the last six iterations of the chunk form a window W[0..6]; W[6] == W[0] (bit for bit) proves
     // the trajectory periodic with a period dividing 6, and the terms of window updates 2, 4 and 6 are then the terms
     // of every later check point (their distance to this one is a multiple of 50 == 2 mod 6 iterations).
-    const bool window = FR && g.n_iters >= 8;
-    const int n_plain = window ? g.n_iters - 6 : g.n_iters - 1;
+    const bool window = FR && n_iters >= 8;
+    const int n_plain = window ? n_iters - 6 : n_iters - 1;
     double s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
+    // one vote per row and iteration decides whether any element needs the small-a Taylor form (rare: fixed points sit
+    // above 1/35 and only transients dip below 1/16); the running minimum is taken while the new values are produced
+    float amin = fminf(a[0].x, a[0].y);
+#pragma unroll
+    for (int j = 1; j < NP; ++j) amin = fminf(amin, fminf(a[j].x, a[j].y));
     for (int it = 0; it < n_plain; ++it) {
       const RowPsi rp = row_psi(s);
+      const bool any_small = __any_sync(0xffffffffu, amin < kSmallA);
+      amin = 3.0e38f;
+      if (!any_small) {
 #pragma unroll
-      for (int j = 0; j < NP; ++j) a[j] = mm_update_pair(a[j], ny[j * 32], rp);
+        for (int j = 0; j < NP; ++j) {
+          a[j] = mm_update_pair<0>(a[j], ny[j * 32], rp);
+          amin = fminf(amin, fminf(a[j].x, a[j].y));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          a[j] = mm_update_pair<1>(a[j], ny[j * 32], rp);
+          amin = fminf(amin, fminf(a[j].x, a[j].y));
+        }
+      }
       s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     }
     if (FR && window) {
@@ -219,19 +250,21 @@ mm_chunk_kernel(const ChunkArgs g) {
       }
       if (k < n_tail) s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     }
+    if (!FR) {  // (the alpha of a free-running row is discarded: only its criterion terms are kept)
 #pragma unroll
-    for (int j = 0; j < NP - 1; ++j) {
-      aout[(2 * j) * 32 + lane] = a[j].x;
-      aout[(2 * j + 1) * 32 + lane] = a[j].y;
+      for (int j = 0; j < NP - 1; ++j) {
+        aout[(2 * j) * 32 + lane] = a[j].x;
+        aout[(2 * j + 1) * 32 + lane] = a[j].y;
+      }
+      if (ok_x) aout[dx] = a[NP - 1].x;
+      if (ok_y) aout[dy] = a[NP - 1].y;
     }
-    if (ok_x) aout[dx] = a[NP - 1].x;
-    if (ok_y) aout[dy] = a[NP - 1].y;
 
     if (!FR) {
       dsq_cta += (double)(d2.x + d2.y);
       asq_cta += (double)(a2.x + a2.y);
     } else {
-      if (g.work_ctr && lane == 0) atomicAdd(g.work_ctr, (unsigned long long)g.n_iters);  // row-iterations executed
+      if (g.work_ctr && lane == 0) atomicAdd(g.work_ctr, (unsigned long long)n_iters);  // row-iterations executed
       // (a) period dividing 6 iterations, proven inside this chunk
       bool same6 = window;
       if (window) {
@@ -247,8 +280,8 @@ mm_chunk_kernel(const ChunkArgs g) {
       int period_chunks = 0;
       if (!same6) {
         float* sn = g.snap + row * D;
-        bool same = g.snap_age > 0;
-        if (g.snap_age > 0) {
+        bool same = snap_age > 0;
+        if (snap_age > 0) {
 #pragma unroll
           for (int j = 0; j < NP - 1; ++j)
             same &= (sn[(2 * j) * 32 + lane] == a[j].x) & (sn[(2 * j + 1) * 32 + lane] == a[j].y);
@@ -257,8 +290,8 @@ mm_chunk_kernel(const ChunkArgs g) {
           same = __all_sync(0xffffffffu, same);
         }
         if (same) {
-          period_chunks = g.snap_age;
-        } else if (g.snap_write) {
+          period_chunks = snap_age;
+        } else if (snap_write) {
 #pragma unroll
           for (int j = 0; j < NP - 1; ++j) {
             sn[(2 * j) * 32 + lane] = a[j].x;
@@ -274,20 +307,23 @@ mm_chunk_kernel(const ChunkArgs g) {
       if (lane == 0) {
         double2* rc = g.row_cache + row;  // [n_checks][rows_total] so that the per-check sums read coalesced
         const long rs = g.rows_total;
-        rc[g.check_idx * rs] = make_double2(t6x, t6y);
+        rc[check_idx * rs] = make_double2(t6x, t6y);
         if (same6) {
-          for (int j = g.check_idx + 1; j < g.n_checks; ++j) {
-            const int ph = (2 * (j - g.check_idx)) % 6;
+          for (int j = check_idx + 1; j < g.n_checks; ++j) {
+            const int ph = (2 * (j - check_idx)) % 6;
             rc[j * rs] = ph == 0 ? make_double2(t6x, t6y) : (ph == 2 ? make_double2(t2x, t2y) : make_double2(t4x, t4y));
           }
           g.frozen[row] = 6;
         } else if (period_chunks > 0) {
           // state_end(c) == state_end(c - period)  =>  terms(j) == terms(j - period) for every later check j
-          for (int j = g.check_idx + 1; j < g.n_checks; ++j) rc[j * rs] = rc[(j - period_chunks) * rs];
+          for (int j = check_idx + 1; j < g.n_checks; ++j) rc[j * rs] = rc[(j - period_chunks) * rs];
           g.frozen[row] = period_chunks;
         }
       }
+      froze = same6 || period_chunks > 0;  // warp-uniform
     }
+    if (FR && froze) break;
+    }  // chunks
   }
 
   if (!FR) {
@@ -555,8 +591,6 @@ SpecFn spec_fn(int np) {
   }
 }
 
-constexpr int kSnapEvery = 3;  // snapshot fallback: detects chunk-periods 1..3 (iteration periods dividing 50, 100, 150)
-
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -609,7 +643,8 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
         has_check = 1;
       }
     }
-    if (free_run && !has_check) break;  // dead rows: alpha is discarded, only check terms matter -> no tail chunk
+    if (free_run && (!has_check || check_idx > 0)) break;  // dead rows: one launch walks all chunks (no tail chunk:
+                                                           // their alpha is discarded, only check terms matter)
     ChunkArgs g{};
     g.alpha_in = (start == 0) ? p.alpha_in : p.alpha_out;
     g.alpha_out = p.alpha_out;
@@ -633,10 +668,10 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
       g.rows_total = p.rows_total;
       g.frozen = p.frozen;
       g.snap = p.snap;
-      // periodicity snapshots every kSnapEvery chunks, compared at every chunk end in between
-      g.snap_age = check_idx == 0 ? 0 : ((check_idx - 1) % kSnapEvery) + 1;
-      g.snap_write = check_idx % kSnapEvery == 0 ? 1 : 0;
+      // periodicity snapshots every kSnapEvery chunks, compared at every chunk end in between (derived in the kernel)
       g.work_ctr = p.work_ctr;
+      g.fr_chunks = p.n_checks;
+      g.fr_chunk_iters = check_every;
     }
     fn(g, p.n_blocks, st);
     note_launch();

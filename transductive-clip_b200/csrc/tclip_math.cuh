@@ -222,6 +222,10 @@ struct RowPsi {
   float k23;   // k * 2^23 (exact)
 };
 
+// kSmall selects how the a < 1/16 Taylor form is handled: 2 = warp vote + uniform branch per pair (any caller), 1 = always
+// evaluated and selected per element, 0 = skipped — the caller has established that no element of the warp is below 1/16
+// (mm_chunk_kernel votes once per row and iteration on the running minimum instead of once per pair).
+template <int kSmall = 2>
 TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, RowPsi rp) {
   const float2 X = f2add(a, f2(5.0f));
   const float2 w = f2fma(a, X, f2(5.0f));
@@ -256,11 +260,14 @@ TCLIP_HD float2 mm_update_pair(float2 a, float2 ny, RowPsi rp) {
   M = f2fma(a2, f2(1.0f + rp.dpsi), f2fma(a2, nEd, M));            // 2a (-E) + 2a
   M = f2fma(lnX, f2(-9.0f), M);
   M = f2fma(LP, f2(2.0f * kLn2), M);
+  bool any_small = kSmall == 1;
+  if (kSmall == 2) {
 #if defined(__CUDA_ARCH__)
-  const bool any_small = __any_sync(0xffffffffu, (a.x < kSmallA) | (a.y < kSmallA));
+    any_small = __any_sync(0xffffffffu, (a.x < kSmallA) | (a.y < kSmallA));
 #else
-  const bool any_small = (a.x < kSmallA) | (a.y < kSmallA);
+    any_small = (a.x < kSmallA) | (a.y < kSmallA);
 #endif
+  }
   if (any_small) {
     // Taylor form of 2N for a < 1/16: 2 a^2 (c2 + c3 a + ... + c7 a^5), truncation < 1e-7 relative (warp-uniform branch:
     // with y >= log(1e-15) the fixed points sit above 1/35, so whole warps rarely come here)
