@@ -73,7 +73,7 @@ struct Carver {
 };
 
 constexpr int kSplitCap = 1480;   // the few-rows M-step kernel (one row per CTA) handles up to this many live rows
-constexpr int kSparseCap = 4096; // row-wise E-step kernels handle up to this many live + newly dead rows
+constexpr int kSparseCap = 4096; // row-wise E-step kernels handle up to this many live rows
 constexpr int kMaxChecks = 64;  // cached criterion terms per dead row (iter_mm / check_every must stay below)
 
 struct EmWorkspace {
@@ -176,8 +176,12 @@ int validate(const tclip_dirichlet_problem* p) {
 
 // ---- small driver-side kernels --------------------------------------------------------------------------------
 __global__ void fill_kernel(float* p, float v, long n) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n && (reinterpret_cast<unsigned long long>(p) & 15ull) == 0) {
+    *reinterpret_cast<float4*>(p + i) = make_float4(v, v, v, v);
+  } else {
+    for (long j = i; j < n; ++j) p[j] = v;
+  }
 }
 __global__ void zero_int_kernel(int* p, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,7 +254,7 @@ classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid
     counts[0] = base_l;
     counts[1] = base_n;
     counts[2] = (s_changed || base_n > 0) ? 1 : 0;
-    gate[0] = base_l + base_n;  // rows the row-wise kernels would have to touch
+    gate[0] = base_l;           // rows the row-wise kernels have to recompute (newly dead rows only get their y filled)
     gate[1] = cap;
     split_gate[0] = base_l;
     split_gate[1] = split_cap;
@@ -569,7 +573,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
   // initialisation: v = 0, u = query, alpha = 1 (em_dirichlet.py:202-210); features logged once
   TCLIP_CUDA(cudaMemsetAsync(p->v, 0, sizeof(float) * (size_t)rows, st));
   TCLIP_CUDA(cudaMemcpyAsync(p->u, p->x_q, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
-  fill_kernel<<<(unsigned)(((long)rows * D + 255) / 256), 256, 0, st>>>(p->alpha, 1.0f, (long)rows * D);
+  fill_kernel<<<(unsigned)(((long)rows * D + 1023) / 1024), 256, 0, st>>>(p->alpha, 1.0f, (long)rows * D);
   tclip::note_launch();
   TCLIP_CUDA(tclip::log_features(p->x_q, w.logz, (long)T * n * D, st));
   if (few) {

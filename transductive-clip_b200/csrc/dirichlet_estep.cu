@@ -139,13 +139,17 @@ moments_rows_kernel(const float* __restrict__ u, const float* __restrict__ logz,
                     float* __restrict__ y, const int* __restrict__ rows, const int* __restrict__ n_rows, int fill_only,
                     int n, int K, int D, const int* __restrict__ gate) {
   if (dense_selected(gate)) return;
+  if (fill_only) {  // newly empty clusters (any number of them): y = -10
+    const int nr = *n_rows;
+    for (int b = blockIdx.x; b < nr; b += gridDim.x) {
+      float* o = y + (long)rows[b] * D;
+      for (int d = threadIdx.x; d < D; d += blockDim.x) o[d] = -10.0f;
+    }
+    return;
+  }
   if ((int)blockIdx.x >= *n_rows) return;
   const int row = rows[blockIdx.x];
   float* out = y + (long)row * D;
-  if (fill_only) {
-    for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = -10.0f;
-    return;
-  }
   extern __shared__ float ucol[];  // [n] responsibilities of this cluster
   const int t = row / K, k = row % K;
   for (int i = threadIdx.x; i < n; i += blockDim.x) ucol[i] = u[((long)t * n + i) * K + k];
@@ -266,7 +270,8 @@ __global__ void criterion_mean_kernel(const float* __restrict__ task_crit, float
 // ---- Dirichlet log-normaliser: norm[t,k] = lnGamma(sum_d a) - sum_d lnGamma(a), float64, one warp per row --------
 __global__ void __launch_bounds__(128)
 lognorm_kernel(const float* __restrict__ alpha, double* __restrict__ norm, const int* __restrict__ live, int rows,
-               int D) {
+               int D, const int* __restrict__ gate) {
+  if (!dense_selected(gate)) return;  // few live rows: lognorm_rows_kernel
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -281,6 +286,32 @@ lognorm_kernel(const float* __restrict__ alpha, double* __restrict__ norm, const
   s = warp_sum_f64(s);
   lg = warp_sum_f64(lg);
   if (lane == 0) norm[row] = lgamma(s) - lg;
+}
+
+// Few live rows (skip-dead schedule): one CTA per live row, its D lgamma evaluations dealt to four warps.
+__global__ void __launch_bounds__(128)
+lognorm_rows_kernel(const float* __restrict__ alpha, double* __restrict__ norm, const int* __restrict__ rows,
+                    const int* __restrict__ n_rows, int D, const int* __restrict__ gate) {
+  if (dense_selected(gate)) return;
+  if ((int)blockIdx.x >= *n_rows) return;
+  __shared__ double ps[4], pl[4];
+  const int row = rows[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* a = alpha + (long)row * D;
+  double s = 0.0, lg = 0.0;
+  for (int d = threadIdx.x; d < D; d += 128) {
+    const double v = (double)a[d];
+    s += v;
+    lg += lgamma(v);
+  }
+  s = warp_sum_f64(s);
+  lg = warp_sum_f64(lg);
+  if (lane == 0) {
+    ps[warp] = s;
+    pl[warp] = lg;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) norm[row] = lgamma((ps[0] + ps[1]) + (ps[2] + ps[3])) - ((pl[0] + pl[1]) + (pl[2] + pl[3]));
 }
 
 // ---- contraction l3[t,n,k] = sum_d logz[t,n,d] (alpha[t,k,d] - 1): [n x D] . [D x K] per task ---------------------
@@ -641,7 +672,11 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
   const int rows = T * K;
   float* dst = l3 ? l3 : u;
   const int* gate = (sp && l3) ? sp->gate : nullptr;
-  lognorm_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, norm, l3 ? live : nullptr, rows, D);
+  lognorm_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, norm, l3 ? live : nullptr, rows, D, gate);
+  if (gate) {
+    lognorm_rows_kernel<<<sp->cap, 128, 0, st>>>(alpha, norm, sp->rows_live, sp->n_live, D, gate);
+    note_launch(1);
+  }
   note_launch(1);
   if (use_tensor_cores(n, K, D)) {
     if (cudaError_t e = logits_tc(logz, alpha, dst, T, n, K, D, gate, false, st)) return e;

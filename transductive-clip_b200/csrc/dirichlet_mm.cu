@@ -23,6 +23,7 @@
 //   * mm_spec_kernel: one row per CTA and the whole M-step in one launch for the few live rows of that schedule.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <array>
 #include <cstdlib>
 #include <utility>
@@ -479,40 +480,46 @@ mm_spec_kernel(const SpecArgs g) {
 
 // One CTA: the checks in order, each over the terms of all speculated rows (fixed summation order) plus the cached dead
 // rows; the first one below tol fires.  state->iters_done and state->fired are what the reference would have ended with.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 mm_spec_resolve_kernel(const SpecArgs g) {
   if (!(g.split_gate[0] <= g.split_gate[1])) return;
-  __shared__ double2 red[256];
+  __shared__ double2 tot[32];
   __shared__ int fired;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   if (threadIdx.x == 0) fired = -1;
   __syncthreads();
   const int n_rows = *g.n_rows_dev;
-  for (int c = 0; c < g.n_checks; ++c) {
-    double2 acc = make_double2(0.0, 0.0);
-    for (int i = threadIdx.x; i < n_rows; i += 256) {
-      const double2 p = g.terms[(long)c * g.cap + i];
-      acc.x += p.x;
-      acc.y += p.y;
+  // one warp per check point sums that check's terms (lane-strided, then a shuffle tree: a fixed order); thread 0 then
+  // walks the checks of the round in order
+  for (int c0 = 0; c0 < g.n_checks; c0 += n_warps) {
+    const int c = c0 + warp;
+    if (c < g.n_checks) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int i = lane; i < n_rows; i += 32) {
+        const double2 p = g.terms[(long)c * g.cap + i];
+        acc.x += p.x;
+        acc.y += p.y;
+      }
+      acc.x = warp_sum_f64(acc.x);
+      acc.y = warp_sum_f64(acc.y);
+      if (lane == 0) tot[warp] = acc;
     }
-    red[threadIdx.x] = acc;
     __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-      if ((int)threadIdx.x < w) {
-        red[threadIdx.x].x += red[threadIdx.x + w].x;
-        red[threadIdx.x].y += red[threadIdx.x + w].y;
-      }
-      __syncthreads();
-    }
     if (threadIdx.x == 0) {
-      double num = red[0].x, den = red[0].y;
-      if (g.extra) {
-        num += g.extra[c].x;
-        den += g.extra[c].y;
+      for (int w = 0; w < n_warps && c0 + w < g.n_checks; ++w) {
+        double num = tot[w].x, den = tot[w].y;
+        if (g.extra) {
+          num += g.extra[c0 + w].x;
+          den += g.extra[c0 + w].y;
+        }
+        g.state->last_num = num;
+        g.state->last_den = den;
+        const float crit = (float)num / (float)den;
+        if (crit < g.tol) {
+          fired = c0 + w;
+          break;
+        }
       }
-      g.state->last_num = num;
-      g.state->last_den = den;
-      const float crit = (float)num / (float)den;
-      if (crit < g.tol) fired = c;
     }
     __syncthreads();
     if (fired >= 0) break;
@@ -698,7 +705,7 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
     g.tol = tol;
     g.state = p.state;
     spec_fn(np)(g, st);
-    mm_spec_resolve_kernel<<<1, 256, 0, st>>>(g);
+    mm_spec_resolve_kernel<<<1, 32 * std::max(1, std::min(g.n_checks, 32)), 0, st>>>(g);
     mm_spec_apply_kernel<<<g.cap, 256, 0, st>>>(g);
     note_launch(3);
   }
