@@ -183,6 +183,8 @@ typedef struct tclip_dirichlet_problem {
   long long* mm_rows;                /* out [iters] rows actually iterated x iterations (work done), may be NULL */
   void* const* iter_events;          /* optional [iters] cudaEvent_t recorded after each outer iteration */
   void* const* mm_events;            /* optional [2*iters] cudaEvent_t recorded before / after each M-step */
+  double* mm_crit;                   /* optional out [iters][2]: (||a_new - a||^2, ||a||^2) over the whole batch at the last
+                                        check point each M-step evaluated (the two norms of em_dirichlet.py:170-171) */
 } tclip_dirichlet_problem;
 
 /* Runs zero_shot/em_dirichlet.py:195-244 (hard: zero_shot/hard_em_dirichlet.py:215-269) or, with n_support > 0,

@@ -304,8 +304,12 @@ __global__ void __launch_bounds__(256) count_live_kernel(const int* __restrict__
 
 __global__ void record_work_kernel(const tclip::MMState* state, const int* counts, const unsigned long long* work_ctr,
                                    const int* n_live_dev, int rows, int iter_mm, int* mm_iters, int* n_live,
-                                   long long* mm_rows) {
+                                   long long* mm_rows, double* mm_crit) {
   const int done = state->iters_done;
+  if (mm_crit) {
+    mm_crit[0] = state->last_num;
+    mm_crit[1] = state->last_den;
+  }
   *mm_iters = done;
   *n_live = n_live_dev ? *n_live_dev : rows;
   if (mm_rows) {
@@ -661,7 +665,8 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       n_live_dev = p->n_live + it;
     }
     record_work_kernel<<<1, 1, 0, st>>>(w.state, skip ? w.counts : nullptr, w.work_ctr, n_live_dev, rows, p->iter_mm,
-                                         p->mm_iters + it, p->n_live + it, p->mm_rows ? p->mm_rows + it : nullptr);
+                                         p->mm_iters + it, p->n_live + it, p->mm_rows ? p->mm_rows + it : nullptr,
+                                         p->mm_crit ? p->mm_crit + 2 * it : nullptr);
     tclip::note_launch();
     // empty clusters keep their previous row; logged criterion (em_dirichlet.py:224-226,236-238)
     TCLIP_CUDA(tclip::commit(p->alpha, w.work, few ? nullptr : w.live, skip ? w.dead_age : nullptr, w.rowstat,

@@ -190,8 +190,14 @@ mm_chunk_kernel(const ChunkArgs g) {
     // Free-running rows: the last six iterations of the chunk form a window W[0..6]; W[6] == W[0] (bit for bit) proves
     // the trajectory periodic with a period dividing 6, and the terms of window updates 2, 4 and 6 are then the terms
     // of every later check point (their distance to this one is a multiple of 50 == 2 mod 6 iterations).
-    const bool window = FR && n_iters >= 8;
+    // (the phase bookkeeping below assumes check points 2 mod 6 iterations apart: 50, the reference's spacing, is)
+    const bool window = FR && n_iters >= 8 && (g.fr_chunk_iters % 6 == 2);
     const int n_plain = window ? n_iters - 6 : n_iters - 1;
+    // Early proof: every six iterations the state is compared with the one six iterations earlier (kept in the warp's
+    // shared-memory slice).  Equal => periodic from there on, so the window is run right away instead of at the chunk end;
+    // its distance `delta` to the chunk end is kept even, so that the check points still fall on window updates 2, 4, 6.
+    int delta = 0;
+    const int probe0 = 6 + (n_iters & 1);
     double s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     // one vote per row and iteration decides whether any element needs the small-a Taylor form (rare: fixed points sit
     // above 1/35 and only transients dip below 1/16); the running minimum is taken while the new values are produced
@@ -199,6 +205,23 @@ mm_chunk_kernel(const ChunkArgs g) {
 #pragma unroll
     for (int j = 1; j < NP; ++j) amin = fminf(amin, fminf(a[j].x, a[j].y));
     for (int it = 0; it < n_plain; ++it) {
+      if (FR && window && it >= probe0 && (it - probe0) % 6 == 0) {
+        bool same = it > probe0;
+        if (same) {
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            const float2 w0 = a0s[j * 32];
+            same &= (w0.x == a[j].x) & (w0.y == a[j].y);
+          }
+          same = __all_sync(0xffffffffu, same);
+        }
+        if (same) {
+          delta = n_plain - it;
+          break;
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) a0s[j * 32] = a[j];
+      }
       const RowPsi rp = row_psi(s);
       const bool any_small = __any_sync(0xffffffffu, amin < kSmallA);
       amin = 3.0e38f;
@@ -265,7 +288,7 @@ mm_chunk_kernel(const ChunkArgs g) {
       dsq_cta += (double)(d2.x + d2.y);
       asq_cta += (double)(a2.x + a2.y);
     } else {
-      if (g.work_ctr && lane == 0) atomicAdd(g.work_ctr, (unsigned long long)n_iters);  // row-iterations executed
+      if (g.work_ctr && lane == 0) atomicAdd(g.work_ctr, (unsigned long long)(n_iters - delta));  // row-iterations executed
       // (a) period dividing 6 iterations, proven inside this chunk
       bool same6 = window;
       if (window) {
@@ -308,10 +331,11 @@ mm_chunk_kernel(const ChunkArgs g) {
       if (lane == 0) {
         double2* rc = g.row_cache + row;  // [n_checks][rows_total] so that the per-check sums read coalesced
         const long rs = g.rows_total;
-        rc[check_idx * rs] = make_double2(t6x, t6y);
+        if (!same6) rc[check_idx * rs] = make_double2(t6x, t6y);
         if (same6) {
-          for (int j = check_idx + 1; j < g.n_checks; ++j) {
-            const int ph = (2 * (j - check_idx)) % 6;
+          // check j is (delta + 50 (j - check_idx)) iterations after the window's last update
+          for (int j = check_idx; j < g.n_checks; ++j) {
+            const int ph = (delta + 2 * (j - check_idx)) % 6;
             rc[j * rs] = ph == 0 ? make_double2(t6x, t6y) : (ph == 2 ? make_double2(t2x, t2y) : make_double2(t4x, t4y));
           }
           g.frozen[row] = 6;

@@ -43,6 +43,7 @@ class DirichletProblem(ctypes.Structure):
         ("criterions", c_void_p), ("mm_iters", c_void_p), ("n_live", c_void_p), ("mm_rows", c_void_p),
         ("iter_events", POINTER(c_void_p)),
         ("mm_events", POINTER(c_void_p)),
+        ("mm_crit", c_void_p),
     ]
 
 

@@ -52,7 +52,7 @@ class _DirichletBase(object):
             raise ValueError(f"mm_mode must be one of {sorted(_MM_MODES)}, got {mode!r}")
         self.mm_mode = mode
         self.u = self.alpha = self.v = None
-        self.mm_iters = self.n_live = self.mm_rows = None
+        self.mm_iters = self.n_live = self.mm_rows = self.mm_crit = None
 
     def __del__(self):
         try:
@@ -122,6 +122,7 @@ class _DirichletBase(object):
                                x_s=support, y_s=y_s, mm_mode=_MM_MODES[self.mm_mode], record_events=True)
         self.u, self.alpha, self.v, self.labels = res["u"], res["alpha"], res["v"], res["labels"]
         self.mm_iters, self.n_live, self.mm_rows = res["mm_iters"], res["n_live"], res["mm_rows"]
+        self.mm_crit = res["mm_crit"]
         self._em_events = (start, res["events"])
         self._mm_events = res["mm_events"]
         crit = res["criterions"]

@@ -318,6 +318,7 @@ def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lamb
         "mm_iters": torch.zeros(max(iters, 1), device=dev, dtype=torch.int32)[:iters],
         "n_live": torch.zeros(max(iters, 1), device=dev, dtype=torch.int32)[:iters],
         "mm_rows": torch.zeros(max(iters, 1), device=dev, dtype=torch.int64)[:iters],
+        "mm_crit": torch.zeros(max(iters, 1), 2, device=dev, dtype=torch.float64)[:iters],
     }
     events = [torch.cuda.Event(enable_timing=True) for _ in range(iters)] if record_events else []
     mm_events = [torch.cuda.Event(enable_timing=True) for _ in range(2 * iters)] if record_events else []
@@ -332,7 +333,7 @@ def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lamb
         check_every=int(check_every), tol=float(tol), lambd=float(lambd), hard=int(bool(hard)), mm_mode=int(mm_mode),
         x_q=_ptr(x_q), x_s=_ptr(x_s), y_s=_ptr(y_s), u=_ptr(out["u"]), alpha=_ptr(out["alpha"]), v=_ptr(out["v"]),
         labels=_ptr(out["labels"]), criterions=_ptr(out["criterions"]), mm_iters=_ptr(out["mm_iters"]),
-        n_live=_ptr(out["n_live"]), mm_rows=_ptr(out["mm_rows"]),
+        n_live=_ptr(out["n_live"]), mm_rows=_ptr(out["mm_rows"]), mm_crit=_ptr(out["mm_crit"]),
         iter_events=ctypes.cast(ev_arr, ctypes.POINTER(ctypes.c_void_p)) if ev_arr is not None else None,
         mm_events=ctypes.cast(mm_arr, ctypes.POINTER(ctypes.c_void_p)) if mm_arr is not None else None)
     nbytes = lib.tclip_dirichlet_em_workspace_bytes(ctypes.byref(p))
