@@ -208,45 +208,59 @@ classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid
     s_changed = 0;
   }
   int base_l = 0, base_n = 0, changed = 0;
-  for (int r0 = 0, tile = 0; r0 < rows; r0 += 1024, ++tile) {
-    const int r = r0 + threadIdx.x;
-    const bool in = r < rows;
-    const bool l = in && live[r] != 0;
-    const int age = in ? dead_age[r] : 0;
-    const bool nw = in && !l && !cache_valid[r];
-    if (in && (l != (age == 0))) changed = 1;   // was live (age 0) and is not any more, or the reverse
-    const unsigned bl = __ballot_sync(0xffffffffu, l), bn = __ballot_sync(0xffffffffu, nw);
-    const int buf = tile & 1;
-    if (lane == 0) {
-      wl[buf][warp] = __popc(bl);
-      wn[buf][warp] = __popc(bn);
-    }
-    __syncthreads();
-    const int vl = wl[buf][lane], vn = wn[buf][lane];  // lane i holds the totals of warp i
-    int sl = vl, sn = vn;
+  constexpr int kBatch = 8;  // tiles whose flags are fetched together (one exposed memory latency per batch)
+  for (int r00 = 0, tile = 0; r00 < rows; r00 += 1024 * kBatch) {
+    int lv[kBatch], ag[kBatch], cv[kBatch];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, sl, o), b = __shfl_up_sync(0xffffffffu, sn, o);
-      if (lane >= o) {
-        sl += a;
-        sn += b;
-      }
+    for (int b = 0; b < kBatch; ++b) {
+      const int r = r00 + b * 1024 + threadIdx.x;
+      const bool in = r < rows;
+      lv[b] = in ? live[r] : 0;
+      ag[b] = in ? dead_age[r] : 0;
+      cv[b] = in ? cache_valid[r] : 1;
     }
-    const int tot_l = __shfl_sync(0xffffffffu, sl, 31), tot_n = __shfl_sync(0xffffffffu, sn, 31);
-    const int off_l = __shfl_sync(0xffffffffu, sl - vl, warp), off_n = __shfl_sync(0xffffffffu, sn - vn, warp);
-    if (in) {
-      dead_age[r] = l ? 0 : age + 1;
-      if (l) {
-        list_live[base_l + off_l + __popc(bl & lt)] = r;
-        cache_valid[r] = 0;
-      } else if (nw) {
-        list_new[base_n + off_n + __popc(bn & lt)] = r;
-        cache_valid[r] = 1;
-        frozen[r] = 0;
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b, ++tile) {
+      const int r = r00 + b * 1024 + threadIdx.x;
+      if (r00 + b * 1024 >= rows) break;  // CTA-uniform
+      const bool in = r < rows;
+      const bool l = in && lv[b] != 0;
+      const int age = ag[b];
+      const bool nw = in && !l && !cv[b];
+      if (in && (l != (age == 0))) changed = 1;   // was live (age 0) and is not any more, or the reverse
+      const unsigned bl = __ballot_sync(0xffffffffu, l), bn = __ballot_sync(0xffffffffu, nw);
+      const int buf = tile & 1;
+      if (lane == 0) {
+        wl[buf][warp] = __popc(bl);
+        wn[buf][warp] = __popc(bn);
       }
+      __syncthreads();
+      const int vl = wl[buf][lane], vn = wn[buf][lane];  // lane i holds the totals of warp i
+      int sl = vl, sn = vn;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, sl, o), c = __shfl_up_sync(0xffffffffu, sn, o);
+        if (lane >= o) {
+          sl += a;
+          sn += c;
+        }
+      }
+      const int tot_l = __shfl_sync(0xffffffffu, sl, 31), tot_n = __shfl_sync(0xffffffffu, sn, 31);
+      const int off_l = __shfl_sync(0xffffffffu, sl - vl, warp), off_n = __shfl_sync(0xffffffffu, sn - vn, warp);
+      if (in) {
+        dead_age[r] = l ? 0 : age + 1;
+        if (l) {
+          list_live[base_l + off_l + __popc(bl & lt)] = r;
+          cache_valid[r] = 0;
+        } else if (nw) {
+          list_new[base_n + off_n + __popc(bn & lt)] = r;
+          cache_valid[r] = 1;
+          frozen[r] = 0;
+        }
+      }
+      base_l += tot_l;
+      base_n += tot_n;
     }
-    base_l += tot_l;
-    base_n += tot_n;
   }
   if (changed) s_changed = 1;
   __syncthreads();
