@@ -159,6 +159,17 @@ int tclip_kmeans_assign(const float* x, const float* w, const float* v, float te
 int tclip_kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long long per_task,
                        void* stream);
 
+/* Cluster -> class matching and the task accuracy.  probs [T, proto_rows, K] float32: row c of task t = class
+ * probabilities of cluster c (clusters in order of first appearance, as tclip_cluster_prototypes delivers them);
+ * n_clusters [T], sample_cluster [T,n] int32.  graph_matching != 0: minimum-cost assignment of the clusters to distinct
+ * classes with cost -probs in float64 (SciPy's linear_sum_assignment algorithm, one warp per task); == 0: arg-max class
+ * per cluster.  Outputs: cluster_class [T,n] int32 (-1 beyond n_clusters), new_labels [T,n] int64 (may be NULL), and, when
+ * y_q [T,n] int64 is given, acc [T] = mean(new_labels == y_q).  Replaces compute_graph_matching / compute_basic_matching
+ * (src/utils.py:380-417) and zero_shot/em_dirichlet.py:86-92. */
+int tclip_match_clusters(const float* probs, const int* n_clusters, const int* sample_cluster, const long long* y_q,
+                         int graph_matching, int* cluster_class, long long* new_labels, float* acc, int T, int n, int K,
+                         int proto_rows, void* stream);
+
 /* ---- fused driver: the whole run_method loop, enqueued on one stream without host synchronisation -------------- */
 typedef struct tclip_dirichlet_problem {
   int n_task, n_query, n_class, dim; /* T, n, K, D (D == K: softmax features) */

@@ -244,6 +244,36 @@ def test_stage_cluster_prototypes_and_matching(dev):
     got_b = matching.basic_matching(cl["proto"].cpu().numpy(), cl["n_clusters"].cpu().numpy(),
                                     cl["sample_cluster"].cpu().numpy())
     assert (got_b == want_b.numpy()).all()
+    # the device kernel (what the method classes call) against both
+    y = torch.randint(0, K, labels.shape, generator=g).to(dev)
+    dm = ops.match_clusters(cl["proto"], cl["n_clusters"], cl["sample_cluster"], y, graph_matching=True)
+    assert (dm["new_labels"].cpu().numpy() == want.numpy()).all()
+    np.testing.assert_array_equal(dm["acc"].cpu().numpy(), (want.to(dev) == y).float().mean(1).cpu().numpy())
+    db = ops.match_clusters(cl["proto"], cl["n_clusters"], cl["sample_cluster"], y, graph_matching=False)
+    assert (db["new_labels"].cpu().numpy() == want_b.numpy()).all()
+
+
+@pytest.mark.parametrize("T,n,K,seed", [(6, 75, 1000, 0), (8, 75, 100, 1), (5, 75, 20, 2), (3, 40, 64, 3), (4, 128, 2000, 4)])
+def test_device_assignment_equals_scipy(dev, T, n, K, seed):
+    """tclip_match_clusters vs scipy.optimize.linear_sum_assignment on rectangular cost matrices with as many clusters as
+    a task can have (every query its own cluster when K >= n): many augmenting steps, long alternating paths."""
+    from scipy.optimize import linear_sum_assignment
+    from tclip_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    probs = torch.softmax(3 * torch.randn(T, n, K, generator=g), -1)           # concentrated rows -> contested classes
+    hot = torch.randint(0, max(K // 8, 2), (T, n), generator=g)                # many clusters want the same few classes
+    probs = (probs + 2.0 * torch.nn.functional.one_hot(hot, K).float()) / 3.0
+    n_clusters = torch.tensor([min(n, K) - (i % 3) for i in range(T)], dtype=torch.int32)
+    sample_cluster = torch.stack([torch.randint(0, int(c), (n,), generator=g) for c in n_clusters]).int()
+    out = ops.match_clusters(probs.to(dev), n_clusters.to(dev), sample_cluster.to(dev), None, graph_matching=True)
+    cc = out["cluster_class"].cpu().numpy()
+    for t in range(T):
+        c = int(n_clusters[t])
+        cost = -probs[t, :c].double().numpy()
+        rows, cols = linear_sum_assignment(cost)
+        assert (cc[t, :c] == cols).all(), (t, cost[rows, cols].sum(), cost[np.arange(c), cc[t, :c]].sum())
+        assert (cc[t, c:] == -1).all()
+        assert (out["new_labels"][t].cpu().numpy() == cols[sample_cluster[t].numpy()]).all()
 
 
 @pytest.mark.parametrize("K,T,iters,hard", [(100, 6, 6, False), (100, 5, 5, True), (1000, 3, 4, False)])

@@ -493,6 +493,18 @@ int tclip_cluster_prototypes(const int* labels, const float* feats, int* cluster
 }
 
 // ---- k-means family -------------------------------------------------------------------------------------------------
+int tclip_match_clusters(const float* probs, const int* n_clusters, const int* sample_cluster, const long long* y_q,
+                         int graph_matching, int* cluster_class, long long* new_labels, float* acc, int T, int n, int K,
+                         int proto_rows, void* stream) {
+  if (!probs || !n_clusters || !sample_cluster || !cluster_class || T < 1 || n < 1 || K < 1 || proto_rows < 1 ||
+      (y_q && !acc))
+    return fail(TCLIP_ERR_INVALID, "tclip_match_clusters: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::match_clusters(probs, n_clusters, sample_cluster, y_q, graph_matching, cluster_class, new_labels, acc,
+                                   T, n, K, proto_rows, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
 int tclip_normalize_rows(const float* x, float* out, long long rows, int D, void* stream) {
   if (!x || !out || rows < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_normalize_rows: bad arguments");
   if (int rc = current_device_ok()) return rc;

@@ -93,6 +93,11 @@ cudaError_t cluster_prototypes(const int* labels, const float* feats, int* clust
                                int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
                                cudaStream_t st);
 
+// matching.cu: rectangular assignment (clusters -> classes) per task on the device + relabelled accuracy
+cudaError_t match_clusters(const float* proto, const int* n_clusters, const int* sample_cluster, const long long* y_q,
+                           int graph_matching, int* cluster_class, long long* new_labels, float* acc, int T, int n, int K,
+                           int proto_rows, cudaStream_t st);
+
 // ---- soft / hard k-means and EM-Gaussian (kmeans.cu) -----------------------------------------------------------------
 cudaError_t normalize_rows(const float* x, float* out, long rows, int D, cudaStream_t st);
 cudaError_t kmeans_similarity(const float* a, const float* text, float scale, float* u, long M, int K, int D,

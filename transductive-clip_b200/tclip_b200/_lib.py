@@ -71,6 +71,8 @@ SIGNATURES = {
     "tclip_dirichlet_contraction": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "tclip_cluster_prototypes": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_int, c_int, c_int, c_void_p]),
+    "tclip_match_clusters": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_int, c_int, c_int, c_void_p]),
     "tclip_normalize_rows": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "tclip_kmeans_similarity": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "tclip_kmeans_centroids": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -1,4 +1,4 @@
-"""Cluster -> class label matching (host side).
+"""Cluster -> class label matching, host form (the checker of ``ops.match_clusters``; the method classes use the device kernel).
 
 Mirrors ``compute_graph_matching`` / ``compute_basic_matching`` of the reference (``src/utils.py:380-417``): per task,
 clusters are taken in order of first appearance among the predictions, the cost row of cluster c is

@@ -8,7 +8,8 @@ Drop-in for the reference classes (same constructor, same ``run_task`` contract,
 The callers are ``src/eval_zero_shot.py:113-138,171-177`` and ``src/eval_few_shot.py:189-211,250-259``.
 
 All arithmetic of ``run_method`` happens in CUDA kernels behind ``ops.dirichlet_em`` (one C-ABI call that enqueues the
-whole EM loop); the only host work is the Hungarian label matching, which uses the reference's own SciPy solver.
+whole EM loop), the cluster -> class assignment included (``ops.match_clusters``: SciPy's shortest-augmenting-path
+algorithm restated for one warp per task; ``tclip_b200.matching`` keeps the SciPy form the tests compare it with).
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ import os
 import numpy as np
 import torch
 
-from .. import matching, ops
+from .. import ops
 from ..logger import Logger
 
 _MM_MODES = {"dense": ops.TCLIP_MM_DENSE, "skip_dead": ops.TCLIP_MM_SKIP_DEAD}
@@ -95,21 +96,17 @@ class _DirichletBase(object):
         self.test_acc.append(accuracy)
 
     def compute_acc_clustering(self, query, y_q):
-        """Cluster prototypes on the device, Hungarian matching on the host (zero_shot/em_dirichlet.py:61-92)."""
+        """Cluster prototypes, minimum-cost cluster -> class assignment and accuracy on the device
+        (zero_shot/em_dirichlet.py:61-92, src/utils.py:380-417)."""
         if not self.args.use_softmax_feature:
             raise ValueError("The selected method is unable to handle query features that are not in the unit simplex")
         cl = ops.cluster_prototypes(self.labels, query)
-        n_clusters = cl["n_clusters"].cpu().numpy()
-        sample_cluster = cl["sample_cluster"].cpu().numpy()
-        # only the rows of existing clusters cross PCIe (a task has <= n_query clusters, usually a handful)
-        max_c = max(int(n_clusters.max()), 1)
-        proto = cl["proto"][:, :max_c].contiguous().cpu().numpy()
-        if self.args.graph_matching == True:  # noqa: E712  (same truthiness test as the reference)
-            new_preds = matching.graph_matching(proto, n_clusters, sample_cluster)
-        else:
-            new_preds = matching.basic_matching(proto, n_clusters, sample_cluster)
-        new_preds_q = torch.from_numpy(new_preds).to(self.device)
-        accuracy = (new_preds_q == y_q).float().mean(1, keepdim=True)
+        # softmax features: the prototypes are the class probabilities (zero_shot/em_dirichlet.py:72-74); assignment and
+        # accuracy stay on the device, nothing but the accuracies crosses PCIe
+        res = ops.match_clusters(cl["proto"], cl["n_clusters"], cl["sample_cluster"], y_q.contiguous(),
+                                 graph_matching=(self.args.graph_matching == True))  # noqa: E712 (reference's test)
+        self.new_labels = res["new_labels"]
+        accuracy = res["acc"].unsqueeze(1)
         self.test_acc.append(accuracy)
 
     def _run_em(self, query, support=None, y_s=None):

@@ -6,7 +6,7 @@ Drop-in for the reference classes (same constructor, ``run_task`` contract and l
   ``src/eval_zero_shot.py:119-137,171-177``.
 
 The loop (w -> u [-> v]) is the reference's, every numeric step is a kernel of ``csrc/kmeans.cu`` reached through the C
-ABI; the Hungarian label matching runs on the host with the reference's own SciPy solver.  Both feature kinds are
+ABI, the cluster -> class assignment included (``ops.match_clusters``).  Both feature kinds are
 supported: softmax features (u starts from the features) and visual features (u starts from
 ``softmax(T * normalize(x) @ text.T)``; ``text`` comes from ``model.encode_text`` exactly like ``clip_weights``,
 ``src/utils.py:363-377``).
@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .. import matching, ops
+from .. import ops
 from ..logger import Logger
 
 
@@ -95,22 +95,19 @@ class _KMeansBase(object):
         return ops.kmeans_similarity(ops.normalize_rows(query), self._text_features, float(self.args.T))
 
     def compute_acc_clustering(self, query, y_q):
-        """Prototypes of the arg-max clusters on the device, matching on the host (soft_kmeans.py:33-66)."""
+        """Prototypes of the arg-max clusters, cluster -> class assignment and accuracy on the device
+        (soft_kmeans.py:33-66, src/utils.py:380-417)."""
         cl = ops.cluster_prototypes(self.labels, query)
-        n_clusters = cl["n_clusters"].cpu().numpy()
-        sample_cluster = cl["sample_cluster"].cpu().numpy()
-        max_c = max(int(n_clusters.max()), 1)
-        proto = cl["proto"][:, :max_c].contiguous()
+        probs = cl["proto"]
         if not self.args.use_softmax_feature:
-            # probs = softmax(T * normalize(prototype) @ text.T); rows of clusters that do not exist are never read
-            proto = ops.kmeans_similarity(ops.normalize_rows(proto), self._text_features, float(self.args.T))
-        proto = proto.cpu().numpy()
-        if self.args.graph_matching == True:  # noqa: E712  (same truthiness test as the reference)
-            new_preds = matching.graph_matching(proto, n_clusters, sample_cluster)
-        else:
-            new_preds = matching.basic_matching(proto, n_clusters, sample_cluster)
-        new_preds_q = torch.from_numpy(new_preds).to(self.device)
-        self.test_acc.append((new_preds_q == y_q).float().mean(1, keepdim=True))
+            # probs = softmax(T * normalize(prototype) @ text.T); only the rows of existing clusters are worth the GEMM
+            max_c = max(int(cl["n_clusters"].max().item()), 1)
+            probs = ops.kmeans_similarity(ops.normalize_rows(probs[:, :max_c].contiguous()), self._text_features,
+                                          float(self.args.T))
+        res = ops.match_clusters(probs, cl["n_clusters"], cl["sample_cluster"], y_q.contiguous(),
+                                 graph_matching=(self.args.graph_matching == True))  # noqa: E712 (reference's test)
+        self.new_labels = res["new_labels"]
+        self.test_acc.append(res["acc"].unsqueeze(1))
 
     # ------------------------------------------------------------------------------------------------------------
     def run_method(self, query, y_q):

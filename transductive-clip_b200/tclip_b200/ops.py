@@ -165,6 +165,29 @@ def cluster_prototypes(labels: torch.Tensor, feats: torch.Tensor):
     return out
 
 
+def match_clusters(probs: torch.Tensor, n_clusters: torch.Tensor, sample_cluster: torch.Tensor,
+                   y_q: torch.Tensor | None = None, graph_matching: bool = True) -> dict:
+    """Cluster -> class matching on the device (``compute_graph_matching`` / ``compute_basic_matching``,
+    src/utils.py:380-417): dict(cluster_class [T,n] int32, new_labels [T,n] int64, acc [T] float32 | None)."""
+    lib = _lib.load()
+    _need(probs, torch.float32, "probs"), _need(n_clusters, torch.int32, "n_clusters")
+    _need(sample_cluster, torch.int32, "sample_cluster")
+    T, rows, K = probs.shape
+    n = sample_cluster.shape[1]
+    dev = probs.device
+    if y_q is not None:
+        _need(y_q, torch.int64, "y_q")
+    out = {
+        "cluster_class": torch.empty(T, n, device=dev, dtype=torch.int32),
+        "new_labels": torch.empty(T, n, device=dev, dtype=torch.int64),
+        "acc": torch.empty(T, device=dev, dtype=torch.float32) if y_q is not None else None,
+    }
+    check(lib.tclip_match_clusters(_ptr(probs), _ptr(n_clusters), _ptr(sample_cluster), _ptr(y_q),
+                                   int(bool(graph_matching)), _ptr(out["cluster_class"]), _ptr(out["new_labels"]),
+                                   _ptr(out["acc"]), T, n, K, rows, _stream()))
+    return out
+
+
 # ---- k-means family ------------------------------------------------------------------------------------------------
 KMEANS_SOFT, KMEANS_GAUSS, KMEANS_HARD = 0, 1, 2
 
