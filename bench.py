@@ -293,7 +293,25 @@ def main():
     e3.record()
     barrier()
     clocks = sampler.stop()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    ms_e2e_rank = e2.elapsed_time(e3)
+    ms_e2e = max_over_ranks(ms_e2e_rank)
+    # diagnostics of the e2e leg: this rank's host->device copy of one batch on its own (pinned memory, CUDA events),
+    # and every rank's e2e time (a slow PCIe path or a starved host core shows up here, not in the device-resident leg)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        _x = host[a.warmup]["x_q"].to(dev, non_blocking=True)
+    c1.record()
+    c1.synchronize()
+    h2d_ms_rank = c0.elapsed_time(c1) / 3
+    del _x
+    per_rank = [[ms_e2e_rank / a.steps, h2d_ms_rank]]
+    if world > 1:
+        tt = torch.tensor(per_rank[0], device=dev, dtype=torch.float64)
+        gl = [torch.zeros_like(tt) for _ in range(world)] if rank == 0 else None
+        dist.gather(tt, gl, dst=0)
+        if rank == 0:
+            per_rank = [g.tolist() for g in gl]
 
     # ---- the dominant kernel alone: mm_chunk_kernel on a full batch of rows (T*K rows x D), two launches (51 + 50 MM
     # iterations, exactly the first two chunks of an M-step), CUDA events on the launching stream -------------------------
@@ -346,7 +364,9 @@ def main():
                              % (T * K * K * 4 / 1e6),
                        "mean_accuracy": acc_mean},
             "e2e": {"value": e2e, "unit": "tasks/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / a.steps},
+                    "ms_per_step": ms_e2e / a.steps,
+                    "per_rank_ms_per_step": [round(x[0], 3) for x in per_rank],
+                    "per_rank_h2d_ms": [round(x[1], 3) for x in per_rank]},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {

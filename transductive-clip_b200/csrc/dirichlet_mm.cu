@@ -598,19 +598,9 @@ constexpr auto make_table(std::integer_sequence<int, I...>) {
 
 // NP = ceil(D / 64) pairs dealt to W = min(4, NP) warps, NPW = ceil(NP / W) pairs each.  The kernel is issue-bound on the
 // SMs that hold two rows, and every warp repeats the row total and psi(s): 4 warps x 4 pairs measured 1.1 ms per
-// 1000-iteration M-step of 224 rows, 8 x 2 1.3 ms, 16 x 1 1.8 ms (profiles/r1_spec_kernel.md).
+// 1000-iteration M-step of 224 rows, 8 x 2 1.3 ms, 16 x 1 1.8 ms, 2 x 8 1.4 ms (profiles/r1_spec_kernel.md; measured
+// through an environment knob that commit 565e2b8 still has, removed since).
 SpecFn spec_fn(int np) {
-  static const int w = [] {
-    const char* e = std::getenv("TCLIP_SPEC_W");  // experiments only
-    return e ? std::atoi(e) : 4;
-  }();
-  static const int pipe = [] {
-    const char* e = std::getenv("TCLIP_SPEC_PIPE");  // experiments only
-    return e ? std::atoi(e) : 1;
-  }();
-  if (np > 8 && w == 2) return &launch_spec<2, 8, false>;
-  if (np > 8 && w == 8) return &launch_spec<8, 2>;
-  if (np > 12 && !pipe) return &launch_spec<4, 4, false>;
   switch (np) {
     case 1: return &launch_spec<1, 1>;
     case 2: return &launch_spec<2, 1>;
