@@ -115,6 +115,49 @@ def test_zero_shot_vs_oracle(dev, K, T, iters, hard, mode, seed):
     assert np.isfinite(logs["criterions"]).all() and np.isfinite(logs["timestamps"])
 
 
+@pytest.mark.parametrize("iter_mm", [1, 2, 49, 50, 51, 52, 101, 230])
+@pytest.mark.parametrize("mode", ["dense", "skip_dead"])
+def test_iter_mm_boundaries_vs_oracle(dev, iter_mm, mode):
+    """M-steps shorter than / ending exactly at / just past a check point (the exit test is `l > 0 and l % 50 == 0`,
+    em_dirichlet.py:169): no check, a check on the last iteration, a one-iteration tail chunk."""
+    from tclip_b200 import tasks
+    from tclip_b200.methods.dirichlet import EM_DIRICHLET
+    K, T, iters = 24, 3, 4
+    td, _ = tasks.make_zero_shot_batch(T, K, seed=40 + iter_mm)
+    m = EM_DIRICHLET(model=None, device=dev, log_file=None, args=make_args(K, iters=iters, iter_mm=iter_mm, mm_mode=mode))
+    logs = m.run_task({k: v.clone() for k, v in td.items()})
+    r32 = R.dirichlet_zero_shot(td["x_q"], td["y_q"], K, iters=iters, iter_mm=iter_mm)
+    r64 = R.dirichlet_zero_shot(td["x_q"], td["y_q"], K, iters=iters, iter_mm=iter_mm, dtype=torch.float64)
+    assert m.mm_iters.cpu().tolist() == r32.mm_iters
+    assert m.n_live.cpu().tolist() == r32.n_live
+    assert (m.labels.cpu().long() == r32.preds).float().mean().item() >= LABEL_AGREE
+    assert abs(float(logs["acc"].mean()) - float(r32.acc.mean())) <= ACC_TOL
+    for t in range(T):
+        assert _rel(m.alpha.cpu()[t], r64.alpha[t]) <= max(ALPHA_REL, 2.0 * _rel(r32.alpha[t], r64.alpha[t]))
+
+
+@pytest.mark.parametrize("check_every,iter_mm", [(8, 120), (10, 95), (25, 130), (7, 60), (50, 1000), (0, 40)])
+def test_check_spacing_schedules_agree(dev, check_every, iter_mm):
+    """The C ABI takes the check spacing as a parameter (50 upstream).  The periodic-extension bookkeeping of the
+    skip-dead schedule is only valid for spacings of 2 mod 6 and must switch itself off otherwise: both schedules have to
+    agree for any spacing (MM iteration counts, live clusters, labels, alpha)."""
+    from tclip_b200 import ops, tasks
+    from tclip_b200._lib import TCLIP_MM_DENSE, TCLIP_MM_SKIP_DEAD
+    K, T, iters = 30, 4, 5
+    td, _ = tasks.make_zero_shot_batch(T, K, seed=77)
+    xq = td["x_q"].to(dev)
+    out = {}
+    for name, mode in (("dense", TCLIP_MM_DENSE), ("skip", TCLIP_MM_SKIP_DEAD)):
+        out[name] = ops.dirichlet_em(xq, K, iters=iters, iter_mm=iter_mm, lambd=float(int(K / 5) * 75), hard=False,
+                                     check_every=check_every, mm_mode=mode)
+    d, s_ = out["dense"], out["skip"]
+    assert d["mm_iters"].cpu().tolist() == s_["mm_iters"].cpu().tolist()
+    assert d["n_live"].cpu().tolist() == s_["n_live"].cpu().tolist()
+    assert (d["labels"] == s_["labels"]).all()
+    assert _rel(s_["alpha"], d["alpha"]) < 1e-5
+    np.testing.assert_allclose(s_["mm_crit"].cpu().numpy()[:, 1], d["mm_crit"].cpu().numpy()[:, 1], rtol=1e-4)
+
+
 @pytest.mark.parametrize("K,T,shots,iters,hard,seed", [
     (20, 3, 2, 4, False, 0),
     (20, 3, 2, 4, True, 1),
