@@ -13,6 +13,10 @@ MM early exit is batch-global); ``value`` = tasks of all ranks / max-over-ranks 
   value        inputs already resident in HBM (``run_method``), timed with CUDA events;
   e2e          the reference-facing call ``run_task(task_dic)`` with pinned HOST tensors: H2D + EM + D2H of the
                accuracies inside the timed region;
+               both legs keep ``--streams`` (default 4) whole batches in flight per GPU — every batch is one unchanged
+               ``run_method`` / ``run_task`` call on its own CUDA stream and host thread (``tclip_b200.pipeline``), because
+               half of a batch is a latency-bound tail that leaves the SMs idle; ``serial`` inside ``value``'s line and
+               inside ``e2e`` is the same leg strictly one batch after the other (the reference's evaluator loop);
   roofline     the dominant kernel (mm_chunk_kernel, the MM M-step) run alone on a full batch of rows (T*K rows x D, two
                launches = the first 101 MM iterations of an M-step): algorithmic flop (74 per element-update, SURVEY.md
                §8(d)) / launch time from CUDA events on the launching stream; peak = FP32 FMA issue rate measured by the
@@ -58,6 +62,8 @@ def parse():
     ap.add_argument("--classes", type=int, default=K_CLASSES)
     ap.add_argument("--tasks-per-batch", type=int, default=TASKS_PER_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="run_task batches in flight per GPU (own CUDA stream + host thread each); 1 = strictly serial")
     return ap.parse_args()
 
 
@@ -233,20 +239,31 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def step_resident(s, xq, yq):
+    from tclip_b200.pipeline import BatchPipeline
+    pipe = BatchPipeline(dev, streams=a.streams) if a.streams > 1 else None
+
+    def run_many(fn, items):
+        """Whole batches, up to --streams of them in flight (each on its own CUDA stream from its own host thread); every
+        call is complete (stream synchronised) when it returns."""
+        return pipe.map(fn, list(items)) if pipe else [fn(i) for i in items]
+
+    def step_resident(s):
         m = cls(model=None, device=dev, log_file=None, args=args)
-        m.run_method(query=xq, y_q=yq)
-        return m
+        m.run_method(query=resident[s][0], y_q=resident[s][1])
+        # keep the CUDA events and the small per-iteration counters only (a retained 300 MB alpha would force a cudaMalloc
+        # in a later step); they are read after the timed region
+        return (m._mm_events, m.mm_rows, m.mm_iters, torch.cat(m.test_acc, dim=1).mean())
 
     def step_e2e(s):
         m = cls(model=None, device=dev, log_file=None, args=args)
-        logs = m.run_task(task_dic=dict(host[s]))
-        return m, logs
+        return m.run_task(task_dic=dict(host[s]))
 
+    timed = list(range(a.warmup, n_steps))
     # ---- leg 1: inputs resident in HBM ------------------------------------------------------------------------------
     resident = [(h["x_q"].to(dev), h["y_q"].long().squeeze(2).to(dev)) for h in host]
-    for s in range(a.warmup):
-        step_resident(s, *resident[s])
+    torch.cuda.synchronize()
+    if a.warmup > 0:
+        run_many(step_resident, [s % a.warmup for s in range(max(a.warmup, a.streams))])   # every stream gets warm
     # a fresh box idles at low clocks and W steps of ~50 ms do not always bring it up: ~0.5 s of register-only FMA work
     # (untimed) before the timed region, so both legs run at the clocks the sampler reports
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -256,43 +273,54 @@ def main():
     barrier()
     sampler.start()
     launches0 = ops.launch_count()
+    # the default stream is idle during the legs, so these two events are processed the moment they are recorded:
+    # before the first batch is submitted, and after every batch's stream has been synchronised
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    # M-step (dominant kernel) device time and executed work of the timed steps, this rank.  run_method has already
-    # synchronised on its last event and read the accuracies back when it returns, so reading the per-step counters here
-    # adds no wait; nothing of a step is kept alive (a retained 300 MB alpha would force a cudaMalloc in the next step)
-    kept = []
-    for s in range(a.warmup, n_steps):
-        m = step_resident(s, *resident[s])
-        # keep the CUDA events and the small per-iteration counters only; they are read after the timed region
-        kept.append((m._mm_events, m.mm_rows, m.mm_iters, m.test_acc))
-        del m
+    kept = run_many(step_resident, timed)
     e1.record()
     barrier()
     launches = ops.launch_count() - launches0
     ms_resident = max_over_ranks(e0.elapsed_time(e1))
-    mm_ms, updates, dense_updates = 0.0, 0.0, 0.0
-    accs = []
-    for ev, mm_rows, mm_iters, test_acc in kept:
-        mm_ms += sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(iters))
-        updates += float(mm_rows.sum().item()) * K
-        dense_updates += float(mm_iters.sum().item()) * T * K * K
-        accs.append(float(torch.as_tensor(test_acc).float().mean().item()) if not isinstance(test_acc, list)
-                    else torch.cat(test_acc, dim=1).mean().item())
+    accs = [float(k[3].item()) for k in kept]
     del kept
 
     # ---- leg 2: end to end through run_task with pinned host inputs ---------------------------------------------------
-    step_e2e(0)
+    if a.warmup > 0:
+        run_many(step_e2e, [s % a.warmup for s in range(max(1, a.streams))])
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    d2h_bytes = 0
-    for s in range(a.warmup, n_steps):
-        m, logs = step_e2e(s)
-        d2h_bytes = logs["acc"].nbytes + logs["criterions"].nbytes
+    all_logs = run_many(step_e2e, timed)
     e3.record()
     barrier()
+    d2h_bytes = all_logs[-1]["acc"].nbytes + all_logs[-1]["criterions"].nbytes
+    del all_logs
+
+    # ---- the same two legs strictly one batch after the other (what the reference's evaluator loop does), for reference;
+    # the per-M-step device times and work counters of `roofline.in_step` come from here (undisturbed by other streams)
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    kept = [step_resident(s) for s in timed]
+    e5.record()
+    barrier()
+    ms_resident_serial = max_over_ranks(e4.elapsed_time(e5))
+    mm_ms, updates, dense_updates = 0.0, 0.0, 0.0
+    for ev, mm_rows, mm_iters, _acc in kept:
+        mm_ms += sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(iters))
+        updates += float(mm_rows.sum().item()) * K
+        dense_updates += float(mm_iters.sum().item()) * T * K * K
+    del kept
+    e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e6.record()
+    for s in timed:
+        step_e2e(s)
+    e7.record()
+    barrier()
+    ms_e2e_serial = max_over_ranks(e6.elapsed_time(e7))
     clocks = sampler.stop()
+    if pipe:
+        pipe.close()
     ms_e2e_rank = e2.elapsed_time(e3)
     ms_e2e = max_over_ranks(ms_e2e_rank)
     # diagnostics of the e2e leg: this rank's host->device copy of one batch on its own (pinned memory, CUDA events),
@@ -358,13 +386,19 @@ def main():
         out = {
             "metric": "EM-Dirichlet tasks/sec (K=D=1000, N=75)", "value": value, "unit": "tasks/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_resident / a.steps, "higher_is_better": True,
+            "serial": {"value": tasks_total / (ms_resident_serial * 1e-3), "ms_per_step": ms_resident_serial / a.steps},
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "mm_mode": a.mm_mode, "tasks_per_step_per_gpu": T, "seed": SEED,
+                       "streams": a.streams,
+                       "concurrency": ("%d whole batches in flight per GPU, each one unchanged run_task / run_method call on "
+                                       "its own CUDA stream and host thread (tclip_b200.pipeline); `serial` = one at a time, "
+                                       "as the reference's evaluator loop" % a.streams),
                        "l2": "per-step working set alpha/y/work = 3 x %.0f MB > 126 MB L2; a different batch every step"
                              % (T * K * K * 4 / 1e6),
                        "mean_accuracy": acc_mean},
             "e2e": {"value": e2e, "unit": "tasks/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / a.steps,
+                    "serial": {"value": tasks_total / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial / a.steps},
                     "per_rank_ms_per_step": [round(x[0], 3) for x in per_rank],
                     "per_rank_h2d_ms": [round(x[1], 3) for x in per_rank]},
             "gpu_launches": int(launches),
@@ -385,7 +419,7 @@ def main():
                 "mufu_achieved_tops": kernel_updates * MUFU_PER_UPDATE / (kernel_ms * 1e-3) / 1e12,
                 "mufu_peak_tops": mufu_peak,
                 "algorithmic_bytes_per_launch": 12.0 * T * K * K,
-                "in_step": {"mm_share_of_step": mm_ms / (e0.elapsed_time(e1)),
+                "in_step": {"mm_share_of_step": mm_ms / (e4.elapsed_time(e5)),
                             "element_updates_per_s": updates / (mm_ms * 1e-3),
                             "element_updates_executed_per_task": updates / (T * a.steps),
                             "element_updates_dense_per_task": dense_updates / (T * a.steps)},

@@ -345,6 +345,30 @@ def test_mm_exit_norms_agree_between_schedules(dev, K, T, iters, hard):
     np.testing.assert_allclose(crit["skip_dead"][1:, 0], crit["dense"][1:, 0], rtol=5e-3)
 
 
+def test_batches_in_flight_equal_serial(dev):
+    """tclip_b200.pipeline: whole run_task batches on three CUDA streams / host threads give, batch by batch, exactly what
+    the same calls give one after the other (own scratch per stream, no shared state between batches)."""
+    from tclip_b200 import tasks
+    from tclip_b200.methods.dirichlet import EM_DIRICHLET, HARD_EM_DIRICHLET
+    from tclip_b200.pipeline import BatchPipeline
+    K, T, iters = 100, 8, 5
+    batches = [tasks.make_zero_shot_batch(T, K, seed=5, batch_index=i)[0] for i in range(7)]
+
+    def run(i):
+        cls = HARD_EM_DIRICHLET if i % 2 else EM_DIRICHLET
+        m = cls(model=None, device=dev, log_file=None, args=make_args(K, iters=iters))
+        logs = m.run_task({k: v.clone() for k, v in batches[i].items()})
+        return logs["acc"], logs["criterions"], m.alpha.cpu(), m.mm_iters.cpu()
+
+    serial = [run(i) for i in range(len(batches))]
+    with BatchPipeline(dev, streams=3) as pipe:
+        piped = pipe.map(run, range(len(batches)))
+    for a, b in zip(serial, piped):
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+        assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # BASELINE sizes (K = D = 1000, n = 75): size-independent properties
 # ------------------------------------------------------------------------------------------------------------------

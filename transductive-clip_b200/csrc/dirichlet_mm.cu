@@ -576,6 +576,10 @@ __global__ void mm_reset_kernel(MMState* state) {
   state->last_den = 0.0;
 }
 
+// (Capping the residency of this kernel at 3 or 4 CTAs per SM — so that a few-rows kernel of another batch in flight,
+// tclip_b200.pipeline, finds free registers next to it — was measured and does not pay: 2.42–2.48 k tasks/s against 2.53 k
+// uncapped with 4 batches in flight, and the kernel alone drops from 0.60 to 0.57–0.59 of the FMA rate;
+// gpurun_out/bs.json runs of scripts/gpu_streams.sh, commit message of this change.)
 template <int NP, bool FR>
 void launch_chunk(const ChunkArgs& g, int n_blocks, cudaStream_t st) {
   const size_t smem = (size_t)(kMMThreads / 32) * NP * 32 * sizeof(float2) * (FR ? 2 : 1);

@@ -4,6 +4,7 @@ fallback path."""
 from __future__ import annotations
 
 import ctypes
+import threading
 
 import torch
 
@@ -303,16 +304,19 @@ def kmeans_udiff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 _WORKSPACES: dict = {}
+_WORKSPACES_LOCK = threading.Lock()
 
 
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """One cached scratch buffer per device, grown on demand (a new method object is built per batch)."""
-    key = (device.type, device.index)
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        _WORKSPACES.pop(key, None)
-        ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
-        _WORKSPACES[key] = ws
+    """One cached scratch buffer per (device, CUDA stream), grown on demand (a new method object is built per batch;
+    batches in flight on different streams — ``tclip_b200.pipeline`` — must not share scratch)."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    with _WORKSPACES_LOCK:
+        ws = _WORKSPACES.get(key)
+        if ws is None or ws.numel() < nbytes:
+            _WORKSPACES.pop(key, None)
+            ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+            _WORKSPACES[key] = ws
     return ws
 
 

@@ -1,0 +1,56 @@
+"""Several ``run_task`` batches in flight on one GPU.
+
+The evaluators of the reference run their batches strictly one after the other (``src/eval_zero_shot.py:157-177``:
+build the method, ``logs = method.run_task(task_dic=tasks)``, next batch).  On a B200 one ImageNet-shape batch spends
+half of its time in a latency-bound tail (a few hundred non-empty clusters iterate 18 x 1000 times; <10 % of the SMs'
+issue slots are used), so the whole job — thousands of independent batches — is faster with a few batches in flight:
+the tail of one overlaps the throughput-bound head of the next.  Nothing of ``run_task`` changes: every
+batch is still one call of the reference-facing method on its own CUDA stream from its own host thread (ctypes and the
+CUDA synchronisation calls release the GIL), with its own scratch buffers; results come back in submission order.
+
+    pipe = BatchPipeline(device, streams=3)
+    logs = pipe.map(lambda tasks: Method(model=None, device=device, log_file=None, args=args).run_task(task_dic=tasks),
+                    batches)
+"""
+from __future__ import annotations
+
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, Iterable, List
+
+import torch
+
+
+class BatchPipeline:
+    def __init__(self, device, streams: int = 3):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("tclip_b200 runs on B200 GPUs only: device must be a CUDA device (no CPU fallback)")
+        if streams < 1:
+            raise ValueError("streams must be >= 1")
+        self.streams = int(streams)
+        self._local = threading.local()
+        self._pool = ThreadPoolExecutor(max_workers=self.streams, thread_name_prefix="tclip-batch")
+
+    def _run(self, fn: Callable, item):
+        if getattr(self._local, "stream", None) is None:
+            torch.cuda.set_device(self.device)
+            self._local.stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._local.stream):
+            out = fn(item)
+            self._local.stream.synchronize()  # the batch is complete (and its scratch reusable) when the call returns
+        return out
+
+    def map(self, fn: Callable, items: Iterable) -> List:
+        """``[fn(item) for item in items]`` with up to ``streams`` calls in flight; results in submission order."""
+        futures = [self._pool.submit(self._run, fn, it) for it in items]
+        return [f.result() for f in futures]
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
