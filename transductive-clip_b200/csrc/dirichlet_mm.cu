@@ -197,6 +197,7 @@ mm_chunk_kernel(const ChunkArgs g) {
     // shared-memory slice).  Equal => periodic from there on, so the window is run right away instead of at the chunk end;
     // its distance `delta` to the chunk end is kept even, so that the check points still fall on window updates 2, 4, 6.
     int delta = 0;
+    bool at_fixed_point = false;
     const int probe0 = 6 + (n_iters & 1);
     double s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     // one vote per row and iteration decides whether any element needs the small-a Taylor form (rare: fixed points sit
@@ -249,20 +250,30 @@ mm_chunk_kernel(const ChunkArgs g) {
       }
       s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
       // An exact fixed point (measured: every empty cluster's row reaches one after 12-14 iterations,
-      // profiles/r1_dead_rows_periodicity.txt): every later update is the identity, so the window can run right away;
-      // all its terms are equal (0 and the row's squared norm), which makes the parity of `delta` irrelevant.
+      // profiles/r1_dead_rows_periodicity.txt): every later update is the identity, so the terms of every later check
+      // are 0 and the row's squared norm; no window needed.
       if (FR && __all_sync(0xffffffffu, fixed_point)) {
-        delta = n_plain - (it + 1);
+        at_fixed_point = true;
+        delta = n_iters - (it + 1);  // iterations not executed (work accounting; the phase is irrelevant here)
         break;
       }
     }
-    if (FR && window) {
+    if (FR && window && !at_fixed_point) {
 #pragma unroll
       for (int j = 0; j < NP; ++j) a0s[j * 32] = a[j];
     }
     float2 d2 = make_float2(0.0f, 0.0f), a2 = make_float2(0.0f, 0.0f);  // terms of the last update
-    float2 d2_k2 = d2, a2_k2 = d2, d2_k4 = d2, a2_k4 = d2;               // FR: window updates 2 and 4
-    const int n_tail = window ? 6 : 1;
+    if (FR && at_fixed_point) {
+      // what every later check iteration would compute: a_new - a = 0 exactly, and the squared norm of this state,
+      // accumulated in the same order as in the loop below
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const float2 ao = (j == NP - 1) ? f2mul(a[j], tail_mask) : a[j];
+        a2 = f2fma(ao, ao, a2);
+      }
+    }
+    float2 d2_k2 = d2, a2_k2 = a2, d2_k4 = d2, a2_k4 = a2;               // FR: window updates 2 and 4
+    const int n_tail = (FR && at_fixed_point) ? 0 : (window ? 6 : 1);
     for (int k = 1; k <= n_tail; ++k) {
       const RowPsi rp = row_psi(s);
       d2 = make_float2(0.0f, 0.0f);
@@ -307,7 +318,7 @@ mm_chunk_kernel(const ChunkArgs g) {
       if (g.work_ctr && lane == 0) atomicAdd(g.work_ctr, (unsigned long long)(n_iters - delta));  // row-iterations executed
       // (a) period dividing 6 iterations, proven inside this chunk
       bool same6 = window;
-      if (window) {
+      if (window && !at_fixed_point) {
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
           const float2 w0 = a0s[j * 32];
