@@ -112,6 +112,15 @@ def test_no_cpu_fallback():
         ops.log_features(torch.ones(4))
     with pytest.raises(ValueError, match="mm_mode"):
         EM_DIRICHLET(model=None, device=torch.device("cpu"), log_file=None, args=make_args(20, mm_mode="bogus"))
+    from tclip_b200.pipeline import BatchPipeline
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BatchPipeline(torch.device("cpu"), streams=2)
+    for bad in ("contraction", "match_clusters"):
+        assert hasattr(ops, bad)
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        ops.contraction(torch.zeros(1, 3, 4), torch.ones(1, 4, 4))
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        ops.match_clusters(torch.zeros(1, 3, 4), torch.zeros(1, dtype=torch.int32), torch.zeros(1, 3, dtype=torch.int32))
 
 
 def _free_port():
