@@ -299,6 +299,9 @@ def main():
 
     # ---- the same two legs strictly one batch after the other (what the reference's evaluator loop does), for reference;
     # the per-M-step device times and work counters of `roofline.in_step` come from here (undisturbed by other streams)
+    if a.warmup > 0:
+        step_resident(0)        # the default stream has not been used yet (its scratch and tensors are not allocated)
+        torch.cuda.synchronize()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record()
     kept = [step_resident(s) for s in timed]
