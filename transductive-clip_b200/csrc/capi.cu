@@ -97,6 +97,7 @@ struct EmWorkspace {
   double2* extra;       // [n_checks] sum of the cached terms over all dead rows
   float* l3;            // [T,n,K] persistent contraction log z . (alpha-1)^T (only live columns are recomputed)
   int* dead_age;        // [rows] consecutive outer iterations the cluster has been empty
+  int4* tile_counts;    // [ceil(rows / 1024)] per-tile {n_live, n_new, changed} of the row classification
   int* gate;            // {n_live, row cap}: device-side choice between dense and row-wise E-step kernels
   int* split_gate;      // {n_live, kSplitCap}: device-side choice of the few-rows M-step kernel
   double2* spec_terms;  // [n_checks][kSplitCap] criterion terms of the speculated rows
@@ -152,6 +153,7 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
     w.list_live = c.take<int>(rows);
     w.list_new = c.take<int>(rows);
     w.counts = c.take<int>(4);
+    w.tile_counts = c.take<int4>((rows + 1023) / 1024);
     w.work_ctr = c.take<unsigned long long>(1);
   }
   w.bytes = c.off;
@@ -188,89 +190,132 @@ __global__ void zero_int_kernel(int* p, long n) {
   if (i < n) p[i] = 0;
 }
 
-// Stable compaction of the row classes (single CTA so the order, hence every later summation order, is fixed):
+// Stable compaction of the row classes (ascending row order, so every later summation order is fixed):
 //   live rows                      -> list_live   (iterated in the main loop)
 //   dead rows without a valid cache -> list_new    (full trajectory once, terms cached)
-// Tiles of 1024 consecutive rows (coalesced), ballot + popc inside a warp, a 32-entry shuffle scan across the warps; one
-// barrier per tile (double-buffered warp totals).  counts = {n_live, n_new, changed}: `changed` says whether the set of
-// dead rows or any cached term differs from the previous outer iteration (else the cached sums stay valid).
+// Two passes over tiles of 1024 consecutive rows, one CTA per tile: classify_count_kernel leaves per-tile counts,
+// classify_write_kernel adds up the counts of the tiles before its own and scatters its rows (ballot + popc inside a warp,
+// a 32-entry shuffle scan across the warps).  counts = {n_live, n_new, changed}: `changed` says whether the set of dead
+// rows or any cached term differs from the previous outer iteration (else the cached sums stay valid).
+struct RowFlags {
+  bool in, live, fresh;
+  int age;
+};
+
+__device__ __forceinline__ RowFlags row_flags(const int* live, const int* cache_valid, const int* dead_age, int r, int rows) {
+  RowFlags f;
+  f.in = r < rows;
+  f.live = f.in && live[r] != 0;
+  f.age = f.in ? dead_age[r] : 0;
+  f.fresh = f.in && !f.live && !cache_valid[r];
+  return f;
+}
+
 __global__ void __launch_bounds__(1024)
-classify_rows_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ frozen,
-                     int* __restrict__ dead_age, int* __restrict__ list_live, int* __restrict__ list_new,
-                     int* __restrict__ counts, int* __restrict__ gate, int cap, int* __restrict__ split_gate,
-                     int split_cap, unsigned long long* __restrict__ work_ctr, int rows) {
-  __shared__ int wl[2][32], wn[2][32];
-  __shared__ int s_changed;
+classify_count_kernel(const int* __restrict__ live, const int* __restrict__ cache_valid, const int* __restrict__ dead_age,
+                      int4* __restrict__ tile_counts, int rows) {
+  __shared__ int wl[32], wn[32], wc[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RowFlags f = row_flags(live, cache_valid, dead_age, blockIdx.x * 1024 + threadIdx.x, rows);
+  const unsigned bl = __ballot_sync(0xffffffffu, f.live), bn = __ballot_sync(0xffffffffu, f.fresh);
+  const unsigned bc = __ballot_sync(0xffffffffu, f.in && (f.live != (f.age == 0)));  // was live and is not, or the reverse
+  if (lane == 0) {
+    wl[warp] = __popc(bl);
+    wn[warp] = __popc(bn);
+    wc[warp] = bc != 0u;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int a = wl[lane], b = wn[lane], c = wc[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      c |= __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) tile_counts[blockIdx.x] = make_int4(a, b, c, 0);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+classify_write_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ frozen,
+                      int* __restrict__ dead_age, const int4* __restrict__ tile_counts, int* __restrict__ list_live,
+                      int* __restrict__ list_new, int* __restrict__ counts, int* __restrict__ gate, int cap,
+                      int* __restrict__ split_gate, int split_cap, unsigned long long* __restrict__ work_ctr, int rows) {
+  __shared__ int wl[32], wn[32];
+  __shared__ int4 red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  if (threadIdx.x == 0) {
-    *work_ctr = 0ull;
-    s_changed = 0;
-  }
-  int base_l = 0, base_n = 0, changed = 0;
-  constexpr int kBatch = 8;  // tiles whose flags are fetched together (one exposed memory latency per batch)
-  for (int r00 = 0, tile = 0; r00 < rows; r00 += 1024 * kBatch) {
-    int lv[kBatch], ag[kBatch], cv[kBatch];
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      const int r = r00 + b * 1024 + threadIdx.x;
-      const bool in = r < rows;
-      lv[b] = in ? live[r] : 0;
-      ag[b] = in ? dead_age[r] : 0;
-      cv[b] = in ? cache_valid[r] : 1;
+  // counts of the tiles before this one (x, y) and of all tiles (z, w; `changed` folded into the sign bit-free w2 below)
+  int4 acc = make_int4(0, 0, 0, 0);
+  int chg = 0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 1024) {
+    const int4 c = tile_counts[i];
+    if (i < (int)blockIdx.x) {
+      acc.x += c.x;
+      acc.y += c.y;
     }
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b, ++tile) {
-      const int r = r00 + b * 1024 + threadIdx.x;
-      if (r00 + b * 1024 >= rows) break;  // CTA-uniform
-      const bool in = r < rows;
-      const bool l = in && lv[b] != 0;
-      const int age = ag[b];
-      const bool nw = in && !l && !cv[b];
-      if (in && (l != (age == 0))) changed = 1;   // was live (age 0) and is not any more, or the reverse
-      const unsigned bl = __ballot_sync(0xffffffffu, l), bn = __ballot_sync(0xffffffffu, nw);
-      const int buf = tile & 1;
-      if (lane == 0) {
-        wl[buf][warp] = __popc(bl);
-        wn[buf][warp] = __popc(bn);
-      }
-      __syncthreads();
-      const int vl = wl[buf][lane], vn = wn[buf][lane];  // lane i holds the totals of warp i
-      int sl = vl, sn = vn;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, sl, o), c = __shfl_up_sync(0xffffffffu, sn, o);
-        if (lane >= o) {
-          sl += a;
-          sn += c;
-        }
-      }
-      const int tot_l = __shfl_sync(0xffffffffu, sl, 31), tot_n = __shfl_sync(0xffffffffu, sn, 31);
-      const int off_l = __shfl_sync(0xffffffffu, sl - vl, warp), off_n = __shfl_sync(0xffffffffu, sn - vn, warp);
-      if (in) {
-        dead_age[r] = l ? 0 : age + 1;
-        if (l) {
-          list_live[base_l + off_l + __popc(bl & lt)] = r;
-          cache_valid[r] = 0;
-        } else if (nw) {
-          list_new[base_n + off_n + __popc(bn & lt)] = r;
-          cache_valid[r] = 1;
-          frozen[r] = 0;
-        }
-      }
-      base_l += tot_l;
-      base_n += tot_n;
-    }
+    acc.z += c.x;
+    acc.w += c.y;
+    chg |= c.z;
   }
-  if (changed) s_changed = 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    chg |= __shfl_xor_sync(0xffffffffu, chg, o);
+  }
+  const int r = blockIdx.x * 1024 + threadIdx.x;
+  const RowFlags f = row_flags(live, cache_valid, dead_age, r, rows);
+  const unsigned bl = __ballot_sync(0xffffffffu, f.live), bn = __ballot_sync(0xffffffffu, f.fresh);
+  if (lane == 0) {
+    red[warp] = make_int4(acc.x, acc.y, acc.z, acc.w | (chg << 30));
+    wl[warp] = __popc(bl);
+    wn[warp] = __popc(bn);
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    counts[0] = base_l;
-    counts[1] = base_n;
-    counts[2] = (s_changed || base_n > 0) ? 1 : 0;
-    gate[0] = base_l;           // rows the row-wise kernels have to recompute (newly dead rows only get their y filled)
+  int base_l = 0, base_n = 0, tot_l = 0, tot_n = 0, changed = 0;
+#pragma unroll 4
+  for (int w = 0; w < 32; ++w) {  // every thread folds the 32 warp partials (broadcast reads)
+    const int4 c = red[w];
+    base_l += c.x;
+    base_n += c.y;
+    tot_l += c.z;
+    tot_n += c.w & 0x3fffffff;
+    changed |= c.w >> 30;
+  }
+  const int vl = wl[lane], vn = wn[lane];  // lane i holds the totals of warp i of this tile
+  int sl = vl, sn = vn;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, sl, o), c = __shfl_up_sync(0xffffffffu, sn, o);
+    if (lane >= o) {
+      sl += a;
+      sn += c;
+    }
+  }
+  const int off_l = __shfl_sync(0xffffffffu, sl - vl, warp), off_n = __shfl_sync(0xffffffffu, sn - vn, warp);
+  if (f.in) {
+    dead_age[r] = f.live ? 0 : f.age + 1;
+    if (f.live) {
+      list_live[base_l + off_l + __popc(bl & lt)] = r;
+      cache_valid[r] = 0;
+    } else if (f.fresh) {
+      list_new[base_n + off_n + __popc(bn & lt)] = r;
+      cache_valid[r] = 1;
+      frozen[r] = 0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *work_ctr = 0ull;
+    counts[0] = tot_l;
+    counts[1] = tot_n;
+    counts[2] = (changed || tot_n > 0) ? 1 : 0;
+    gate[0] = tot_l;            // rows the row-wise kernels have to recompute (newly dead rows only get their y filled)
     gate[1] = cap;
-    split_gate[0] = base_l;
+    split_gate[0] = tot_l;
     split_gate[1] = split_cap;
   }
 }
@@ -626,9 +671,12 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     tclip::SparseRows sp{};
     const bool sparse = skip && it > 0;
     if (skip) {
-      classify_rows_kernel<<<1, 1024, 0, st>>>(w.live, w.cache_valid, w.frozen, w.dead_age, w.list_live, w.list_new,
-                                               w.counts, w.gate, kSparseCap, w.split_gate, kSplitCap, w.work_ctr, rows);
-      tclip::note_launch();
+      const int n_tiles = (rows + 1023) / 1024;
+      classify_count_kernel<<<n_tiles, 1024, 0, st>>>(w.live, w.cache_valid, w.dead_age, w.tile_counts, rows);
+      classify_write_kernel<<<n_tiles, 1024, 0, st>>>(w.live, w.cache_valid, w.frozen, w.dead_age, w.tile_counts, w.list_live,
+                                                     w.list_new, w.counts, w.gate, kSparseCap, w.split_gate, kSplitCap,
+                                                     w.work_ctr, rows);
+      tclip::note_launch(2);
       sp.rows_live = w.list_live;
       sp.n_live = w.counts;
       sp.rows_new = w.list_new;

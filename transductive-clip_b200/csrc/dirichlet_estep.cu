@@ -375,7 +375,7 @@ logits_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, f
 
 // Row-wise form for the skip-dead schedule: only the columns of live clusters change between E-steps (an empty cluster
 // keeps its alpha row, hence its column of l3), so one CTA per live row recomputes l3[t, :, k].
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 logits_rows_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, float* __restrict__ l3,
                    const int* __restrict__ rows, const int* __restrict__ n_rows, int n, int K, int D,
                    const int* __restrict__ gate) {
@@ -684,7 +684,7 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
     if (cudaError_t e = logits_simt(logz, alpha, dst, T, n, K, D, gate, st)) return e;
   }
   if (gate) {
-    logits_rows_kernel<<<sp->cap, 128, D * sizeof(float), st>>>(logz, alpha, dst, sp->rows_live, sp->n_live, n, K, D,
+    logits_rows_kernel<<<sp->cap, 256, D * sizeof(float), st>>>(logz, alpha, dst, sp->rows_live, sp->n_live, n, K, D,
                                                                 gate);
     note_launch(1);
   }
