@@ -27,6 +27,9 @@ def shim():
     lib.tclip_host_mm_update.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
     lib.tclip_host_mm_update_pair.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
     lib.tclip_host_mm_update_pair_split.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_double]
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+    lib.tclip_host_row_psi_walk.argtypes = [f64p, f32p, f32p, f32p, ctypes.c_int]
+    lib.tclip_host_row_psi_walk.restype = ctypes.c_int
     lib.tclip_host_digamma.argtypes = [ctypes.c_double]
     lib.tclip_host_digamma.restype = ctypes.c_double
     lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -104,6 +107,36 @@ def test_two_phase_update_is_bit_identical(shim):
         shim.tclip_host_mm_update_pair(a, y, out, a.size, s)
         shim.tclip_host_mm_update_pair_split(a, y, out2, a.size, s)
         assert np.array_equal(out.view(np.uint32), out2.view(np.uint32)), s
+
+
+def test_anchored_row_psi_follows_the_full_evaluation(shim):
+    """row_psi_anchored (Taylor expansion around an anchor total, used by mm_spec_kernel) against the stateless float64
+    evaluation along realistic walks of a row total: slow drift, growth of a diverging row, jumps, tiny totals."""
+    g = np.random.default_rng(5)
+    walks = {
+        "drift": 1.7e5 * np.cumprod(1 + 1e-6 * g.standard_normal(4000)),
+        "growth": 40.0 * np.cumprod(np.full(4000, 1 + 3e-3)),
+        "slow_growth": 900.0 * np.cumprod(np.full(4000, 1 + 2e-5)),
+        "jumps": np.abs(g.standard_normal(2000)) * 1e4 + 20.0,
+        "small": np.linspace(0.3, 25.0, 3000),
+    }
+    for name, s in walks.items():
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        a, f, dk = (np.empty(s.size, np.float32) for _ in range(3))
+        n_full = shim.tclip_host_row_psi_walk(s, a, f, dk, s.size)
+        # psi(s) = dpsi + k ln2: compare the reconstructed values (the anchored form keeps the anchor's k)
+        rec_a = a.astype(np.float64) + (dk.astype(np.float64) / 8388608.0) * np.log(2.0)
+        err = np.abs(rec_a - f.astype(np.float64))
+        assert err.max() <= 6.5e-8, (name, err.max())                  # one float32 ulp of |dpsi| < 0.75
+        same_k = dk == 0
+        assert np.mean(a[same_k] == f[same_k]) > 0.97, (name, np.mean(a[same_k] == f[same_k]))
+        ref = special.digamma(s)
+        k = (dk.astype(np.float64) / 8388608.0)
+        del ref, k
+        if name in ("drift", "slow_growth"):
+            assert n_full <= 8, (name, n_full)                          # the logarithm is almost never evaluated
+        if name == "growth":
+            assert n_full < s.size // 3, (name, n_full)
 
 
 def test_mm_rows_track_the_oracle(shim):

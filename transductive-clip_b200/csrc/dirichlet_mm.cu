@@ -480,8 +480,9 @@ mm_spec_kernel(const SpecArgs g) {
   double s = row_total(0);
   int parity = 1;
   int next_check = g.check_every > 0 ? g.check_every : 0x7fffffff, c = 0;
+  PsiAnchor anchor;  // psi(s) by expansion around an earlier row total: the float64 logarithm leaves the serial path
   for (int l = 0; l < g.iter_mm; ++l) {
-    const RowPsi rp = row_psi(s);
+    const RowPsi rp = row_psi_anchored(s, anchor);
     float2 an[NPW];
 #pragma unroll
     for (int j = 0; j < NPW; ++j) an[j] = PIPE ? mm_update_post(pre[j], a[j], ny[j], rp) : mm_update_pair(a[j], ny[j], rp);

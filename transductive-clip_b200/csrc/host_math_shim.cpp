@@ -41,6 +41,22 @@ void tclip_host_mm_update_pair_split(const float* a, const float* y, float* out,
     out[i + 1] = r.y;
   }
 }
+// row_psi_anchored along a walk of row totals: out_dpsi[i], out_full[i] = dpsi of the anchored / the stateless evaluation,
+// out_dk23 = difference of the two exponent splits; returns how many steps took the full evaluation (re-anchored)
+int tclip_host_row_psi_walk(const double* s, float* out_dpsi, float* out_full, float* out_dk23, int n) {
+  tclip::PsiAnchor an;
+  int full = 0;
+  for (int i = 0; i < n; ++i) {
+    const double before = an.s;
+    const tclip::RowPsi a = tclip::row_psi_anchored(s[i], an);
+    if (an.s != before) ++full;
+    const tclip::RowPsi f = tclip::row_psi(s[i]);
+    out_dpsi[i] = a.dpsi;
+    out_full[i] = f.dpsi;
+    out_dk23[i] = a.k23 - f.k23;
+  }
+  return full;
+}
 // rows x D MM iterations on the host: the CPU twin of the kernel's inner loop (row sum in double).
 // D = padded (even) row length, n_valid = real row length: like the kernel, padding never enters the row total.
 void tclip_host_mm_rows(float* alpha, const float* y, int rows, int D, int n_valid, int iters) {

@@ -404,8 +404,13 @@ TCLIP_HD LogParts log_parts_f64(double s) {
   return out;
 }
 
-// psi(s) for the row total s > 0 (normal float64), split as k ln2 + dpsi with 2^k ~ s.
-TCLIP_HD RowPsi row_psi(double s) {
+// psi(s) for the row total s > 0 (normal float64), split as k ln2 + dpsi with 2^k ~ s; dpsi still in float64 here.
+struct RowPsiD {
+  double dpsi;
+  float k23;
+};
+
+TCLIP_HD RowPsiD row_psi_f64(double s) {
   double acc = 0.0;
   double x = s;
   while (x < 10.0) {  // only rows with a tiny total mass take this path
@@ -430,9 +435,62 @@ TCLIP_HD RowPsi row_psi(double s) {
   ser = fma(r2, ser, 1.0 / 120.0);
   ser = fma(r2, ser, -1.0 / 12.0);
   const double tail = fma(r2, ser, -0.5 * r) + acc;   // psi(x) - ln x + acc
-  RowPsi out;
-  out.dpsi = (float)(fma((double)(lx.e - k), 0.693147180559945309417, lx.lnm) + tail);
+  RowPsiD out;
+  out.dpsi = fma((double)(lx.e - k), 0.693147180559945309417, lx.lnm) + tail;
   out.k23 = (float)k * 8388608.0f;
+  return out;
+}
+
+TCLIP_HD RowPsi row_psi(double s) {
+  const RowPsiD d = row_psi_f64(s);
+  RowPsi out;
+  out.dpsi = (float)d.dpsi;
+  out.k23 = d.k23;
+  return out;
+}
+
+// The same through a fourth-order Taylor expansion around an anchor total, for the latency-bound few-rows kernel: between
+// two MM iterations of a row the total moves by 1e-3 .. 1e-7 of itself, so with d = s - s_a
+//   psi(s) = psi(s_a) + d psi^(1)(s_a) + d^2 psi^(2)(s_a)/2 + d^3 psi^(3)(s_a)/6 + d^4 psi^(4)(s_a)/24
+// replaces the float64 logarithm (a ~20-operation dependent chain) by five fused multiply-adds while |d| <= s_a / 64
+// (remainder (d/s)^5 / 5 < 2e-10, far below the float32 ulp of dpsi, 3e-8); outside that window, and for s_a < 16 (where
+// the asymptotic series of the derivatives would need more terms), the full evaluation runs and becomes the new anchor.
+// The expansion is always taken from the anchor, never chained, so nothing accumulates.  The result can differ from
+// row_psi(s) in the last float32 bit of dpsi (tests/test_math_host.py bounds it); the kernels that prove periodicity from
+// the row state alone (mm_chunk_kernel) keep the stateless row_psi.
+struct PsiAnchor {
+  double s = 0.0;     // 0: no anchor yet
+  double dpsi = 0.0;  // psi(s) - k ln2
+  double c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0;  // derivatives 1..4 of psi at s, divided by 1, 2, 6, 24
+  float k23 = 0.0f;
+};
+
+TCLIP_HD RowPsi row_psi_anchored(double s, PsiAnchor& an) {
+  const double d = s - an.s;
+  RowPsi out;
+  if (an.s >= 16.0 && fabs(d) <= an.s * (1.0 / 64.0)) {
+    double p = fma(d, an.c4, an.c3);
+    p = fma(d, p, an.c2);
+    p = fma(d, p, an.c1);
+    out.dpsi = (float)fma(d, p, an.dpsi);
+    out.k23 = an.k23;
+    return out;
+  }
+  const RowPsiD f = row_psi_f64(s);
+  an.s = s;
+  an.dpsi = f.dpsi;
+  an.k23 = f.k23;
+  if (s >= 16.0) {
+    // derivatives of psi from its asymptotic series (next terms: 1/(42 s^7) in the first one, < 1e-10 at s = 16)
+    const double r = rcp_f64(s);
+    const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2;
+    an.c1 = r + fma(r2, 0.5, fma(r3, 1.0 / 6.0, -(r4 * r) * (1.0 / 30.0)));
+    an.c2 = 0.5 * (-(r2 + r3) + fma(r4, -0.5, (r3 * r3) * (1.0 / 6.0)));
+    an.c3 = (fma(r3, 2.0, fma(r4, 3.0, (r4 * r) * 2.0)) - r4 * r3) * (1.0 / 6.0);
+    an.c4 = (fma(r4, -6.0, fma(r4 * r, -12.0, (r3 * r3) * -10.0)) + 7.0 * (r4 * r4)) * (1.0 / 24.0);
+  }
+  out.dpsi = (float)f.dpsi;
+  out.k23 = f.k23;
   return out;
 }
 
