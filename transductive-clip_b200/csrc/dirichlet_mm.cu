@@ -149,6 +149,11 @@ mm_chunk_kernel(const ChunkArgs g) {
   // [warps][NP][32] pairs of -y, and for free-running rows a second slice: the state six iterations before the chunk end
   extern __shared__ float2 smem2[];
   __shared__ double2 red[kMMThreads];
+  // Rows that are not free-running take psi(s) from the expansion around an anchor total (tclip_math.cuh:
+  // row_psi_anchored): all lanes of a warp hold the same values, so the anchor lives once per warp in shared memory.  The
+  // free-running rows keep the stateless evaluation: their periodicity proofs need the update to be a function of the
+  // row state alone.
+  __shared__ PsiAnchor anchors[kMMThreads / 32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   constexpr int kWarps = kMMThreads / 32;
@@ -200,6 +205,10 @@ mm_chunk_kernel(const ChunkArgs g) {
     bool at_fixed_point = false;
     const int probe0 = 6 + (n_iters & 1);
     double s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
+    if (!FR) {
+      psi_anchor_reset(anchors[warp]);  // (every lane writes the same values)
+      __syncwarp();
+    }
     // one vote per row and iteration decides whether any element needs the small-a Taylor form (rare: fixed points sit
     // above 1/35 and only transients dip below 1/16); the running minimum is taken while the new values are produced
     float amin = fminf(a[0].x, a[0].y);
@@ -225,7 +234,13 @@ mm_chunk_kernel(const ChunkArgs g) {
 #pragma unroll
         for (int j = 0; j < NP; ++j) a0s[j * 32] = a[j];
       }
-      const RowPsi rp = row_psi(s);
+      RowPsi rp;
+      if (FR) {
+        rp = row_psi(s);
+      } else {
+        rp = row_psi_anchored(s, anchors[warp]);
+        __syncwarp();
+      }
       const bool any_small = __any_sync(0xffffffffu, amin < kSmallA);
       amin = 3.0e38f;
       bool fixed_point = FR && window;  // free-running rows: did this update leave every element unchanged?
@@ -481,6 +496,7 @@ mm_spec_kernel(const SpecArgs g) {
   int parity = 1;
   int next_check = g.check_every > 0 ? g.check_every : 0x7fffffff, c = 0;
   PsiAnchor anchor;  // psi(s) by expansion around an earlier row total: the float64 logarithm leaves the serial path
+  psi_anchor_reset(anchor);
   for (int l = 0; l < g.iter_mm; ++l) {
     const RowPsi rp = row_psi_anchored(s, anchor);
     float2 an[NPW];

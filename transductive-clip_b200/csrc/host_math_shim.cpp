@@ -45,6 +45,7 @@ void tclip_host_mm_update_pair_split(const float* a, const float* y, float* out,
 // out_dk23 = difference of the two exponent splits; returns how many steps took the full evaluation (re-anchored)
 int tclip_host_row_psi_walk(const double* s, float* out_dpsi, float* out_full, float* out_dk23, int n) {
   tclip::PsiAnchor an;
+  tclip::psi_anchor_reset(an);
   int full = 0;
   for (int i = 0; i < n; ++i) {
     const double before = an.s;

@@ -458,12 +458,19 @@ TCLIP_HD RowPsi row_psi(double s) {
 // The expansion is always taken from the anchor, never chained, so nothing accumulates.  The result can differ from
 // row_psi(s) in the last float32 bit of dpsi (tests/test_math_host.py bounds it); the kernels that prove periodicity from
 // the row state alone (mm_chunk_kernel) keep the stateless row_psi.
-struct PsiAnchor {
-  double s = 0.0;     // 0: no anchor yet
-  double dpsi = 0.0;  // psi(s) - k ln2
-  double c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0;  // derivatives 1..4 of psi at s, divided by 1, 2, 6, 24
-  float k23 = 0.0f;
+struct PsiAnchor {      // plain data: it also lives in shared memory (one per warp in mm_chunk_kernel)
+  double s;             // 0: no anchor yet
+  double dpsi;          // psi(s) - k ln2
+  double c1, c2, c3, c4;  // derivatives 1..4 of psi at s, divided by 1, 2, 6, 24
+  float k23;
 };
+
+TCLIP_HD void psi_anchor_reset(PsiAnchor& an) {
+  an.s = 0.0;
+  an.dpsi = 0.0;
+  an.c1 = an.c2 = an.c3 = an.c4 = 0.0;
+  an.k23 = 0.0f;
+}
 
 TCLIP_HD RowPsi row_psi_anchored(double s, PsiAnchor& an) {
   const double d = s - an.s;
