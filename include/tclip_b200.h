@@ -170,6 +170,14 @@ int tclip_match_clusters(const float* probs, const int* n_clusters, const int* s
                          int graph_matching, int* cluster_class, long long* new_labels, float* acc, int T, int n, int K,
                          int proto_rows, void* stream);
 
+/* Device-side construction of a task batch from the cached features: x_q[m, :] = features[idx[m], :] (features [n_rows, F]
+ * float32, idx [count] int64, count = T * n_query), y_q[m] = labels[idx[m]] (int64; labels / y_q may be NULL).  `bad`
+ * (device int, may be NULL, caller zeroes it) counts indices outside [0, n_rows); their rows are written as zeros / -1.
+ * Replaces all_features_query[indices, :] / all_labels_query[indices] (src/eval_zero_shot.py:158-163) and the torch.cat
+ * of Tasks_Generator_zero_shot.generate_tasks (src/task_generator_zero_shot.py:36-65). */
+int tclip_gather_tasks(const float* features, const long long* labels, const long long* idx, float* x_q, long long* y_q,
+                       long long n_rows, long long count, int F, int* bad, void* stream);
+
 /* ---- fused driver: the whole run_method loop, enqueued on one stream without host synchronisation -------------- */
 typedef struct tclip_dirichlet_problem {
   int n_task, n_query, n_class, dim; /* T, n, K, D (D == K: softmax features) */

@@ -345,6 +345,44 @@ def test_mm_exit_norms_agree_between_schedules(dev, K, T, iters, hard):
     np.testing.assert_allclose(crit["skip_dead"][1:, 0], crit["dense"][1:, 0], rtol=5e-3)
 
 
+def test_device_task_construction(dev):
+    """tasks.DeviceTaskSource: gathering the sampler's indices on the device gives the tensors the evaluator builds on the
+    host (src/eval_zero_shot.py:158-168), ragged feature widths included, and run_task takes them as they are."""
+    import random
+    from tclip_b200 import ops, tasks
+    from tclip_b200.methods.dirichlet import EM_DIRICHLET
+    g = torch.Generator().manual_seed(8)
+    for N, F in ((3000, 100), (500, 37), (64, 1024)):
+        feats = torch.softmax(3 * torch.randn(N, F, generator=g), -1)
+        labels = torch.randint(0, 20, (N,), generator=g)
+        idx = torch.randint(0, N, (5, 75), generator=g)
+        x, y, bad = ops.gather_tasks(feats.to(dev), labels.to(dev), idx.to(dev))
+        assert int(bad.item()) == 0
+        assert torch.equal(x.cpu(), feats[idx]) and torch.equal(y.cpu(), labels[idx])
+    idx[0, 0] = N                                                       # out of range: counted, zero row
+    x, y, bad = ops.gather_tasks(feats.to(dev), labels.to(dev), idx.to(dev))
+    assert int(bad.item()) == 1 and float(x[0, 0].abs().sum()) == 0.0 and int(y[0, 0]) == -1
+    # evaluator-level: same sampler seeds -> same tasks -> same logs as the host-built task_dic
+    K, T = 40, 4
+    feats = torch.softmax(4 * torch.randn(6000, K, generator=g), -1)
+    labels = torch.randint(0, K, (6000,), generator=g)
+    src = tasks.DeviceTaskSource(feats, labels, dev)
+    def sampler():
+        random.seed(1)
+        torch.manual_seed(2)
+        return tasks.ZeroShotQuerySampler(T, K, 75, labels)
+    on_dev = src.generate_tasks(sampler())
+    host_idx = torch.stack(list(sampler()))
+    on_host = {"x_q": feats[host_idx], "y_q": labels[host_idx].unsqueeze(-1)}
+    assert torch.equal(on_dev["x_q"].cpu(), on_host["x_q"]) and torch.equal(on_dev["y_q"].cpu(), on_host["y_q"])
+    logs = []
+    for td in (on_dev, on_host):
+        m = EM_DIRICHLET(model=None, device=dev, log_file=None, args=make_args(K, iters=4))
+        logs.append(m.run_task(dict(td)))
+    np.testing.assert_array_equal(logs[0]["acc"], logs[1]["acc"])
+    np.testing.assert_array_equal(logs[0]["criterions"], logs[1]["criterions"])
+
+
 def test_batches_in_flight_equal_serial(dev):
     """tclip_b200.pipeline: whole run_task batches on three CUDA streams / host threads give, batch by batch, exactly what
     the same calls give one after the other (own scratch per stream, no shared state between batches)."""

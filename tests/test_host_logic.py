@@ -123,6 +123,34 @@ def test_no_cpu_fallback():
         ops.match_clusters(torch.zeros(1, 3, 4), torch.zeros(1, dtype=torch.int32), torch.zeros(1, 3, dtype=torch.int32))
 
 
+def test_zero_shot_sampler_mirrors_the_reference():
+    """tasks.ZeroShotQuerySampler draws the same index lists as the reference's CategoriesSampler_zero_shot +
+    SamplerQuery_zero_shot under the same seeds (needs the reference checkout: build container only)."""
+    import random
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference checkout not present")
+    mod = ref_loader.load("sampler_zero_shot")
+    g = torch.Generator().manual_seed(3)
+    n_class, n_query, n_batch = 40, 75, 6
+    labels = torch.randint(0, n_class, (5000,), generator=g)
+    def draw(make):
+        random.seed(11)
+        torch.manual_seed(12)
+        return [q.clone() for q in make()]
+    def ref():
+        cs = mod.CategoriesSampler_zero_shot(n_batch, 5, n_class, n_query, force_query_size=True)
+        cs.create_list_classes(labels)
+        return mod.SamplerQuery_zero_shot(cs)
+    want = draw(ref)
+    got = draw(lambda: tasks.ZeroShotQuerySampler(n_batch, n_class, n_query, labels, force_query_size=True))
+    assert len(want) == len(got) == n_batch
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tasks.DeviceTaskSource(torch.zeros(4, 3), torch.zeros(4), torch.device("cpu"))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

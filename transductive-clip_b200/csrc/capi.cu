@@ -550,6 +550,15 @@ int tclip_match_clusters(const float* probs, const int* n_clusters, const int* s
   return TCLIP_OK;
 }
 
+int tclip_gather_tasks(const float* features, const long long* labels, const long long* idx, float* x_q, long long* y_q,
+                       long long n_rows, long long count, int F, int* bad, void* stream) {
+  if (!features || !idx || !x_q || n_rows < 1 || count < 1 || F < 1 || (y_q && !labels))
+    return fail(TCLIP_ERR_INVALID, "tclip_gather_tasks: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::gather_tasks(features, labels, idx, x_q, y_q, n_rows, count, F, bad, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
 int tclip_normalize_rows(const float* x, float* out, long long rows, int D, void* stream) {
   if (!x || !out || rows < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_normalize_rows: bad arguments");
   if (int rc = current_device_ok()) return rc;

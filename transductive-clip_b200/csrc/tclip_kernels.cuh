@@ -98,6 +98,10 @@ cudaError_t match_clusters(const float* proto, const int* n_clusters, const int*
                            int graph_matching, int* cluster_class, long long* new_labels, float* acc, int T, int n, int K,
                            int proto_rows, cudaStream_t st);
 
+// task_gather.cu: x_q[m, :] = features[idx[m], :], y_q[m] = labels[idx[m]] (device-side task construction)
+cudaError_t gather_tasks(const float* features, const long long* labels, const long long* idx, float* x_q,
+                         long long* y_q, long long n_rows, long long count, int F, int* bad, cudaStream_t st);
+
 // ---- soft / hard k-means and EM-Gaussian (kmeans.cu) -----------------------------------------------------------------
 cudaError_t normalize_rows(const float* x, float* out, long rows, int D, cudaStream_t st);
 cudaError_t kmeans_similarity(const float* a, const float* text, float scale, float* u, long M, int K, int D,

@@ -189,6 +189,22 @@ def match_clusters(probs: torch.Tensor, n_clusters: torch.Tensor, sample_cluster
     return out
 
 
+def gather_tasks(features: torch.Tensor, labels: torch.Tensor | None, idx: torch.Tensor):
+    """x_q [*, F] = features[idx], y_q [*] = labels[idx] on the device (``idx`` int64 CUDA tensor of any shape).
+    Raises ``IndexError`` if an index lies outside the feature matrix."""
+    lib = _lib.load()
+    _need(features, torch.float32, "features"), _need(idx, torch.int64, "idx")
+    if labels is not None:
+        _need(labels, torch.int64, "labels")
+    N, F = features.shape
+    x_q = torch.empty(*idx.shape, F, device=features.device, dtype=torch.float32)
+    y_q = torch.empty(idx.shape, device=features.device, dtype=torch.int64) if labels is not None else None
+    bad = torch.zeros(1, device=features.device, dtype=torch.int32)
+    check(lib.tclip_gather_tasks(_ptr(features), _ptr(labels), _ptr(idx), _ptr(x_q), _ptr(y_q), N, idx.numel(), F,
+                                 _ptr(bad), _stream()))
+    return x_q, y_q, bad
+
+
 # ---- k-means family ------------------------------------------------------------------------------------------------
 KMEANS_SOFT, KMEANS_GAUSS, KMEANS_HARD = 0, 1, 2
 

@@ -92,3 +92,64 @@ def shard_batches(n_batches: int, rank: int, world_size: int) -> list[int]:
     """Whole ``run_task`` batches are the unit of sharding (the MM break test is batch-global,
     ``src/methods/zero_shot/em_dirichlet.py:169-175``): batch i goes to rank i mod W."""
     return [i for i in range(n_batches) if i % world_size == rank]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Device-side task construction from cached features (SURVEY.md §8(f) rank 3)
+# ----------------------------------------------------------------------------------------------------------------------
+class ZeroShotQuerySampler:
+    """The index sampler of the reference's zero-shot evaluator: ``CategoriesSampler_zero_shot`` +
+    ``SamplerQuery_zero_shot`` (``src/sampler_zero_shot.py:6-72``), same random calls in the same order
+    (``random.randint(3, 10)`` for k_eff, ``torch.randperm`` for the classes and for the samples), so that with the same
+    seeds it yields the same index lists.  Iterating yields ``n_batch`` int64 tensors of ``n_query`` indices into the
+    cached feature matrix.  ``force_query_size`` re-draws the classes until they hold at least ``n_query`` samples, as the
+    evaluator asks (``src/eval_zero_shot.py:153-154``)."""
+
+    def __init__(self, n_batch: int, n_class: int, n_query: int, labels, force_query_size: bool = True):
+        import numpy as np
+        self.n_batch, self.n_class, self.n_query = int(n_batch), int(n_class), int(n_query)
+        self.force_query_size = force_query_size
+        lab = np.asarray(labels.cpu() if isinstance(labels, torch.Tensor) else labels)
+        self.m_ind_query = [torch.from_numpy(np.argwhere(lab == i).reshape(-1)) for i in range(self.n_class)]
+
+    def __len__(self):
+        return self.n_batch
+
+    def __iter__(self):
+        import random
+        for _ in range(self.n_batch):
+            k_eff = random.randint(3, 10)
+            query_size, n_trials = 0, 0
+            while query_size < self.n_query and n_trials < 1:
+                classes = torch.randperm(self.n_class)[:k_eff].tolist()
+                pool = torch.cat([self.m_ind_query[c] for c in classes])
+                query = pool[torch.randperm(len(pool))[:self.n_query]]
+                if not self.force_query_size:
+                    n_trials += 1
+                query_size = len(query)
+            yield query
+
+
+class DeviceTaskSource:
+    """Cached features and labels resident on the GPU; ``generate_tasks(sampler)`` turns the sampler's index lists into a
+    ``task_dic`` of CUDA tensors with one gather kernel (``tclip_gather_tasks``).  Stands in for the per-task indexing of
+    the evaluator plus ``Tasks_Generator_zero_shot.generate_tasks`` (``src/eval_zero_shot.py:158-168``,
+    ``src/task_generator_zero_shot.py:36-65``): same tensors, but only T*n indices cross PCIe instead of T*n*F floats.
+    ``sampler`` is any iterable of index tensors — this module's ``ZeroShotQuerySampler`` or the reference's own
+    ``SamplerQuery_zero_shot``."""
+
+    def __init__(self, all_features, all_labels, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("tclip_b200 runs on B200 GPUs only: device must be a CUDA device (no CPU fallback)")
+        self.features = all_features.to(self.device, torch.float32).contiguous()
+        self.labels = all_labels.to(self.device).long().contiguous()
+
+    def generate_tasks(self, sampler) -> dict:
+        from . import ops
+        idx = torch.stack([torch.as_tensor(i, dtype=torch.int64) for i in sampler])          # [T, n] on the host
+        idx = idx.pin_memory().to(self.device, non_blocking=True)
+        x_q, y_q, bad = ops.gather_tasks(self.features, self.labels, idx)
+        if int(bad.item()):
+            raise IndexError("sampler index outside the cached feature matrix")
+        return {"x_q": x_q, "y_q": y_q.unsqueeze(-1)}
