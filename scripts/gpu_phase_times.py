@@ -8,7 +8,7 @@ from tclip_b200 import tasks, ops
 from tclip_b200.methods.dirichlet import EM_DIRICHLET, HARD_EM_DIRICHLET
 from oracle.ref_loader import make_args
 dev = torch.device("cuda:0")
-K, T = 1000, 75
+K, T = int(os.environ.get("PT_K", 1000)), int(os.environ.get("PT_T", 75))
 ONLY_SKIP = "--skip-only" in sys.argv
 for hard, iters in ((False, 20), (True, 10)):
     for mode in ("skip_dead", "dense"):

@@ -206,7 +206,8 @@ mm_chunk_kernel(const ChunkArgs g) {
     const int probe0 = 6 + (n_iters & 1);
     double s = warp_sum_f64((double)lane_tree_sum<NP>(a, tail_mask));
     if (!FR) {
-      psi_anchor_reset(anchors[warp]);  // (every lane writes the same values)
+      __syncwarp();                     // the previous row of this warp is done with its anchor
+      if (lane == 0) psi_anchor_reset(anchors[warp]);
       __syncwarp();
     }
     // one vote per row and iteration decides whether any element needs the small-a Taylor form (rare: fixed points sit
@@ -238,7 +239,10 @@ mm_chunk_kernel(const ChunkArgs g) {
       if (FR) {
         rp = row_psi(s);
       } else {
-        rp = row_psi_anchored(s, anchors[warp]);
+        PsiAnchor an = anchors[warp];        // broadcast read: the 32 lanes hold the same row total, hence the same anchor
+        const double anchored_at = an.s;
+        rp = row_psi_anchored(s, an);
+        if (an.s != anchored_at && lane == 0) anchors[warp] = an;  // re-anchored (rare): one lane publishes it
         __syncwarp();
       }
       const bool any_small = __any_sync(0xffffffffu, amin < kSmallA);
@@ -652,7 +656,7 @@ constexpr auto make_table(std::integer_sequence<int, I...>) {
 SpecFn spec_fn(int np) {
   switch (np) {
     case 1: return &launch_spec<1, 1>;
-    case 2: return &launch_spec<2, 1>;
+    case 2: return &launch_spec<1, 2>;   // D <= 128: one warp, no cross-warp traffic on the serial path
     case 3: return &launch_spec<3, 1>;
     case 4: return &launch_spec<4, 1>;
     case 5: case 6: case 7: case 8: return &launch_spec<4, 2>;
