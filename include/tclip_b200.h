@@ -178,6 +178,15 @@ int tclip_match_clusters(const float* probs, const int* n_clusters, const int* s
 int tclip_gather_tasks(const float* features, const long long* labels, const long long* idx, float* x_q, long long* y_q,
                        long long n_rows, long long count, int F, int* bad, void* stream);
 
+/* The few-shot form of the same: Tasks_Generator_few_shot.get_task (src/task_generator_few_shot.py:27-58) relabels every
+ * task and, with softmax features, re-orders the columns.  col_perm [T, U] int64 = the task's `unique_labels`, label_map
+ * [T, n_labels] int64 = position of every label in that list (both built on the host with the reference's torch calls);
+ * idx [T * per_task].  x_out[t, m, j] = features[idx[t, m], col_perm[t, j]] ([T, per_task, U]), y_out[t, m] =
+ * label_map[t, labels[idx[t, m]]].  `bad` counts rows with an index, column or label out of range. */
+int tclip_gather_tasks_remap(const float* features, const long long* labels, const long long* idx, const long long* col_perm,
+                             const long long* label_map, float* x_out, long long* y_out, long long n_rows, long long count,
+                             int per_task, int F, int U, int n_labels, int* bad, void* stream);
+
 /* ---- fused driver: the whole run_method loop, enqueued on one stream without host synchronisation -------------- */
 typedef struct tclip_dirichlet_problem {
   int n_task, n_query, n_class, dim; /* T, n, K, D (D == K: softmax features) */

@@ -71,3 +71,21 @@ class patched_oracle:
     def __exit__(self, *exc):
         R.mm_update_alpha = self._orig
         return False
+
+
+def few_shot_tasks_on_host(fs, ls, fq, lq, idx_s, idx_q):
+    """``Tasks_Generator_few_shot.get_task`` + ``generate_tasks`` (src/task_generator_few_shot.py:27-99, softmax features)
+    written out with torch indexing on the host: the checker of ``tasks.DeviceFewShotTaskSource``.  Validated against the
+    reference's own class in tests/test_host_logic.py."""
+    import torch
+    out = {"x_s": [], "y_s": [], "x_q": [], "y_q": []}
+    for i_s, i_q in zip(idx_s, idx_q):
+        lab_s, lab_q = ls[i_s], lq[i_q]
+        uniq = torch.flip(torch.unique(lab_s, sorted=False), dims=(0,))
+        ns, nq = torch.zeros_like(lab_s), torch.zeros_like(lab_q)
+        for j, y in enumerate(uniq):
+            ns[lab_s == y] = j
+            nq[lab_q == y] = j
+        out["x_s"].append(fs[i_s][:, uniq]); out["y_s"].append(ns.long())
+        out["x_q"].append(fq[i_q][:, uniq]); out["y_q"].append(nq.long())
+    return {k: torch.stack(v) for k, v in out.items()}

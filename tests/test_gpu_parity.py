@@ -383,6 +383,35 @@ def test_device_task_construction(dev):
     np.testing.assert_array_equal(logs[0]["criterions"], logs[1]["criterions"])
 
 
+def test_device_few_shot_task_construction(dev):
+    """tasks.DeviceFewShotTaskSource against the host construction of tests/host_twin.py (which the CPU suite checks against
+    the reference's own Tasks_Generator_few_shot)."""
+    import random
+    from tclip_b200 import tasks
+    g = torch.Generator().manual_seed(21)
+    n_class, n_query, T, shots, k_eff = 16, 75, 3, 2, 5
+    fs = torch.softmax(2 * torch.randn(400, n_class, generator=g), -1)
+    ls = torch.cat([torch.arange(n_class).repeat(5), torch.randint(0, n_class, (320,), generator=g)])
+    fq = torch.softmax(2 * torch.randn(3000, n_class, generator=g), -1)
+    lq = torch.randint(0, n_class, (3000,), generator=g)
+    def samplers():
+        random.seed(3)
+        torch.manual_seed(4)
+        return tasks.FewShotSamplers(T, k_eff, n_class, shots, n_query, ls, lq)
+    smp = samplers()
+    idx_q = list(smp.query())
+    idx_s = list(smp.support())
+    from host_twin import few_shot_tasks_on_host
+    want = few_shot_tasks_on_host(fs, ls, fq, lq, idx_s, idx_q)   # checked against the reference in test_host_logic.py
+    src = tasks.DeviceFewShotTaskSource(fs, ls, fq, lq, dev)
+    smp = samplers()
+    q_it = list(smp.query())
+    got = src.generate_tasks(smp.support(), q_it)
+    for k in want:
+        assert torch.equal(got[k].cpu().reshape(want[k].shape), want[k]), k
+    assert got["x_s"].shape == (T, n_class * shots, n_class) and got["y_q"].shape == (T, n_query, 1)
+
+
 def test_batches_in_flight_equal_serial(dev):
     """tclip_b200.pipeline: whole run_task batches on three CUDA streams / host threads give, batch by batch, exactly what
     the same calls give one after the other (own scratch per stream, no shared state between batches)."""

@@ -151,6 +151,56 @@ def test_zero_shot_sampler_mirrors_the_reference():
         tasks.DeviceTaskSource(torch.zeros(4, 3), torch.zeros(4), torch.device("cpu"))
 
 
+def test_few_shot_samplers_mirror_the_reference():
+    import random
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference checkout not present")
+    mod = ref_loader.load("sampler_few_shot")
+    g = torch.Generator().manual_seed(4)
+    n_class, n_query, n_batch, shots, k_eff = 12, 75, 4, 3, 5
+    ls = torch.cat([torch.arange(n_class).repeat(6), torch.randint(0, n_class, (200,), generator=g)])
+    lq = torch.randint(0, n_class, (4000,), generator=g)
+    def seeded():
+        random.seed(5)
+        torch.manual_seed(6)
+    seeded()
+    cs = mod.CategoriesSampler_few_shot(n_batch, k_eff, n_class, shots, n_query, force_query_size=True)
+    cs.create_list_classes(ls, lq)
+    want_q = [q.clone() for q in mod.SamplerQuery_few_shot(cs)]
+    want_s = [q.clone() for q in mod.SamplerSupport_few_shot(cs)]
+    seeded()
+    mine = tasks.FewShotSamplers(n_batch, k_eff, n_class, shots, n_query, ls, lq)
+    got_q = [q.clone() for q in mine.query()]
+    got_s = [q.clone() for q in mine.support()]
+    assert all(torch.equal(a, b) for a, b in zip(want_q, got_q)) and len(got_q) == n_batch
+    assert all(torch.equal(a, b) for a, b in zip(want_s, got_s)) and len(got_s) == n_batch
+
+
+def test_few_shot_host_construction_equals_reference_generator():
+    from oracle import ref_loader
+    from host_twin import few_shot_tasks_on_host
+    if not ref_loader.available():
+        pytest.skip("reference checkout not present")
+    g = torch.Generator().manual_seed(22)
+    n_class, n_query, T, shots, k_eff = 16, 75, 3, 2, 5
+    fs = torch.softmax(2 * torch.randn(400, n_class, generator=g), -1)
+    ls = torch.cat([torch.arange(n_class).repeat(5), torch.randint(0, n_class, (320,), generator=g)])
+    fq = torch.softmax(2 * torch.randn(3000, n_class, generator=g), -1)
+    lq = torch.randint(0, n_class, (3000,), generator=g)
+    torch.manual_seed(9)
+    smp = tasks.FewShotSamplers(T, k_eff, n_class, shots, n_query, ls, lq)
+    idx_q, idx_s = list(smp.query()), list(smp.support())
+    want = few_shot_tasks_on_host(fs, ls, fq, lq, idx_s, idx_q)
+    gen = ref_loader.load("task_generator_few_shot").Tasks_Generator_few_shot(
+        k_eff=k_eff, shot=shots, n_query=n_query, n_class=n_class,
+        loader_support=[(fs[i, :], ls[i]) for i in idx_s], loader_query=[(fq[i, :], lq[i]) for i in idx_q],
+        model=None, args=make_args(n_class, use_softmax_feature=True))
+    ref = gen.generate_tasks()
+    for k in want:
+        assert torch.equal(ref[k].reshape(want[k].shape), want[k]), k
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

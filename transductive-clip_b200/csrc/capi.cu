@@ -559,6 +559,18 @@ int tclip_gather_tasks(const float* features, const long long* labels, const lon
   return TCLIP_OK;
 }
 
+int tclip_gather_tasks_remap(const float* features, const long long* labels, const long long* idx, const long long* col_perm,
+                             const long long* label_map, float* x_out, long long* y_out, long long n_rows, long long count,
+                             int per_task, int F, int U, int n_labels, int* bad, void* stream) {
+  if (!features || !labels || !idx || !col_perm || !label_map || !x_out || n_rows < 1 || count < 1 || per_task < 1 ||
+      F < 1 || U < 1 || n_labels < 1 || count % per_task != 0)
+    return fail(TCLIP_ERR_INVALID, "tclip_gather_tasks_remap: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::gather_tasks_remap(features, labels, idx, col_perm, label_map, x_out, y_out, n_rows, count, per_task,
+                                       F, U, n_labels, bad, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
 int tclip_normalize_rows(const float* x, float* out, long long rows, int D, void* stream) {
   if (!x || !out || rows < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_normalize_rows: bad arguments");
   if (int rc = current_device_ok()) return rc;

@@ -52,3 +52,57 @@ cudaError_t gather_tasks(const float* features, const long long* labels, const l
 }
 
 }  // namespace tclip
+
+// Few-shot form: Tasks_Generator_few_shot.get_task (src/task_generator_few_shot.py:27-58) also relabels every task —
+// `unique_labels = flip(unique(labels_support, sorted=False))`, label y -> its position in that list, and with softmax
+// features the columns are re-ordered the same way (`data[:, unique_labels]`).  The per-task column list (col_perm [T, U])
+// and the label map (label_map [T, n_labels], 0 where the reference leaves its zeros) are built on the host with the
+// reference's own torch calls; this kernel applies them while gathering: x_out[t, m, j] = features[idx[t, m], col_perm[t, j]],
+// y_out[t, m] = label_map[t, labels[idx[t, m]]].
+namespace tclip {
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+gather_tasks_remap_kernel(const float* __restrict__ features, const long long* __restrict__ labels,
+                          const long long* __restrict__ idx, const long long* __restrict__ col_perm,
+                          const long long* __restrict__ label_map, float* __restrict__ x_out,
+                          long long* __restrict__ y_out, long long n_rows, long long count, int per_task, int F, int U,
+                          int n_labels, int* __restrict__ bad) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= count) return;
+  const long long t = m / per_task;
+  long long r = idx[m];
+  bool ok = r >= 0 && r < n_rows;
+  if (!ok) r = 0;
+  const float* src = features + r * F;
+  const long long* perm = col_perm + t * U;
+  float* dst = x_out + m * U;
+  for (int j = lane; j < U; j += 32) {
+    const long long c = perm[j];
+    const bool okc = c >= 0 && c < F;
+    ok &= okc;
+    dst[j] = (ok && okc) ? src[c] : 0.0f;
+  }
+  long long lab = ok ? labels[r] : -1;
+  const bool okl = lab >= 0 && lab < n_labels;
+  if (lane == 0 && y_out) y_out[m] = okl ? label_map[t * n_labels + lab] : -1;
+  ok = __all_sync(0xffffffffu, ok) && okl;
+  if (!ok && lane == 0 && bad) atomicAdd(bad, 1);
+}
+
+}  // namespace
+
+cudaError_t gather_tasks_remap(const float* features, const long long* labels, const long long* idx,
+                               const long long* col_perm, const long long* label_map, float* x_out, long long* y_out,
+                               long long n_rows, long long count, int per_task, int F, int U, int n_labels, int* bad,
+                               cudaStream_t st) {
+  const long long blocks = (count + 7) / 8;
+  gather_tasks_remap_kernel<<<(unsigned)blocks, 256, 0, st>>>(features, labels, idx, col_perm, label_map, x_out, y_out,
+                                                             n_rows, count, per_task, F, U, n_labels, bad);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace tclip

@@ -102,6 +102,11 @@ cudaError_t match_clusters(const float* proto, const int* n_clusters, const int*
 cudaError_t gather_tasks(const float* features, const long long* labels, const long long* idx, float* x_q,
                          long long* y_q, long long n_rows, long long count, int F, int* bad, cudaStream_t st);
 
+cudaError_t gather_tasks_remap(const float* features, const long long* labels, const long long* idx,
+                               const long long* col_perm, const long long* label_map, float* x_out, long long* y_out,
+                               long long n_rows, long long count, int per_task, int F, int U, int n_labels, int* bad,
+                               cudaStream_t st);
+
 // ---- soft / hard k-means and EM-Gaussian (kmeans.cu) -----------------------------------------------------------------
 cudaError_t normalize_rows(const float* x, float* out, long rows, int D, cudaStream_t st);
 cudaError_t kmeans_similarity(const float* a, const float* text, float scale, float* u, long M, int K, int D,

@@ -75,6 +75,8 @@ SIGNATURES = {
                                      c_int, c_int, c_int, c_void_p]),
     "tclip_gather_tasks": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int,
                                    c_void_p, c_void_p]),
+    "tclip_gather_tasks_remap": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                         c_longlong, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tclip_normalize_rows": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "tclip_kmeans_similarity": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "tclip_kmeans_centroids": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -205,6 +205,24 @@ def gather_tasks(features: torch.Tensor, labels: torch.Tensor | None, idx: torch
     return x_q, y_q, bad
 
 
+def gather_tasks_remap(features: torch.Tensor, labels: torch.Tensor, idx: torch.Tensor, col_perm: torch.Tensor,
+                       label_map: torch.Tensor):
+    """Few-shot task construction: idx [T, m], col_perm [T, U], label_map [T, n_labels] (int64 CUDA tensors) ->
+    x [T, m, U] = features[idx][:, :, col_perm], y [T, m] = label_map[t, labels[idx]]; ``bad`` counts out-of-range rows."""
+    lib = _lib.load()
+    _need(features, torch.float32, "features"), _need(labels, torch.int64, "labels"), _need(idx, torch.int64, "idx")
+    _need(col_perm, torch.int64, "col_perm"), _need(label_map, torch.int64, "label_map")
+    N, F = features.shape
+    T, m = idx.shape
+    U, n_labels = col_perm.shape[1], label_map.shape[1]
+    x = torch.empty(T, m, U, device=features.device, dtype=torch.float32)
+    y = torch.empty(T, m, device=features.device, dtype=torch.int64)
+    bad = torch.zeros(1, device=features.device, dtype=torch.int32)
+    check(lib.tclip_gather_tasks_remap(_ptr(features), _ptr(labels), _ptr(idx), _ptr(col_perm), _ptr(label_map), _ptr(x),
+                                       _ptr(y), N, T * m, m, F, U, n_labels, _ptr(bad), _stream()))
+    return x, y, bad
+
+
 # ---- k-means family ------------------------------------------------------------------------------------------------
 KMEANS_SOFT, KMEANS_GAUSS, KMEANS_HARD = 0, 1, 2
 

@@ -153,3 +153,85 @@ class DeviceTaskSource:
         if int(bad.item()):
             raise IndexError("sampler index outside the cached feature matrix")
         return {"x_q": x_q, "y_q": y_q.unsqueeze(-1)}
+
+
+class FewShotSamplers:
+    """The two index samplers of the reference's few-shot evaluator (``src/sampler_few_shot.py``): ``support()`` mirrors
+    ``SamplerSupport_few_shot`` (``s_shot`` samples of every class, one ``torch.randperm`` per class) and ``query()``
+    mirrors ``SamplerQuery_few_shot`` (``k_eff`` classes by ``torch.randperm``, then ``n_query`` of their samples).  The
+    evaluator iterates the query sampler completely before the support sampler (``src/eval_few_shot.py:233-243``); keep
+    that order to reproduce its random stream."""
+
+    def __init__(self, n_batch: int, k_eff: int, n_class: int, s_shot: int, n_query: int, label_support, label_query,
+                 force_query_size: bool = True):
+        import numpy as np
+        self.n_batch, self.k_eff, self.n_class = int(n_batch), int(k_eff), int(n_class)
+        self.s_shot, self.n_query, self.force_query_size = int(s_shot), int(n_query), force_query_size
+        ls = np.asarray(label_support.cpu() if isinstance(label_support, torch.Tensor) else label_support)
+        lq = np.asarray(label_query.cpu() if isinstance(label_query, torch.Tensor) else label_query)
+        n = int(ls.max()) + 1
+        self.m_ind_support = [torch.from_numpy(np.argwhere(ls == i).reshape(-1)) for i in range(n)]
+        self.m_ind_query = [torch.from_numpy(np.argwhere(lq == i).reshape(-1)) for i in range(n)]
+
+    def support(self):
+        for _ in range(self.n_batch):
+            yield torch.cat([self.m_ind_support[c][torch.randperm(len(self.m_ind_support[c]))[:self.s_shot]]
+                             for c in range(self.n_class)])
+
+    def query(self):
+        for _ in range(self.n_batch):
+            query_size, n_trials = 0, 0
+            while query_size < self.n_query and n_trials < 1:
+                classes = torch.randperm(self.n_class)[:self.k_eff].tolist()
+                pool = torch.cat([self.m_ind_query[c] for c in classes])
+                query = pool[torch.randperm(len(pool))[:self.n_query]]
+                if not self.force_query_size:
+                    n_trials += 1
+                query_size = len(query)
+            yield query
+
+
+class DeviceFewShotTaskSource:
+    """Few-shot counterpart of ``DeviceTaskSource``: support and query features resident on the GPU; ``generate_tasks``
+    applies the sampler's index lists and the per-task relabelling / column re-ordering of
+    ``Tasks_Generator_few_shot.get_task`` (``src/task_generator_few_shot.py:27-58``) in two gather kernels.  The task's
+    ``unique_labels`` come from the very torch call the reference makes (``torch.flip(torch.unique(labels_support,
+    sorted=False), dims=(0,))`` on the host copy of the S support labels), so the class order is the reference's."""
+
+    def __init__(self, features_support, labels_support, features_query, labels_query, device,
+                 use_softmax_feature: bool = True):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("tclip_b200 runs on B200 GPUs only: device must be a CUDA device (no CPU fallback)")
+        self.use_softmax_feature = bool(use_softmax_feature)
+        self.labels_support_host = labels_support.cpu().long()
+        self.fs = features_support.to(self.device, torch.float32).contiguous()
+        self.ls = self.labels_support_host.to(self.device).contiguous()
+        self.fq = features_query.to(self.device, torch.float32).contiguous()
+        self.lq = labels_query.to(self.device).long().contiguous()
+
+    def generate_tasks(self, sampler_support, sampler_query) -> dict:
+        from . import ops
+        idx_q = torch.stack([torch.as_tensor(i, dtype=torch.int64) for i in sampler_query])      # query sampler first
+        idx_s = torch.stack([torch.as_tensor(i, dtype=torch.int64) for i in sampler_support])
+        T, F = idx_s.shape[0], self.fs.shape[1]
+        if self.use_softmax_feature:
+            uniq = [torch.flip(torch.unique(self.labels_support_host[idx_s[t]], sorted=False), dims=(0,)) for t in range(T)]
+            if len({int(u.numel()) for u in uniq}) != 1:
+                raise ValueError("tasks of one batch must see the same number of support classes")
+            col_perm = torch.stack(uniq)                                                         # [T, U]
+            n_labels = int(max(int(self.labels_support_host.max()), int(col_perm.max()))) + 1
+            label_map = torch.zeros(T, n_labels, dtype=torch.int64)                              # zeros_like in get_task
+            label_map.scatter_(1, col_perm, torch.arange(col_perm.shape[1]).expand(T, -1))
+        else:  # visual features: data and labels pass through unchanged
+            col_perm = torch.arange(F).expand(T, -1).contiguous()
+            n_labels = int(self.labels_support_host.max()) + 1
+            label_map = torch.arange(n_labels).expand(T, -1).contiguous()
+        dev = self.device
+        put = lambda x: x.contiguous().pin_memory().to(dev, non_blocking=True)
+        idx_q, idx_s, col_perm, label_map = put(idx_q), put(idx_s), put(col_perm), put(label_map)
+        x_s, y_s, bad_s = ops.gather_tasks_remap(self.fs, self.ls, idx_s, col_perm, label_map)
+        x_q, y_q, bad_q = ops.gather_tasks_remap(self.fq, self.lq, idx_q, col_perm, label_map)
+        if int((bad_s + bad_q).item()):
+            raise IndexError("sampler index, class column or label outside the cached features")
+        return {"x_s": x_s, "y_s": y_s.unsqueeze(-1), "x_q": x_q, "y_q": y_q.unsqueeze(-1)}
