@@ -119,3 +119,20 @@ def test_kmeans_rn50_shape_properties(dev):
             live = sizes > 0
             assert torch.allclose(nxt.w[live], w[live], rtol=1e-4, atol=1e-6)
             assert (nxt.w[~live] == 0).all()
+
+
+def test_feature_extraction_epilogue(dev):
+    """tclip_b200.features.softmax_features / visual_features vs the reference's formulas in float64
+    (src/utils.py:286-290,343-344)."""
+    from tclip_b200 import features
+    g = torch.Generator().manual_seed(12)
+    for N, E, K, T in ((300, 1024, 1000, 30.0), (77, 512, 37, 10.0), (5, 64, 3, 50.0)):
+        emb = 3.0 * torch.randn(N, E, generator=g)
+        txt = torch.nn.functional.normalize(torch.randn(K, E, generator=g), dim=-1)
+        want_v = torch.nn.functional.normalize(emb.double(), dim=-1)
+        want_s = torch.softmax(T * want_v @ txt.double().T, -1)
+        got_v = features.visual_features(emb.to(dev)).cpu()
+        got_s = features.softmax_features(emb.to(dev), txt.to(dev), T).cpu()
+        np.testing.assert_allclose(got_v.numpy(), want_v.numpy(), rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(got_s.numpy(), want_s.numpy(), rtol=2e-4, atol=1e-7)
+        assert torch.allclose(got_s.sum(-1), torch.ones(N), atol=1e-5)

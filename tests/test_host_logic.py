@@ -201,6 +201,31 @@ def test_few_shot_host_construction_equals_reference_generator():
         assert torch.equal(ref[k].reshape(want[k].shape), want[k]), k
 
 
+def test_feature_cache_format_roundtrip(tmp_path):
+    """tclip_b200.features writes / reads the reference's .plk cache (src/utils.py:241-249,298-306): our file loads with the
+    reference's load_pickle and vice versa; paths follow the reference's naming."""
+    from tclip_b200 import features
+    g = torch.Generator().manual_seed(1)
+    feats = torch.softmax(torch.randn(50, 7, generator=g), -1)
+    labels = torch.randint(0, 7, (50,), generator=g)
+    p = features.softmax_features_path("caltech101", "test", "RN50", 30, root=str(tmp_path))
+    assert p.endswith(os.path.join("caltech101", "saved_features", "test_softmax_RN50_T30.plk"))
+    assert features.visual_features_path("caltech101", "val", "RN50", root="data") == \
+        os.path.join("data", "caltech101", "saved_features", "val_visual_RN50.plk")
+    features.save_features(p, feats, labels)
+    f2, l2 = features.load_features(p)
+    assert torch.equal(f2, feats) and torch.equal(l2, labels) and l2.dtype == torch.int64
+    from oracle import ref_loader
+    if ref_loader.available():
+        utils = ref_loader.load("utils")
+        d = utils.load_pickle(p)                                  # the reference reads our file
+        assert torch.equal(d["concat_features"], feats) and torch.equal(d["concat_labels"], labels)
+        q = str(tmp_path / "ref.plk")
+        utils.save_pickle(q, {"concat_features": feats, "concat_labels": labels.int()})
+        f3, l3 = features.load_features(q)                        # we read the reference's file
+        assert torch.equal(f3, feats) and torch.equal(l3, labels)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
