@@ -63,70 +63,100 @@ __global__ void colsum_v_kernel(const float* __restrict__ u, float* __restrict__
 
 // ---- moments: y[t,k,d] = sum_n u[t,n,k] logz[t,n,d] / colsum[t,k]  (a [K x n] . [n x D] product per task) --------
 // 64(k) x 64(d) tile per CTA, 256 threads, 4x4 outputs per thread, n staged through shared memory.
-constexpr int kMomTile = 64;
-constexpr int kMomStage = 16;
+constexpr int kMomTile = 128;   // clusters x feature columns per CTA
+constexpr int kMomStage = 16;   // queries staged per step
 
 // `gate` (optional, device): {n_live, row cap}; the dense kernel runs iff n_live > cap, the row-wise one otherwise, so
 // the host can enqueue both without knowing how many clusters are alive.
 __device__ __forceinline__ bool dense_selected(const int* gate) { return gate == nullptr || gate[0] > gate[1]; }
 
+// 128 x 128 outputs per CTA, 256 threads, 8 x 8 per thread as two 4-wide groups 64 apart in each direction (16-byte
+// shared-memory reads without bank conflicts, 16-byte global accesses).  Every output is one fma chain over the queries in
+// index order, the order moments_rows_kernel uses too.
 __global__ void __launch_bounds__(256)
 moments_kernel(const float* __restrict__ u, const float* __restrict__ logz, const float* __restrict__ colsum,
                const float* __restrict__ support_sum, const float* __restrict__ support_count,
                float* __restrict__ y, int n, int K, int D, int few_shot, const int* __restrict__ gate) {
   if (!dense_selected(gate)) return;
-  __shared__ float us[kMomStage][kMomTile + 4];
-  __shared__ float ls[kMomStage][kMomTile + 4];
+  __shared__ __align__(16) float us[kMomStage][kMomTile + 4];
+  __shared__ __align__(16) float ls[kMomStage][kMomTile + 4];
   const int t = blockIdx.z;
   const int k0 = blockIdx.y * kMomTile;
   const int d0 = blockIdx.x * kMomTile;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const float* ub = u + (long)t * n * K;
   const float* lb = logz + (long)t * n * D;
+  const bool vec = ((K | D) & 3) == 0 &&
+                   ((reinterpret_cast<unsigned long long>(u) | reinterpret_cast<unsigned long long>(logz) |
+                     reinterpret_cast<unsigned long long>(y)) & 15ull) == 0;
 
-  // a CTA whose 64 clusters are all empty only has to write the fill value
-  float acc[4][4] = {};
+  float acc[8][8] = {};
   for (int n0 = 0; n0 < n; n0 += kMomStage) {
-    for (int i = threadIdx.x; i < kMomStage * kMomTile; i += 256) {
-      const int r = i / kMomTile, c = i % kMomTile;
-      const int nn = n0 + r;
-      us[r][c] = (nn < n && k0 + c < K) ? ub[(long)nn * K + k0 + c] : 0.0f;
-      ls[r][c] = (nn < n && d0 + c < D) ? lb[(long)nn * D + d0 + c] : 0.0f;
+    if (vec) {
+      for (int i = threadIdx.x; i < kMomStage * kMomTile / 4; i += 256) {
+        const int r = i / (kMomTile / 4), c = (i % (kMomTile / 4)) * 4;
+        const int nn = n0 + r;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (nn < n && k0 + c < K) a = *reinterpret_cast<const float4*>(ub + (long)nn * K + k0 + c);
+        if (nn < n && d0 + c < D) b = *reinterpret_cast<const float4*>(lb + (long)nn * D + d0 + c);
+        *reinterpret_cast<float4*>(&us[r][c]) = a;
+        *reinterpret_cast<float4*>(&ls[r][c]) = b;
+      }
+    } else {
+      for (int i = threadIdx.x; i < kMomStage * kMomTile; i += 256) {
+        const int r = i / kMomTile, c = i % kMomTile;
+        const int nn = n0 + r;
+        us[r][c] = (nn < n && k0 + c < K) ? ub[(long)nn * K + k0 + c] : 0.0f;
+        ls[r][c] = (nn < n && d0 + c < D) ? lb[(long)nn * D + d0 + c] : 0.0f;
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kMomStage; ++r) {
-      float uu[4], ll[4];
+      float uu[8], ll[8];
+      const float4 u0 = *reinterpret_cast<const float4*>(&us[r][ty * 4]);
+      const float4 u1 = *reinterpret_cast<const float4*>(&us[r][64 + ty * 4]);
+      const float4 l0 = *reinterpret_cast<const float4*>(&ls[r][tx * 4]);
+      const float4 l1 = *reinterpret_cast<const float4*>(&ls[r][64 + tx * 4]);
+      uu[0] = u0.x; uu[1] = u0.y; uu[2] = u0.z; uu[3] = u0.w; uu[4] = u1.x; uu[5] = u1.y; uu[6] = u1.z; uu[7] = u1.w;
+      ll[0] = l0.x; ll[1] = l0.y; ll[2] = l0.z; ll[3] = l0.w; ll[4] = l1.x; ll[5] = l1.y; ll[6] = l1.z; ll[7] = l1.w;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uu[i] = us[r][ty * 4 + i];
-        ll[i] = ls[r][tx * 4 + i];
-      }
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(uu[i], ll[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(uu[i], ll[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = k0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (k >= K) continue;
     const float cs = colsum[(long)t * K + k];
+    const float sc = few_shot ? support_count[(long)t * K + k] : 0.0f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int d = d0 + tx * 4 + j;
-      if (d >= D) continue;
-      const long o = ((long)t * K + k) * D + d;
-      float val;
-      if (few_shot) {
-        // (1 / (count_s + sum u)) * (support_sum + sum u logz): few_shot/em_dirichlet.py:196-200
-        val = (1.0f / (support_count[(long)t * K + k] + cs)) * (support_sum[o] + acc[i][j]);
-      } else {
-        val = cs > kEps ? acc[i][j] / fmaxf(cs, kEps) : -10.0f;
+    for (int h = 0; h < 2; ++h) {
+      const int dbase = d0 + h * 64 + tx * 4;
+      float val[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = dbase + j;
+        const long o = ((long)t * K + k) * D + d;
+        const float a = acc[i][h * 4 + j];
+        if (few_shot) {
+          // (1 / (count_s + sum u)) * (support_sum + sum u logz): few_shot/em_dirichlet.py:196-200
+          val[j] = d < D ? (1.0f / (sc + cs)) * (support_sum[o] + a) : 0.0f;
+        } else {
+          val[j] = cs > kEps ? a / fmaxf(cs, kEps) : -10.0f;
+        }
       }
-      y[o] = val;
+      const long o0 = ((long)t * K + k) * D + dbase;
+      if (vec && dbase + 3 < D) {
+        *reinterpret_cast<float4*>(y + o0) = make_float4(val[0], val[1], val[2], val[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (dbase + j < D) y[o0 + j] = val[j];
+      }
     }
   }
 }
