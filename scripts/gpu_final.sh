@@ -13,3 +13,11 @@ PY
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_final.csv \
   python bench.py --streams 1 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launch_final.log 2>&1
 ls -la gpurun_out/launches_final.csv
+echo "== full captures: mm_chunk_kernel (dense), mm_spec_kernel, moments_kernel"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mm_chunk_kernel -s 2 -c 1 -o gpurun_out/prof_mm_final2 \
+  python scripts/gpu_probe2.py > gpurun_out/ncu_full_mm_final2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mm_spec_kernel -s 25 -c 1 -o gpurun_out/prof_spec_final \
+  python scripts/gpu_phase_times.py --skip-only > gpurun_out/ncu_full_spec_final.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:moments_kernel -s 0 -c 1 -o gpurun_out/prof_moments_final \
+  python scripts/gpu_phase_times.py --skip-only > gpurun_out/ncu_full_moments_final.log 2>&1
+ls -la gpurun_out/*final*.ncu-rep
