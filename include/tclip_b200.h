@@ -33,7 +33,7 @@ extern "C" {
 #define TCLIP_MM_SKIP_DEAD 1  /* iterate empty-cluster rows once, replay their cached criterion terms afterwards */
 
 /* ---- library / device --------------------------------------------------------------------------------------- */
-int tclip_version(void);                 /* 100 * major + minor */
+int tclip_version(void);                 /* 100 * major + minor; 101 = 1.1 (1.0 + contraction, match_clusters, gather_tasks, mm_crit) */
 const char* tclip_last_error(void);      /* message of the last failing call on this thread ("" if none) */
 int tclip_device_check(int device);      /* TCLIP_OK iff `device` is compute capability 10.x (B200) */
 int tclip_mm_max_dim(void);              /* largest D the M-step kernel supports (1024) */

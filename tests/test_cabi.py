@@ -58,7 +58,7 @@ def test_struct_layout_matches_header():
 
 def test_plain_calls_without_gpu():
     lib = _lib.load()
-    assert lib.tclip_version() == 100
+    assert lib.tclip_version() == 101
     assert lib.tclip_mm_max_dim() == 1024
     assert lib.tclip_launch_count() >= 0
     assert lib.tclip_dirichlet_mm_workspace_bytes(75000) > 0

@@ -382,7 +382,7 @@ __global__ void record_work_kernel(const tclip::MMState* state, const int* count
 // ======================================================================================================================
 extern "C" {
 
-int tclip_version(void) { return 100; }
+int tclip_version(void) { return 101; }  // 1.1: + contraction, match_clusters, gather_tasks[_remap], problem.mm_crit
 
 const char* tclip_last_error(void) { return g_last_error.c_str(); }
 
