@@ -686,12 +686,13 @@ cudaError_t logits_simt(const float* logz, const float* alpha, float* l3, int T,
 
 // The dense contraction runs on the tensor cores (contraction_tc.cu) whenever TMA can address the operands (D % 4 == 0,
 // n <= 128); other shapes take the CUDA-core kernel.  TCLIP_CONTRACTION=simt forces the latter (measurements).
-static bool use_tensor_cores(int n, int K, int D) {
+static bool use_tensor_cores(const float* logz, const float* alpha, int n, int K, int D) {
   static const bool forced_simt = [] {
     const char* e = std::getenv("TCLIP_CONTRACTION");
     return e && std::string(e) == "simt";
   }();
-  return !forced_simt && logits_tc_supported(n, K, D);
+  const bool aligned = ((reinterpret_cast<unsigned long long>(logz) | reinterpret_cast<unsigned long long>(alpha)) & 15ull) == 0;
+  return !forced_simt && aligned && logits_tc_supported(n, K, D);
 }
 
 // l3 == nullptr: the contraction is written into u and soft-maxed in place (stage entry point).  With a persistent l3
@@ -708,7 +709,7 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
     note_launch(1);
   }
   note_launch(1);
-  if (use_tensor_cores(n, K, D)) {
+  if (use_tensor_cores(logz, alpha, n, K, D)) {
     if (cudaError_t e = logits_tc(logz, alpha, dst, T, n, K, D, gate, false, st)) return e;
   } else {
     if (cudaError_t e = logits_simt(logz, alpha, dst, T, n, K, D, gate, st)) return e;

@@ -354,6 +354,13 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return ws
 
 
+def release_workspaces(stream_ids=None) -> None:
+    """Drop cached scratch buffers: those of the given CUDA stream handles, or all of them."""
+    with _WORKSPACES_LOCK:
+        for key in [k for k in _WORKSPACES if stream_ids is None or k[2] in stream_ids]:
+            del _WORKSPACES[key]
+
+
 def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lambd: float, hard: bool,
                  x_s: torch.Tensor | None = None, y_s: torch.Tensor | None = None, check_every: int = 50,
                  tol: float = 1e-11, mm_mode: int = TCLIP_MM_DENSE, record_events: bool = False) -> dict:

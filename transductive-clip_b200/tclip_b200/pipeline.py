@@ -30,12 +30,16 @@ class BatchPipeline:
             raise ValueError("streams must be >= 1")
         self.streams = int(streams)
         self._local = threading.local()
+        self._stream_ids = set()
+        self._lock = threading.Lock()
         self._pool = ThreadPoolExecutor(max_workers=self.streams, thread_name_prefix="tclip-batch")
 
     def _run(self, fn: Callable, item):
         if getattr(self._local, "stream", None) is None:
             torch.cuda.set_device(self.device)
             self._local.stream = torch.cuda.Stream(device=self.device)
+            with self._lock:
+                self._stream_ids.add(self._local.stream.cuda_stream)
         with torch.cuda.stream(self._local.stream):
             out = fn(item)
             self._local.stream.synchronize()  # the batch is complete (and its scratch reusable) when the call returns
@@ -48,6 +52,9 @@ class BatchPipeline:
 
     def close(self):
         self._pool.shutdown(wait=True)
+        from . import ops
+        ops.release_workspaces(self._stream_ids)   # the per-stream scratch (1-2 GB each at ImageNet shape)
+        self._stream_ids = set()
 
     def __enter__(self):
         return self
