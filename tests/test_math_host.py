@@ -33,6 +33,8 @@ def shim():
     lib.tclip_host_digamma.argtypes = [ctypes.c_double]
     lib.tclip_host_digamma.restype = ctypes.c_double
     lib.tclip_host_mm_rows.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.tclip_host_mm_rows_anchored.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.tclip_host_mm_rows_anchored.restype = ctypes.c_int
     return lib
 
 
@@ -148,3 +150,23 @@ def test_mm_rows_track_the_oracle(shim):
     ref, done = R.mm_update_alpha(torch.ones(rows, D, dtype=torch.float64), y.double(), iters, check_every=0 or 10 ** 9)
     assert done == iters
     assert np.max(np.abs(a - ref.numpy()) / ref.numpy()) < 2e-5
+
+
+def test_mm_rows_with_anchored_psi_track_the_stateless_form(shim):
+    """1000 MM iterations with psi(s) from the anchored expansion vs the float64 evaluation every iteration: same alpha to
+    float32 round-off (no drift), on converging rows and on a diverging singleton-cluster row, with few re-anchorings."""
+    g = torch.Generator().manual_seed(4)
+    rows, D, iters = 5, 200, 1000
+    z = torch.softmax(3 * torch.randn(rows, 7, D, generator=g), -1)
+    y = torch.log(z + 1e-15).mean(1)
+    y[0] = torch.log(z[0, 0] + 1e-15)          # a single sample: the Dirichlet MLE diverges, alpha keeps growing
+    y = y.contiguous().numpy()
+    a_full = np.ones((rows, D), dtype=np.float32)
+    a_anch = np.ones((rows, D), dtype=np.float32)
+    shim.tclip_host_mm_rows(a_full, y, rows, D, D, iters)
+    n_full = shim.tclip_host_mm_rows_anchored(a_anch, y, rows, D, D, iters)
+    rel = np.abs(a_anch - a_full) / a_full
+    assert rel[1:].max() < 5e-6, rel[1:].max()
+    assert rel[0].max() < 2e-4, rel[0].max()                    # the diverging row amplifies every rounding difference
+    assert np.isfinite(a_anch).all() and a_anch[0].sum() > 20 * a_anch[1].sum()
+    assert n_full < rows * iters // 4, n_full

@@ -76,4 +76,28 @@ void tclip_host_mm_rows(float* alpha, const float* y, int rows, int D, int n_val
     }
   }
 }
+// the same with psi(s) from the anchored expansion (what mm_spec_kernel and the dense kernel's non-free-running rows do);
+// returns the number of full evaluations (re-anchorings) over all rows
+int tclip_host_mm_rows_anchored(float* alpha, const float* y, int rows, int D, int n_valid, int iters) {
+  int full = 0;
+  for (int r = 0; r < rows; ++r) {
+    float* a = alpha + (long)r * D;
+    const float* yy = y + (long)r * D;
+    tclip::PsiAnchor an;
+    tclip::psi_anchor_reset(an);
+    for (int it = 0; it < iters; ++it) {
+      double s = 0.0;
+      for (int d = 0; d < n_valid; ++d) s += (double)a[d];
+      const double before = an.s;
+      const tclip::RowPsi rp = tclip::row_psi_anchored(s, an);
+      if (an.s != before) ++full;
+      for (int d = 0; d + 1 < D; d += 2) {
+        tclip::float2 r2 = tclip::mm_update_pair(tclip::make_float2(a[d], a[d + 1]), tclip::make_float2(-yy[d], -yy[d + 1]), rp);
+        a[d] = r2.x;
+        a[d + 1] = r2.y;
+      }
+    }
+  }
+  return full;
+}
 }
