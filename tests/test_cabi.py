@@ -89,3 +89,18 @@ def test_no_device_is_an_error_not_a_fallback():
     assert lib.tclip_device_check(0) == -3
     with pytest.raises(_lib.TclipError):
         _lib.check(lib.tclip_device_check(0))
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/tclip_b200.h is the drop-in boundary: it must compile as C (no C++ types, no torch types) and link against
+    the library from a C translation unit."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "tclip_b200.h"\n#include <stddef.h>\n'
+                   'int main(void) { tclip_dirichlet_problem p; (void)p;\n'
+                   '  return (tclip_version() >= 100 && tclip_dirichlet_em_workspace_bytes(NULL) == 0) ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                    _lib.LIB_PATH, "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
