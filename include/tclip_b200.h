@@ -33,10 +33,11 @@ extern "C" {
 #define TCLIP_MM_SKIP_DEAD 1  /* iterate empty-cluster rows once, replay their cached criterion terms afterwards */
 
 /* ---- library / device --------------------------------------------------------------------------------------- */
-int tclip_version(void);                 /* 100 * major + minor; 101 = 1.1 (1.0 + contraction, match_clusters, gather_tasks, mm_crit) */
+int tclip_version(void);                 /* 100 * major + minor; 102 = 1.2 (1.1 + spec_probe, spec_rows_cap, kmeans_run) */
 const char* tclip_last_error(void);      /* message of the last failing call on this thread ("" if none) */
 int tclip_device_check(int device);      /* TCLIP_OK iff `device` is compute capability 10.x (B200) */
 int tclip_mm_max_dim(void);              /* largest D the M-step kernel supports (1024) */
+int tclip_spec_rows_cap(void);           /* rows the few-rows M-step kernel of the skip-dead schedule handles (1480) */
 long long tclip_launch_count(void);      /* kernels launched by this library in this process so far */
 
 /* Roofline denominators for the M-step (it is FP32/MUFU issue bound, not HBM or tensor bound): launches a
@@ -159,6 +160,35 @@ int tclip_kmeans_assign(const float* x, const float* w, const float* v, float te
 int tclip_kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long long per_task,
                        void* stream);
 
+/* ---- fused driver of the k-means family: the whole run_method loop of soft k-means (soft_kmeans.py:168-220), EM-Gaussian
+ * with identity covariance (em_gaussian.py:171-229) or hard k-means (hard_kmeans.py:153-211), up to but excluding the
+ * accuracy, enqueued on one stream without host synchronisation.  When min(n_query, dim) <= 96 the loop runs in the
+ * coordinates of the task's own samples (Cholesky factor of the n x n Gram matrix; every centroid is a combination of the
+ * task's samples and only distances to those samples are ever needed): same direct-difference distances as the reference,
+ * in <= n dimensions instead of D, and w itself is never formed inside the loop — `coef` receives its coefficients and
+ * tclip_kmeans_expand_centroids (or a non-NULL `w`) turns them into w [T,K,D].  Otherwise the feature-space kernels run
+ * (tclip_kmeans_centroids / tclip_kmeans_assign) and `w` holds the centroids (`coef` is not written). */
+typedef struct tclip_kmeans_problem {
+  int n_task, n_query, n_class, dim; /* T, n, K, D */
+  int iters;                         /* args.iter */
+  int method;                        /* TCLIP_KMEANS_SOFT / TCLIP_KMEANS_GAUSS / TCLIP_KMEANS_HARD */
+  float temperature;                 /* args.T */
+  float lambd;                       /* EM-Gaussian: int(K/5) * n_query (em_gaussian.py:20); ignored otherwise */
+  const float* x;                    /* [T,n,D] query features */
+  float* u;                          /* in: initial assignment [T,n,K] (soft_kmeans.py:185-197), out: final u */
+  float* v;                          /* out [T,K] (EM-Gaussian), may be NULL otherwise */
+  int* labels;                       /* out [T,n] arg-max_k u (hard k-means: the arg-min cluster) */
+  float* coef;                       /* out [T,n,K]: w[t,k,:] = sum_i coef[t,i,k] x[t,i,:] (sample-coordinate form) */
+  float* w;                          /* optional out [T,K,D] */
+  float* criterions;                 /* out [iters] (identically 0 upstream), hard k-means [2*iters] */
+  void* const* iter_events;          /* optional [iters+1] cudaEvent_t: before the first and after every iteration */
+} tclip_kmeans_problem;
+int tclip_kmeans_sample_coordinates(int n_query, int dim);   /* 1 iff tclip_kmeans_run takes the sample-coordinate form */
+size_t tclip_kmeans_workspace_bytes(const tclip_kmeans_problem* p);
+int tclip_kmeans_run(const tclip_kmeans_problem* p, void* workspace, size_t workspace_bytes, void* stream);
+/* w[t,k,:] = sum_i coef[t,i,k] x[t,i,:].  Replaces the [T,n,K,D] broadcast of w_update (soft_kmeans.py:161-166). */
+int tclip_kmeans_expand_centroids(const float* coef, const float* x, float* w, int T, int n, int K, int D, void* stream);
+
 /* Cluster -> class matching and the task accuracy.  probs [T, proto_rows, K] float32: row c of task t = class
  * probabilities of cluster c (clusters in order of first appearance, as tclip_cluster_prototypes delivers them);
  * n_clusters [T], sample_cluster [T,n] int32.  graph_matching != 0: minimum-cost assignment of the clusters to distinct
@@ -213,6 +243,11 @@ typedef struct tclip_dirichlet_problem {
   void* const* mm_events;            /* optional [2*iters] cudaEvent_t recorded before / after each M-step */
   double* mm_crit;                   /* optional out [iters][2]: (||a_new - a||^2, ||a||^2) over the whole batch at the last
                                         check point each M-step evaluated (the two norms of em_dirichlet.py:170-171) */
+  int* spec_probe;                   /* optional out [iters][tclip_spec_rows_cap()][4] (measurement only; skip-dead schedule):
+                                        per live row of the few-rows M-step kernel {MM iterations executed, iteration at
+                                        which the row reached a bit-exact fixed point or -1, iteration at which a longer
+                                        cycle was first seen or -1, its period}.  Non-NULL selects the statistics build of
+                                        that kernel (same arithmetic and results, ~10 % slower). */
 } tclip_dirichlet_problem;
 
 /* Runs zero_shot/em_dirichlet.py:195-244 (hard: zero_shot/hard_em_dirichlet.py:215-269) or, with n_support > 0,

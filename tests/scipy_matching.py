@@ -1,4 +1,5 @@
-"""Cluster -> class label matching, host form (the checker of ``ops.match_clusters``; the method classes use the device kernel).
+"""Cluster -> class label matching, host form: TEST INFRASTRUCTURE, the checker of ``ops.match_clusters`` (the method classes use the
+device kernel; this file is not part of the product package).
 
 Mirrors ``compute_graph_matching`` / ``compute_basic_matching`` of the reference (``src/utils.py:380-417``): per task,
 clusters are taken in order of first appearance among the predictions, the cost row of cluster c is

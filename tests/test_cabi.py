@@ -40,9 +40,10 @@ def test_header_cites_the_reference():
         assert cite in src
 
 
-def test_struct_layout_matches_header():
+@pytest.mark.parametrize("struct,mirror", [("tclip_dirichlet_problem", "DirichletProblem"), ("tclip_kmeans_problem", "KMeansProblem")])
+def test_struct_layout_matches_header(struct, mirror):
     src = open(HEADER).read()
-    body = src[src.index("typedef struct tclip_dirichlet_problem"):src.index("} tclip_dirichlet_problem;")]
+    body = src[src.index("typedef struct " + struct):src.index("} " + struct + ";")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
     for decl in body.split("{", 1)[1].split(";"):
@@ -53,12 +54,12 @@ def test_struct_layout_matches_header():
         first = names[0].split()[-1].lstrip("*")
         fields.append(first)
         fields += [n.strip().lstrip("*") for n in names[1:]]
-    assert fields == [f[0] for f in _lib.DirichletProblem._fields_]
+    assert fields == [f[0] for f in getattr(_lib, mirror)._fields_]
 
 
 def test_plain_calls_without_gpu():
     lib = _lib.load()
-    assert lib.tclip_version() == 101
+    assert lib.tclip_version() == 102
     assert lib.tclip_mm_max_dim() == 1024
     assert lib.tclip_launch_count() >= 0
     assert lib.tclip_dirichlet_mm_workspace_bytes(75000) > 0

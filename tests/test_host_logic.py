@@ -14,7 +14,8 @@ import torch
 
 from oracle import restated as R
 from oracle.ref_loader import make_args
-from tclip_b200 import matching, tasks
+import scipy_matching as matching
+from tclip_b200 import tasks
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

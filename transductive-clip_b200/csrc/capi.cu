@@ -182,7 +182,7 @@ __global__ void fill_kernel(float* p, float v, long n) {
   if (i + 3 < n && (reinterpret_cast<unsigned long long>(p) & 15ull) == 0) {
     *reinterpret_cast<float4*>(p + i) = make_float4(v, v, v, v);
   } else {
-    for (long j = i; j < n; ++j) p[j] = v;
+    for (long j = i; j < n && j < i + 4; ++j) p[j] = v;  // this thread's four elements only (tail / unaligned buffer)
   }
 }
 __global__ void zero_int_kernel(int* p, long n) {
@@ -362,8 +362,8 @@ __global__ void __launch_bounds__(256) count_live_kernel(const int* __restrict__
 }
 
 __global__ void record_work_kernel(const tclip::MMState* state, const int* counts, const unsigned long long* work_ctr,
-                                   const int* n_live_dev, int rows, int iter_mm, int* mm_iters, int* n_live,
-                                   long long* mm_rows, double* mm_crit) {
+                                   const int* split_gate, const int* n_live_dev, int rows, int iter_mm, int* mm_iters,
+                                   int* n_live, long long* mm_rows, double* mm_crit) {
   const int done = state->iters_done;
   if (mm_crit) {
     mm_crit[0] = state->last_num;
@@ -372,7 +372,10 @@ __global__ void record_work_kernel(const tclip::MMState* state, const int* count
   *mm_iters = done;
   *n_live = n_live_dev ? *n_live_dev : rows;
   if (mm_rows) {
-    if (counts) *mm_rows = (long long)counts[0] * done + (long long)*work_ctr;  // live rows + free-running dead rows
+    // row-iterations really executed: the free-running dead rows and the speculated live rows count their own (a
+    // speculated row runs all iter_mm iterations whatever check fires), the chunked live rows run `done` iterations each
+    const bool spec = split_gate && split_gate[0] <= split_gate[1];
+    if (counts) *mm_rows = (spec ? 0ll : (long long)counts[0] * done) + (long long)*work_ctr;
     else *mm_rows = (long long)rows * done;
   }
 }
@@ -382,11 +385,13 @@ __global__ void record_work_kernel(const tclip::MMState* state, const int* count
 // ======================================================================================================================
 extern "C" {
 
-int tclip_version(void) { return 101; }  // 1.1: + contraction, match_clusters, gather_tasks[_remap], problem.mm_crit
+int tclip_version(void) { return 102; }  // 1.2: + problem.spec_probe, tclip_spec_rows_cap, tclip_kmeans_run
 
 const char* tclip_last_error(void) { return g_last_error.c_str(); }
 
 int tclip_mm_max_dim(void) { return tclip::mm_max_dim(); }
+
+int tclip_spec_rows_cap(void) { return kSplitCap; }
 
 long long tclip_launch_count(void) { return tclip::g_launches.load(std::memory_order_relaxed); }
 
@@ -552,8 +557,9 @@ int tclip_match_clusters(const float* probs, const int* n_clusters, const int* s
 
 int tclip_gather_tasks(const float* features, const long long* labels, const long long* idx, float* x_q, long long* y_q,
                        long long n_rows, long long count, int F, int* bad, void* stream) {
-  if (!features || !idx || !x_q || n_rows < 1 || count < 1 || F < 1 || (y_q && !labels))
+  if (!features || !idx || !x_q || n_rows < 1 || count < 0 || F < 1 || (y_q && !labels))
     return fail(TCLIP_ERR_INVALID, "tclip_gather_tasks: bad arguments");
+  if (count == 0) return TCLIP_OK;  // nothing to gather
   if (int rc = current_device_ok()) return rc;
   TCLIP_CUDA(tclip::gather_tasks(features, labels, idx, x_q, y_q, n_rows, count, F, bad, (cudaStream_t)stream));
   return TCLIP_OK;
@@ -562,9 +568,10 @@ int tclip_gather_tasks(const float* features, const long long* labels, const lon
 int tclip_gather_tasks_remap(const float* features, const long long* labels, const long long* idx, const long long* col_perm,
                              const long long* label_map, float* x_out, long long* y_out, long long n_rows, long long count,
                              int per_task, int F, int U, int n_labels, int* bad, void* stream) {
-  if (!features || !labels || !idx || !col_perm || !label_map || !x_out || n_rows < 1 || count < 1 || per_task < 1 ||
+  if (!features || !labels || !idx || !col_perm || !label_map || !x_out || n_rows < 1 || count < 0 || per_task < 1 ||
       F < 1 || U < 1 || n_labels < 1 || count % per_task != 0)
     return fail(TCLIP_ERR_INVALID, "tclip_gather_tasks_remap: bad arguments");
+  if (count == 0) return TCLIP_OK;
   if (int rc = current_device_ok()) return rc;
   TCLIP_CUDA(tclip::gather_tasks_remap(features, labels, idx, col_perm, label_map, x_out, y_out, n_rows, count, per_task,
                                        F, U, n_labels, bad, (cudaStream_t)stream));
@@ -580,7 +587,8 @@ int tclip_normalize_rows(const float* x, float* out, long long rows, int D, void
 
 int tclip_kmeans_similarity(const float* a, const float* text, float scale, float* u, long long M, int K, int D,
                             void* stream) {
-  if (!a || !text || !u || M < 1 || K < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_kmeans_similarity: bad arguments");
+  if (!a || !text || !u || M < 0 || K < 1 || D < 1) return fail(TCLIP_ERR_INVALID, "tclip_kmeans_similarity: bad arguments");
+  if (M == 0) return TCLIP_OK;
   if (int rc = current_device_ok()) return rc;
   TCLIP_CUDA(tclip::kmeans_similarity(a, text, scale, u, (long)M, K, D, (cudaStream_t)stream));
   return TCLIP_OK;
@@ -640,6 +648,53 @@ int tclip_kmeans_udiff(const float* a, const float* b, float* task_norm, float* 
     return fail(TCLIP_ERR_INVALID, "tclip_kmeans_udiff: bad arguments");
   if (int rc = current_device_ok()) return rc;
   TCLIP_CUDA(tclip::kmeans_udiff(a, b, task_norm, mean_out, T, (long)per_task, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+namespace {
+int kmeans_validate(const tclip_kmeans_problem* p, tclip::KMeansRun* r) {
+  if (!p) return fail(TCLIP_ERR_INVALID, "problem is NULL");
+  if (p->n_task < 1 || p->n_query < 1 || p->n_class < 1 || p->dim < 1 || p->iters < 0)
+    return fail(TCLIP_ERR_INVALID, "n_task/n_query/n_class/dim must be >= 1 and iters >= 0");
+  if (p->method < 0 || p->method > 2) return fail(TCLIP_ERR_INVALID, "method must be TCLIP_KMEANS_SOFT / GAUSS / HARD");
+  r->T = p->n_task; r->n = p->n_query; r->K = p->n_class; r->D = p->dim;
+  r->iters = p->iters; r->method = p->method; r->temperature = p->temperature; r->lambd = p->lambd;
+  r->x = p->x; r->u = p->u; r->v = p->v; r->labels = p->labels; r->coef = p->coef; r->w = p->w;
+  r->criterions = p->criterions; r->iter_events = p->iter_events;
+  return TCLIP_OK;
+}
+}  // namespace
+
+int tclip_kmeans_sample_coordinates(int n_query, int dim) { return tclip::kmeans_sample_coordinates(n_query, dim) ? 1 : 0; }
+
+size_t tclip_kmeans_workspace_bytes(const tclip_kmeans_problem* p) {
+  tclip::KMeansRun r{};
+  if (kmeans_validate(p, &r) != TCLIP_OK) return 0;
+  return tclip::kmeans_run_workspace_bytes(r) + 256;
+}
+
+int tclip_kmeans_run(const tclip_kmeans_problem* p, void* workspace, size_t workspace_bytes, void* stream) {
+  tclip::KMeansRun r{};
+  if (int rc = kmeans_validate(p, &r)) return rc;
+  const bool coords = tclip::kmeans_sample_coordinates(r.n, r.D);
+  if (!p->x || !p->u || !p->labels || !p->criterions || (p->method == 1 && !p->v) || (coords && !p->coef) ||
+      (!coords && !p->w && false))
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_run: x/u/labels/criterions (+ v for EM-Gaussian, coef in sample coordinates) must be set");
+  const size_t need = tclip::kmeans_run_workspace_bytes(r);
+  if (!workspace || workspace_bytes < need)
+    return fail(TCLIP_ERR_WORKSPACE, "tclip_kmeans_run: workspace too small (%zu < %zu)", workspace_bytes, need);
+  if ((reinterpret_cast<unsigned long long>(workspace) & 255ull) != 0)
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_run: workspace must be 256-byte aligned");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_run(r, workspace, (cudaStream_t)stream));
+  return TCLIP_OK;
+}
+
+int tclip_kmeans_expand_centroids(const float* coef, const float* x, float* w, int T, int n, int K, int D, void* stream) {
+  if (!coef || !x || !w || T < 1 || n < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_kmeans_expand_centroids: bad arguments");
+  if (int rc = current_device_ok()) return rc;
+  TCLIP_CUDA(tclip::kmeans_expand_centroids(coef, x, w, T, n, K, D, (cudaStream_t)stream));
   return TCLIP_OK;
 }
 
@@ -745,6 +800,8 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       l.split_cap = kSplitCap;
       l.spec_terms = w.spec_terms;
       l.spec_snap = w.spec_snap;
+      l.work_ctr = w.work_ctr;
+      l.spec_probe = p->spec_probe ? reinterpret_cast<int4*>(p->spec_probe) + (size_t)it * kSplitCap : nullptr;
       l.n_rows = rows;
       l.n_blocks = tclip::mm_num_blocks(rows, true);
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nc > 0 ? w.extra : nullptr, st));
@@ -759,7 +816,8 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       tclip::note_launch();
       n_live_dev = p->n_live + it;
     }
-    record_work_kernel<<<1, 1, 0, st>>>(w.state, skip ? w.counts : nullptr, w.work_ctr, n_live_dev, rows, p->iter_mm,
+    record_work_kernel<<<1, 1, 0, st>>>(w.state, skip ? w.counts : nullptr, w.work_ctr, skip ? w.split_gate : nullptr,
+                                         n_live_dev, rows, p->iter_mm,
                                          p->mm_iters + it, p->n_live + it, p->mm_rows ? p->mm_rows + it : nullptr,
                                          p->mm_crit ? p->mm_crit + 2 * it : nullptr);
     tclip::note_launch();

@@ -137,7 +137,7 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)
 template <bool kExternalAcc>
 __global__ void __launch_bounds__(kThreads, 1)
 logits_tc_kernel(const __grid_constant__ CUtensorMap map_logz, const __grid_constant__ CUtensorMap map_alpha,
-                 float* __restrict__ l3, int n, int K, int D, const int* __restrict__ gate) {
+                 float* __restrict__ l3, int n, int K, int D, const int* __restrict__ gate, float b_shift, int b_shared) {
   if (gate != nullptr && !(gate[0] > gate[1])) return;  // the row-wise kernels take this E-step (skip-dead schedule)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -148,7 +148,9 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_logz, const __grid_cons
   uint8_t* const gen_base = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to the same place
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.y, k0 = blockIdx.x * kTileN;
+  // grid: (class tiles, row tiles of the A operand, tasks); b_shared: one B matrix for all tasks (task coordinate 0)
+  const int t = blockIdx.z, m0 = blockIdx.y * kTileM, k0 = blockIdx.x * kTileN;
+  const int tb = b_shared ? 0 : t;
   const int n_kb = (D + kBlockK - 1) / kBlockK;
 
   if (threadIdx.x == 0) {
@@ -182,8 +184,8 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_logz, const __grid_cons
         mbar_wait(empty0 + 8 * s, (use & 1) ^ 1);
         const uint32_t st = base + s * kStageBytes;
         mbar_arrive_expect_tx(full0 + 8 * s, 2 * kTileBytes);
-        tma_load_3d(st, &map_logz, kb * kBlockK, 0, t, full0 + 8 * s);
-        tma_load_3d(st + 2 * kTileBytes, &map_alpha, kb * kBlockK, k0, t, full0 + 8 * s);
+        tma_load_3d(st, &map_logz, kb * kBlockK, m0, t, full0 + 8 * s);
+        tma_load_3d(st + 2 * kTileBytes, &map_alpha, kb * kBlockK, k0, tb, full0 + 8 * s);
       }
     }
   } else if (warp == 1) {
@@ -236,7 +238,7 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_logz, const __grid_cons
 #pragma unroll 4
       for (int i = tid; i < kTileBytes / 16; i += kSplitThreads) {
         float4 x = b_hi[i];
-        x.x -= 1.0f; x.y -= 1.0f; x.z -= 1.0f; x.w -= 1.0f;   // alpha - 1 in fp32, as the reference forms it
+        x.x -= b_shift; x.y -= b_shift; x.z -= b_shift; x.w -= b_shift;   // alpha - 1 in fp32, as the reference forms it (shift 0: plain product)
         float4 h, l;
         h.x = rn_tf32(x.x); h.y = rn_tf32(x.y); h.z = rn_tf32(x.z); h.w = rn_tf32(x.w);
         l.x = rn_tf32(x.x - h.x); l.y = rn_tf32(x.y - h.y); l.z = rn_tf32(x.z - h.z); l.w = rn_tf32(x.w - h.w);
@@ -249,7 +251,7 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_logz, const __grid_cons
   } else {
     // ===== accumulate warps: drain every D-block's partial product, sum in round-to-nearest fp32, store =====
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;                // query index inside the tile
+    const int row = m0 + q * 32 + lane;           // row of the A operand (query index)
     float acc[kTileN];
 #pragma unroll
     for (int j = 0; j < kTileN; ++j) acc[j] = 0.0f;
@@ -327,27 +329,40 @@ bool logits_tc_supported(int n, int K, int D) {
   return n >= 1 && n <= kTileM && K >= 1 && D >= 4 && (D % 4) == 0;
 }
 
-cudaError_t logits_tc(const float* logz, const float* alpha, float* l3, int T, int n, int K, int D, const int* gate,
-                      bool accumulate_in_tmem, cudaStream_t st) {
-  if (!logits_tc_supported(n, K, D)) return cudaErrorInvalidValue;
-  if ((reinterpret_cast<uintptr_t>(logz) | reinterpret_cast<uintptr_t>(alpha)) & 15) return cudaErrorMisalignedAddress;
-  static bool attr_set = false;
-  if (!attr_set) {
+// C[t, m, k] = sum_d A[t, m, d] * (B[tb, k, d] - b_shift), tb = t or 0 (b_tasks == 1): 3 x TF32 on tcgen05, fp32
+// round-to-nearest running sum outside the tensor core.  A [T, M, D], B [b_tasks, N, D], C [T, M, N].
+cudaError_t gemm_nt_tc(const float* a, const float* b, float* c, int T, int M, int N, int D, int b_tasks, float b_shift,
+                       const int* gate, bool accumulate_in_tmem, cudaStream_t st) {
+  if (M < 1 || N < 1 || D < 4 || (D % 4) != 0 || (b_tasks != 1 && b_tasks != T)) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) return cudaErrorMisalignedAddress;
+  // cudaFuncSetAttribute is per device: opt in once per device of this process (idempotent, so a race between two host
+  // threads only repeats the call)
+  static PerDeviceFlags attr_set;
+  const int slot = current_device_slot();
+  if (slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0) {
     cudaError_t e = cudaFuncSetAttribute(logits_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(logits_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
   }
   CUtensorMap ma, mb;
-  if (!make_map(&ma, logz, T, n, D) || !make_map(&mb, alpha, T, K, D)) return cudaErrorInvalidValue;
-  dim3 grid((K + kTileN - 1) / kTileN, T);
+  if (!make_map(&ma, a, T, M, D) || !make_map(&mb, b, b_tasks, N, D)) return cudaErrorInvalidValue;
+  const int m_tiles = (M + kTileM - 1) / kTileM;
+  if (m_tiles > 65535 || T > 65535) return cudaErrorInvalidValue;
+  dim3 grid((N + kTileN - 1) / kTileN, m_tiles, T);
   if (accumulate_in_tmem)
-    logits_tc_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, l3, n, K, D, gate);
+    logits_tc_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, c, M, N, D, gate, b_shift, b_tasks == 1 && T > 1);
   else
-    logits_tc_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, l3, n, K, D, gate);
+    logits_tc_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, c, M, N, D, gate, b_shift, b_tasks == 1 && T > 1);
   note_launch();
   return cudaGetLastError();
+}
+
+cudaError_t logits_tc(const float* logz, const float* alpha, float* l3, int T, int n, int K, int D, const int* gate,
+                      bool accumulate_in_tmem, cudaStream_t st) {
+  if (!logits_tc_supported(n, K, D)) return cudaErrorInvalidValue;
+  return gemm_nt_tc(logz, alpha, l3, T, n, K, D, T, 1.0f, gate, accumulate_in_tmem, st);
 }
 
 }  // namespace tclip

@@ -442,14 +442,26 @@ struct SpecArgs {
   const double2* extra; // optional [n_checks]
   float tol;
   MMState* state;       // iters_done out; `fired` check index in state->done_check
+  unsigned long long* work_ctr;  // optional: += row-iterations executed
+  int4* probe;          // optional [cap]: {iterations executed, iteration of the fixed point or -1, iteration at which a
+                        // longer cycle was first detected or -1, its period} (measurement builds of the kernel only)
 };
 
-template <int W, int NPW, bool PIPE>
+// PROBE = true is the statistics build (tclip_dirichlet_problem.spec_probe): same arithmetic and results, plus per row the
+// iteration at which an update first returned every element bit for bit (an exact fixed point: the update is a
+// deterministic function of the row state, so every later update would be the identity) and Brent's cycle search on the
+// row state.  Measured on the bench workload (profiles/r2_spec_fixed_points.md): no live row ever reaches a fixed point;
+// the singleton clusters (2 of 3 live rows) diverge and are never periodic, the large clusters dither in cycles of
+// 60..480 iterations (elements oscillate by an ulp with periods 2..8, the row period is their least common multiple).
+// So, unlike the empty clusters (mm_chunk_kernel<FR>), live rows offer no exact early stop worth its cost: carrying the
+// per-iteration vote in the product kernel made it 14 % slower, and it is therefore compiled into this build only.
+template <int W, int NPW, bool PIPE, bool PROBE>
 __global__ void __launch_bounds__(32 * W)
 mm_spec_kernel(const SpecArgs g) {
   if (!(g.split_gate[0] <= g.split_gate[1])) return;
   if ((int)blockIdx.x >= *g.n_rows_dev) return;  // CTA-uniform
   __shared__ double part[2][W];
+  __shared__ int flag[2][W];
   __shared__ double2 wred[W];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -475,7 +487,8 @@ mm_spec_kernel(const SpecArgs g) {
   // the reciprocals) is issued together with the row-total shuffles, so it runs in the shadow of the reduction, the CTA
   // barrier and psi(s); what remains on the serial path after psi(s) is mm_update_post (~15 dependent operations).
   PairPre pre[NPW];
-  auto row_total = [&](int parity) -> double {
+  int all_flags = 0;  // OR over the warps of the flags handed to the last row_total call
+  auto row_total = [&](int parity, int my_flags) -> double {
     float2 t = f2mul(a[0], mask[0]);
 #pragma unroll
     for (int j = 1; j < NPW; ++j) t = f2fma(a[j], mask[j], t);
@@ -485,10 +498,20 @@ mm_spec_kernel(const SpecArgs g) {
     }
     const double ws = warp_sum_f64((double)(t.x + t.y));
     if (lane == 0) part[parity][warp] = ws;
+    if constexpr (PROBE) {
+      const int wf = __reduce_or_sync(0xffffffffu, my_flags);
+      if (lane == 0) flag[parity][warp] = wf;
+    }
     __syncthreads();
     double pw[W];  // balanced tree: the total is on the serial path of every iteration
 #pragma unroll
     for (int w = 0; w < W; ++w) pw[w] = part[parity][w];
+    if constexpr (PROBE) {
+      int f = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) f |= flag[parity][w];
+      all_flags = f;
+    }
 #pragma unroll
     for (int st = 1; st < W; st <<= 1) {
 #pragma unroll
@@ -496,11 +519,15 @@ mm_spec_kernel(const SpecArgs g) {
     }
     return pw[0];
   };
-  double s = row_total(0);
+  double s = row_total(0, 0);
   int parity = 1;
   int next_check = g.check_every > 0 ? g.check_every : 0x7fffffff, c = 0;
   PsiAnchor anchor;  // psi(s) by expansion around an earlier row total: the float64 logarithm leaves the serial path
   psi_anchor_reset(anchor);
+  int executed = g.iter_mm, fixed_at = -1;
+  // measurement only: Brent's cycle search on the row state (reference state refreshed at powers of two)
+  float2 ref[PROBE ? NPW : 1];
+  int ref_iter = -1, cyc_at = -1, cyc_period = 0;
   for (int l = 0; l < g.iter_mm; ++l) {
     const RowPsi rp = row_psi_anchored(s, anchor);
     float2 an[NPW];
@@ -537,12 +564,39 @@ mm_spec_kernel(const SpecArgs g) {
       ++c;
       next_check += g.check_every;
     }
+    // bit 0: this update changed an element of the row (padding lanes iterate on a dummy and do not count);
+    // bit 1: the new state differs from the reference state of the cycle search
+    int my_flags = 0;
+    if constexpr (PROBE) {
+#pragma unroll
+      for (int j = 0; j < NPW; ++j) {
+        my_flags |= (int)((an[j].x != a[j].x) & (mask[j].x != 0.0f)) | (int)((an[j].y != a[j].y) & (mask[j].y != 0.0f));
+        if (ref_iter >= 0)
+          my_flags |= ((int)((an[j].x != ref[j].x) & (mask[j].x != 0.0f)) | (int)((an[j].y != ref[j].y) & (mask[j].y != 0.0f))) << 1;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < NPW; ++j) a[j] = an[j];
     if (l + 1 < g.iter_mm) {
-      s = row_total(parity);
+      s = row_total(parity, my_flags);
       parity ^= 1;
+      if constexpr (PROBE) {
+        if (cyc_at < 0 && ref_iter >= 0 && !(all_flags & 2) && (all_flags & 1)) {
+          cyc_at = l + 1;
+          cyc_period = l + 1 - ref_iter;
+        }
+        if (fixed_at < 0 && !(all_flags & 1)) fixed_at = l + 1;
+        if (cyc_at < 0 && l + 1 >= 8 && ((l + 1) & l) == 0) {  // state after l + 1 updates becomes the reference
+#pragma unroll
+          for (int j = 0; j < NPW; ++j) ref[j] = a[j];
+          ref_iter = l + 1;
+        }
+      }
     }
+  }
+  if (threadIdx.x == 0) {
+    if (g.work_ctr) atomicAdd(g.work_ctr, (unsigned long long)executed);
+    if (PROBE && g.probe) g.probe[blockIdx.x] = make_int4(executed, fixed_at, cyc_at, cyc_period);
   }
 #pragma unroll
   for (int j = 0; j < NPW; ++j) {
@@ -637,7 +691,8 @@ void launch_chunk(const ChunkArgs& g, int n_blocks, cudaStream_t st) {
 
 template <int W, int NPW, bool PIPE = true>
 void launch_spec(const SpecArgs& g, cudaStream_t st) {
-  mm_spec_kernel<W, NPW, PIPE><<<g.cap, 32 * W, 0, st>>>(g);
+  if (g.probe) mm_spec_kernel<W, NPW, PIPE, true><<<g.cap, 32 * W, 0, st>>>(g);
+  else mm_spec_kernel<W, NPW, PIPE, false><<<g.cap, 32 * W, 0, st>>>(g);
 }
 
 using SpecFn = void (*)(const SpecArgs&, cudaStream_t);
@@ -665,17 +720,20 @@ SpecFn spec_fn(int np) {
   }
 }
 
+// SM count of the CURRENT device (cached per device index; a failed query is not cached)
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      n = v;
-    else
-      return 148;  // B200; do not cache a failure
+  static PerDeviceFlags cache;
+  const int slot = current_device_slot();
+  if (slot >= 0) {
+    const int c = cache.v[slot].load(std::memory_order_relaxed);
+    if (c > 0) return c;
   }
-  return n;
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+    return 148;  // B200
+  if (slot >= 0) cache.v[slot].store(v, std::memory_order_relaxed);
+  return v;
 }
 
 }  // namespace
@@ -768,6 +826,8 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
     g.cap = p.split_cap;
     g.terms = p.spec_terms;
     g.snap = p.spec_snap;
+    g.work_ctr = p.work_ctr;
+    g.probe = p.spec_probe;
     g.extra = extra_checks;
     g.tol = tol;
     g.state = p.state;

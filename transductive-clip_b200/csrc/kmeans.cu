@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdint>
+
 #include "tclip_kernels.cuh"
 
 namespace tclip {
@@ -401,15 +403,24 @@ cudaError_t normalize_rows(const float* x, float* out, long rows, int D, cudaStr
   return cudaGetLastError();
 }
 
-// u[m,:] = softmax_k(scale * a[m,:] . text[k,:]) for M rows (all tasks flattened; text is shared)
+// u[m,:] = softmax_k(scale * a[m,:] . text[k,:]) for M rows (all tasks flattened; text is shared).  The product runs on the
+// tensor cores (3 x TF32 tcgen05 tiles with the fp32 round-to-nearest running sum of contraction_tc.cu) whenever TMA can
+// address the operands, else on the CUDA cores.
 cudaError_t kmeans_similarity(const float* a, const float* text, float scale, float* u, long M, int K, int D,
                               cudaStream_t st) {
   // batches of <= 64 * 65535 rows through blockIdx.y
   if (M > 64L * 65535) return cudaErrorInvalidValue;
-  pair_kernel<0><<<dim3((K + kTile - 1) / kTile, (unsigned)((M + kTile - 1) / kTile), 1), 256, 0, st>>>(
-      a, text, nullptr, u, (int)M, K, D, 0, 0, 0);
+  const bool tc = D >= 4 && (D % 4) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(text)) & 15) == 0;
+  if (tc) {
+    cudaError_t e = gemm_nt_tc(a, text, u, 1, (int)M, K, D, 1, 0.0f, nullptr, false, st);
+    if (e != cudaSuccess) return e;
+  } else {
+    pair_kernel<0><<<dim3((K + kTile - 1) / kTile, (unsigned)((M + kTile - 1) / kTile), 1), 256, 0, st>>>(
+        a, text, nullptr, u, (int)M, K, D, 0, 0, 0);
+    note_launch();
+  }
   assign_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(u, nullptr, nullptr, scale, 0.0f, u, nullptr, (int)M, 1, K, 3);
-  note_launch(2);
+  note_launch();
   return cudaGetLastError();
 }
 

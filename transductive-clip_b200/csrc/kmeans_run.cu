@@ -1,0 +1,437 @@
+// kmeans_run.cu — soft k-means / hard k-means / EM-Gaussian (identity covariance): the whole run_method loop enqueued on
+// one stream, in the coordinates of the task's own samples.
+//
+// Reference (SegoleneMartin/transductive-CLIP, src/methods/zero_shot/): soft_kmeans.py:105-125,135-220,
+// hard_kmeans.py:26-35,127-211, em_gaussian.py:106-136,138-229.  Per iteration the reference forms two [T,n,K,D]
+// broadcasts: the centroids w = u^T x / sum u (w_update) and the squared distances ||w_k - x_n||^2 (get_logits).
+//
+// B200-first formulation.  Every centroid the loop ever holds is a linear combination of the n query samples of its task
+// (w_init and every w_update are; an empty cluster keeps an earlier combination or is zeroed), and every quantity the loop
+// needs from w is a distance to one of those samples.  With G = X X^T = L L^T (n x n Gram matrix of the task, Cholesky
+// factor L), sample n is row n of L in an orthonormal basis of span{x}, a centroid is wt_k = sum_n c_kn L_n, and
+//     ||w_k - x_n||^2 = || wt_k - L_n ||^2
+// exactly: the same direct-difference form as the reference (no ||w||^2 + ||x||^2 - 2 x.w cancellation), in r = rank(X) <= n
+// dimensions instead of D.  At RN50 shape (n = 75, D = 1024, K = 1000) that is 13.6x fewer flops, and the state of a task
+// is [K, 80] + [n, 80] floats (0.34 MB) instead of w [K, D] (4 MB): the loop leaves HBM altogether (SURVEY.md §8(d) bounds
+// the w-space loop by 8 MB of HBM traffic per task and iteration).  The coefficients c ("coef", laid out like u) are kept
+// so that w = coef^T x can be produced when somebody asks for it (tclip_kmeans_expand_centroids).
+//
+// When D <= n the features are used as they are (Z = x, r = D); when min(n, D) > kMaxR the loop falls back to the
+// feature-space kernels of kmeans.cu.
+//
+// One outer iteration = kproj_iter_kernel (cluster sizes, centroids in sample coordinates with the reference's
+// empty-cluster rule, coefficients, squared distances) + assign_kernel (soft-max / arg-min rows, kmeans.cu)
+// [+ colsum_v for EM-Gaussian's v, + the logged criterion of hard k-means].
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "tclip_kernels.cuh"
+
+namespace tclip {
+
+namespace {
+
+constexpr float kEps = 1e-15f;
+constexpr int kKT = 128;      // classes per CTA of the iteration kernel
+constexpr int kMaxR = 96;     // largest coordinate count (and sample count) of the sample-coordinate form
+constexpr int kMaxPairs = (kMaxR * kMaxR + 255) / 256;
+
+// G[t] = X_t X_t^T in float64 (n <= kMaxR): one CTA per task, every thread owns <= kMaxPairs entries, D walked in slabs of
+// 32 columns staged through shared memory.
+__global__ void __launch_bounds__(256)
+gram_kernel(const float* __restrict__ x, double* __restrict__ G, int n, int D) {
+  __shared__ float xs[kMaxR][33];
+  const int t = blockIdx.x;
+  const float* xb = x + (long)t * n * D;
+  double acc[kMaxPairs];
+#pragma unroll
+  for (int q = 0; q < kMaxPairs; ++q) acc[q] = 0.0;
+  const int pairs = n * n;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    for (int i = threadIdx.x; i < n * 32; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      xs[r][c] = (d0 + c < D) ? xb[(long)r * D + d0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kMaxPairs; ++q) {
+      const int p = threadIdx.x + 256 * q;
+      if (p < pairs) {
+        const int i = p / n, j = p - i * n;
+        double s = acc[q];
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) s = fma((double)xs[i][c], (double)xs[j][c], s);
+        acc[q] = s;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxPairs; ++q) {
+    const int p = threadIdx.x + 256 * q;
+    if (p < pairs) G[(long)t * pairs + p] = acc[q];
+  }
+}
+
+// Z[t] = Cholesky factor of G[t] (lower triangular, float64 arithmetic, stored as float32 [n, zs], zero above the diagonal
+// and in the padding columns).  A pivot that is not above 1e-9 of its original diagonal entry marks a sample that is a
+// linear combination of earlier ones (G is positive SEMI-definite in general: duplicated samples): its column is zero,
+// which keeps L L^T = G to rounding accuracy.
+__global__ void __launch_bounds__(256)
+chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) {
+  extern __shared__ double A[];   // [n][n]
+  __shared__ double piv;
+  const int t = blockIdx.x;
+  for (int i = threadIdx.x; i < n * n; i += 256) A[i] = G[(long)t * n * n + i];
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (threadIdx.x == 0) {
+      const double p = A[j * n + j], orig = G[(long)t * n * n + j * n + j];
+      piv = (p > 1e-9 * orig && p > 0.0) ? sqrt(p) : 0.0;
+    }
+    __syncthreads();
+    const double d = piv;
+    for (int i = j + threadIdx.x; i < n; i += 256) A[i * n + j] = (d > 0.0) ? (i == j ? d : A[i * n + j] / d) : 0.0;
+    __syncthreads();
+    if (d > 0.0) {
+      const int m = n - j - 1;
+      for (int p = threadIdx.x; p < m * m; p += 256) {
+        const int i = j + 1 + p / m, k = j + 1 + p % m;
+        A[i * n + k] -= A[i * n + j] * A[k * n + j];
+      }
+    }
+    __syncthreads();
+  }
+  float* zb = Z + (long)t * n * zs;
+  for (int p = threadIdx.x; p < n * zs; p += 256) {
+    const int i = p / zs, j = p - i * zs;
+    zb[p] = (j <= i && j < n) ? (float)A[i * n + j] : 0.0f;
+  }
+}
+
+// One outer iteration's M-step and distances for a tile of kKT classes of one task, in sample coordinates.
+//   Z    [T, n, zs]   coordinates of the samples (Cholesky rows, or the features themselves), r used columns
+//   u    [T, n, K]    responsibilities the centroids are formed from
+//   coef [T, n, K]    out: u / max(colsum, eps) for the clusters whose centroid is (re)formed; kept / zeroed otherwise
+//   wt   [T, K, rq]   in/out: centroids in sample coordinates
+//   d2   [T, n, K]    out (when want_d2): || wt_k - Z_n ||^2
+// mode 0 (w_init, soft_kmeans.py:135-148): w = sum u x / max(sum u, eps) for every cluster, no mask;
+// mode 1 (w_update of soft k-means / EM-Gaussian, soft_kmeans.py:150-166): clusters with sum u <= eps keep their centroid;
+// mode 2 (hard k-means, hard_kmeans.py:138-151): those clusters are zeroed.
+// Thread tile: 8 classes x MJ coordinates (centroids), 8 classes x MN samples (distances); MJ = ceil(r / 16),
+// MN = ceil(n / 16); rq = 16 MJ.
+template <int MJ, int MN>
+__global__ void __launch_bounds__(256)
+kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__ u, float* __restrict__ coef,
+                  float* __restrict__ wt, float* __restrict__ d2, int n, int K, int r, int mode, int want_d2) {
+  constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
+  extern __shared__ float sm[];
+  float* Zs = sm;                    // [NQ][ZP]  (rows >= n and columns >= r are zero)
+  float* us = Zs + NQ * ZP;          // [NQ][kKT] u tile, later the d2 tile
+  float* wts = us + NQ * kKT;        // [kKT][ZP]
+  float* cs = wts + kKT * ZP;        // [kKT] cluster sizes
+  const int t = blockIdx.y, k0 = blockIdx.x * kKT;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* zb = Z + (long)t * n * zs;
+  const float* ub = u + (long)t * n * K;
+  for (int i = tid; i < NQ * RQ; i += 256) {
+    const int row = i / RQ, c = i - row * RQ;
+    Zs[row * ZP + c] = (row < n && c < r) ? zb[(long)row * zs + c] : 0.0f;
+  }
+  for (int i = tid; i < NQ * kKT; i += 256) {
+    const int row = i / kKT, c = i - row * kKT;
+    us[i] = (row < n && k0 + c < K) ? ub[(long)row * K + k0 + c] : 0.0f;
+  }
+  __syncthreads();
+  if (tid < kKT) {   // cluster sizes in sample order, like u.sum(1)
+    float s = 0.0f;
+    for (int i = 0; i < n; ++i) s += us[i * kKT + tid];
+    cs[tid] = s;
+  }
+  __syncthreads();
+  // centroids of this tile: wt[k, j] = sum_n u[n, k] Z[n, j] / max(cs, eps)
+  {
+    float acc[8][MJ];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int m = 0; m < MJ; ++m) acc[i][m] = 0.0f;
+    for (int nn = 0; nn < n; ++nn) {
+      const float4 u0 = *reinterpret_cast<const float4*>(us + nn * kKT + ty * 8);
+      const float4 u1 = *reinterpret_cast<const float4*>(us + nn * kKT + ty * 8 + 4);
+      const float uv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      float zv[MJ];
+#pragma unroll
+      for (int m = 0; m < MJ; ++m) zv[m] = Zs[nn * ZP + tx + 16 * m];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int m = 0; m < MJ; ++m) acc[i][m] = fmaf(uv[i], zv[m], acc[i][m]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kk = ty * 8 + i, k = k0 + kk;
+      const float c = cs[kk];
+      const bool form = (mode == 0) || (c > kEps);
+      float* wrow = wt + ((long)t * K + k) * RQ;
+#pragma unroll
+      for (int m = 0; m < MJ; ++m) {
+        const int j = tx + 16 * m;
+        float val = 0.0f;
+        if (k < K) {
+          if (form) val = acc[i][m] / fmaxf(c, kEps);
+          else if (mode == 1) val = wrow[j];      // empty cluster keeps its centroid
+          if (form || mode == 2) wrow[j] = val;   // (mode 2: zeroed)
+        }
+        wts[kk * ZP + j] = val;
+      }
+    }
+  }
+  // coefficients of the centroids in terms of the samples (what tclip_kmeans_expand_centroids turns into w)
+  {
+    float* cb = coef + (long)t * n * K;
+    for (int i = tid; i < n * kKT; i += 256) {
+      const int row = i / kKT, kk = i - row * kKT, k = k0 + kk;
+      if (k >= K) continue;
+      const float c = cs[kk];
+      if (mode == 0 || c > kEps) cb[(long)row * K + k] = us[i] / fmaxf(c, kEps);
+      else if (mode == 2) cb[(long)row * K + k] = 0.0f;
+    }
+  }
+  if (!want_d2) return;
+  __syncthreads();
+  // distances: d2[n, k] = sum_j (wt[k, j] - Z[n, j])^2, the reference's direct-difference form
+  float acc[8][MN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int m = 0; m < MN; ++m) acc[i][m] = 0.0f;
+  for (int j = 0; j < r; ++j) {
+    float wv[8], zv[MN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[i] = wts[(ty * 8 + i) * ZP + j];
+#pragma unroll
+    for (int m = 0; m < MN; ++m) zv[m] = Zs[(tx + 16 * m) * ZP + j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int m = 0; m < MN; ++m) {
+        const float df = wv[i] - zv[m];
+        acc[i][m] = fmaf(df, df, acc[i][m]);
+      }
+  }
+  // through shared memory (the u tile is dead) so that the rows go out coalesced
+#pragma unroll
+  for (int m = 0; m < MN; ++m)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) us[(tx + 16 * m) * kKT + ty * 8 + i] = acc[i][m];
+  __syncthreads();
+  float* db = d2 + (long)t * n * K;
+  for (int i = tid; i < n * kKT; i += 256) {
+    const int row = i / kKT, kk = i - row * kKT;
+    if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[i];
+  }
+}
+
+template <int MJ, int MN>
+cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
+                        int r, int mode, int want_d2, cudaStream_t st) {
+  constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
+  const size_t smem = sizeof(float) * ((size_t)NQ * ZP + (size_t)NQ * kKT + (size_t)kKT * ZP + kKT);
+  static PerDeviceFlags attr_set;
+  const int slot = current_device_slot();
+  if (smem > 48 * 1024 && (slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0)) {
+    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
+  }
+  kproj_iter_kernel<MJ, MN><<<dim3((K + kKT - 1) / kKT, T), 256, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2);
+  note_launch();
+  return cudaGetLastError();
+}
+
+template <int MJ>
+cudaError_t launch_iter_mn(int mn, const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n,
+                           int K, int r, int mode, int want_d2, cudaStream_t st) {
+  switch (mn) {
+    case 1: return launch_iter<MJ, 1>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 2: return launch_iter<MJ, 2>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 3: return launch_iter<MJ, 3>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 4: return launch_iter<MJ, 4>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 5: return launch_iter<MJ, 5>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    default: return launch_iter<MJ, 6>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+  }
+}
+
+cudaError_t iterate(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K, int r,
+                    int mode, int want_d2, cudaStream_t st) {
+  const int mj = (r + 15) / 16, mn = (n + 15) / 16;
+  switch (mj) {
+    case 1: return launch_iter_mn<1>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 2: return launch_iter_mn<2>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 3: return launch_iter_mn<3>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 4: return launch_iter_mn<4>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 5: return launch_iter_mn<5>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    default: return launch_iter_mn<6>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+  }
+}
+
+// w[t,k,d] = sum_n coef[t,n,k] x[t,n,d]: 64 (k) x 64 (d) tile per CTA, the samples staged through shared memory
+__global__ void __launch_bounds__(256)
+expand_kernel(const float* __restrict__ coef, const float* __restrict__ x, float* __restrict__ w, int n, int K, int D) {
+  constexpr int kTile = 64, kStage = 16;
+  __shared__ float cs_[kStage][kTile + 4];
+  __shared__ float xs[kStage][kTile + 4];
+  const int t = blockIdx.z;
+  const int k0 = blockIdx.y * kTile, d0 = blockIdx.x * kTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* cb = coef + (long)t * n * K;
+  const float* xb = x + (long)t * n * D;
+  float acc[4][4] = {};
+  for (int n0 = 0; n0 < n; n0 += kStage) {
+    for (int i = threadIdx.x; i < kStage * kTile; i += 256) {
+      const int rr = i / kTile, c = i % kTile;
+      const int nn = n0 + rr;
+      cs_[rr][c] = (nn < n && k0 + c < K) ? cb[(long)nn * K + k0 + c] : 0.0f;
+      xs[rr][c] = (nn < n && d0 + c < D) ? xb[(long)nn * D + d0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < kStage; ++rr) {
+      float cc[4], xx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cc[i] = cs_[rr][ty * 4 + i];
+        xx[i] = xs[rr][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(cc[i], xx[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + tx * 4 + j;
+      if (d < D) w[((long)t * K + k) * D + d] = acc[i][j];
+    }
+  }
+}
+
+inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+bool kmeans_sample_coordinates(int n, int D) { return std::min(n, D) <= kMaxR; }
+
+// rq: row pitch of the sample-coordinate arrays
+static int coord_pitch(int n, int D) { return 16 * ((std::min(n, D) + 15) / 16); }
+
+size_t kmeans_run_workspace_bytes(const KMeansRun& p) {
+  const size_t T = p.T, n = p.n, K = p.K, D = p.D;
+  size_t b = 0;
+  b += align_up(sizeof(float) * T * n * K);              // d2
+  b += align_up(sizeof(float) * T);                      // task norms (criterion)
+  if (p.method == 2) b += align_up(sizeof(float) * T * n * K);   // u_old
+  if (p.method == 1) b += align_up(sizeof(float) * T * K);       // colsum scratch
+  if (kmeans_sample_coordinates(p.n, p.D)) {
+    const size_t rq = coord_pitch(p.n, p.D);
+    b += align_up(sizeof(float) * T * K * rq);           // wt
+    if (D > n) {
+      b += align_up(sizeof(double) * T * n * n);         // G
+      b += align_up(sizeof(float) * T * n * rq);         // Z
+    }
+  } else if (!p.w) {
+    b += align_up(sizeof(float) * T * K * D);            // w of the feature-space fallback
+  }
+  return b;
+}
+
+cudaError_t kmeans_expand_centroids(const float* coef, const float* x, float* w, int T, int n, int K, int D,
+                                    cudaStream_t st) {
+  expand_kernel<<<dim3((D + 63) / 64, (K + 63) / 64, T), 256, 0, st>>>(coef, x, w, n, K, D);
+  note_launch();
+  return cudaGetLastError();
+}
+
+#define KM_TRY(call)                       \
+  do {                                     \
+    cudaError_t e__ = (call);              \
+    if (e__ != cudaSuccess) return e__;    \
+  } while (0)
+
+cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
+  const int T = p.T, n = p.n, K = p.K, D = p.D;
+  char* base = static_cast<char*>(workspace);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = base + off;
+    off += align_up(bytes);
+    return r;
+  };
+  float* d2 = static_cast<float*>(take(sizeof(float) * (size_t)T * n * K));
+  float* task_norm = static_cast<float*>(take(sizeof(float) * (size_t)T));
+  float* u_old = p.method == 2 ? static_cast<float*>(take(sizeof(float) * (size_t)T * n * K)) : nullptr;
+  float* colsum = p.method == 1 ? static_cast<float*>(take(sizeof(float) * (size_t)T * K)) : nullptr;
+  const bool coords = kmeans_sample_coordinates(n, D);
+  const float* Z = p.x;
+  int zs = D, r = D;
+  float *wt = nullptr, *w = p.w;
+  if (coords) {
+    const int rq = coord_pitch(n, D);
+    wt = static_cast<float*>(take(sizeof(float) * (size_t)T * K * rq));
+    if (D > n) {
+      double* G = static_cast<double*>(take(sizeof(double) * (size_t)T * n * n));
+      float* Zc = static_cast<float*>(take(sizeof(float) * (size_t)T * n * rq));
+      gram_kernel<<<T, 256, 0, st>>>(p.x, G, n, D);
+      const size_t smem = sizeof(double) * (size_t)n * n;
+      if (smem > 48 * 1024) KM_TRY(cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      chol_kernel<<<T, 256, smem, st>>>(G, Zc, n, rq);
+      note_launch(2);
+      Z = Zc;
+      zs = rq;
+      r = n;
+    }
+  } else if (!w) {
+    w = static_cast<float*>(take(sizeof(float) * (size_t)T * K * D));
+  }
+  if (p.method == 1) KM_TRY(cudaMemsetAsync(p.v, 0, sizeof(float) * (size_t)T * K, st));
+  // w_init (soft k-means, EM-Gaussian); hard k-means has none (hard_kmeans.py:186)
+  if (p.method != 2) {
+    if (coords) KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, 0, 0, st));
+    else KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, 0, st));
+  } else {
+    KM_TRY(cudaMemcpyAsync(u_old, p.u, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
+  }
+  if (p.iter_events && p.iter_events[0]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[0], st));
+  for (int it = 0; it < p.iters; ++it) {
+    const int mode = p.method == 2 ? 2 : 1;
+    if (coords) {
+      KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, st));
+    } else {
+      KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, mode == 2 ? 0 : 1, st));
+      KM_TRY(kmeans_sqdist(p.x, w, d2, T, n, K, D, st));
+    }
+    KM_TRY(kmeans_assign(d2, p.v, nullptr, p.temperature, p.lambd, p.u, p.labels, T, n, K, p.method, st));
+    if (p.method == 1) KM_TRY(colsum_v(p.u, colsum, p.v, nullptr, T, n, K, st));   // v_update after u_update (em_gaussian.py:212-218)
+    if (p.method == 2) {
+      // logged twice per iteration upstream (hard_kmeans.py:203,208-209)
+      KM_TRY(kmeans_udiff(u_old, p.u, task_norm, p.criterions + 2 * it, T, (long)n * K, st));
+      KM_TRY(cudaMemcpyAsync(p.criterions + 2 * it + 1, p.criterions + 2 * it, sizeof(float), cudaMemcpyDeviceToDevice, st));
+      KM_TRY(cudaMemcpyAsync(u_old, p.u, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
+    }
+    if (p.iter_events && p.iter_events[it + 1]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[it + 1], st));
+  }
+  // the reference copies u_old after the update: the logged criterion of the soft variants is identically 0
+  if (p.method != 2) KM_TRY(cudaMemsetAsync(p.criterions, 0, sizeof(float) * (size_t)std::max(p.iters, 1), st));
+  if (coords && p.w) KM_TRY(kmeans_expand_centroids(p.coef, p.x, p.w, T, n, K, D, st));
+  return cudaGetLastError();
+}
+
+}  // namespace tclip

@@ -11,6 +11,20 @@ namespace tclip {
 extern std::atomic<long long> g_launches;
 inline void note_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Per-device facts (function attributes, SM count) are cached per device index: one process may drive several GPUs, and
+// several host threads (tclip_b200.pipeline) may reach a launcher at once.  A slot is 0 until its fact is established.
+constexpr int kMaxDevices = 64;
+struct PerDeviceFlags {
+  std::atomic<int> v[kMaxDevices];
+  PerDeviceFlags() { for (auto& x : v) x.store(0, std::memory_order_relaxed); }
+};
+// current device index, or -1 (out of the cached range or no device): callers then skip the cache
+inline int current_device_slot() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
 // ---- Dirichlet MM M-step (dirichlet_mm.cu) --------------------------------------------------------------------
 constexpr int kMMThreads = 128;    // 4 warps = 4 rows per CTA
 constexpr int kMMMaxSlots = 32;    // register slots per lane => D <= 1024
@@ -53,6 +67,7 @@ struct MMLaunch {
   int split_cap;
   double2* spec_terms;    // [n_checks][split_cap]
   float* spec_snap;       // [n_checks][split_cap][D]
+  int4* spec_probe;       // optional [split_cap]: per-row convergence statistics (selects the measurement build of the kernel)
 };
 
 int mm_max_dim();
@@ -89,6 +104,10 @@ cudaError_t logits_simt(const float* logz, const float* alpha, float* l3, int T,
                         cudaStream_t st);   // the CUDA-core form (dirichlet_estep.cu), any shape
 cudaError_t logits_tc(const float* logz, const float* alpha, float* l3, int T, int n, int K, int D, const int* gate,
                       bool accumulate_in_tmem, cudaStream_t st);
+// the same kernel as a general batched "NT" product: C[t,m,k] = sum_d A[t,m,d] (B[tb,k,d] - b_shift), B shared by all
+// tasks when b_tasks == 1 (needs D % 4 == 0 and 16-byte aligned operands)
+cudaError_t gemm_nt_tc(const float* a, const float* b, float* c, int T, int M, int N, int D, int b_tasks, float b_shift,
+                       const int* gate, bool accumulate_in_tmem, cudaStream_t st);
 cudaError_t cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
                                int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
                                cudaStream_t st);
@@ -123,6 +142,29 @@ cudaError_t kmeans_assign(const float* d2, const float* v, const float* bias, fl
                           int* labels, int T, int n, int K, int mode, cudaStream_t st);
 cudaError_t kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long per_task,
                          cudaStream_t st);
+
+// kmeans_run.cu: the whole soft k-means / EM-Gaussian / hard k-means loop on one stream, in the coordinates of the task's
+// own samples when min(n, D) is small enough (kmeans_sample_coordinates), else with the feature-space kernels above
+struct KMeansRun {
+  int T, n, K, D;
+  int iters;
+  int method;             // 0 soft k-means, 1 EM-Gaussian, 2 hard k-means (TCLIP_KMEANS_*)
+  float temperature;
+  float lambd;
+  const float* x;         // [T,n,D]
+  float* u;               // [T,n,K] in: initial assignment, out: final
+  float* v;               // [T,K] (method 1)
+  int* labels;            // [T,n]
+  float* coef;            // [T,n,K] w[t,k,:] = sum_n coef[t,n,k] x[t,n,:] (sample-coordinate form only)
+  float* w;               // optional [T,K,D]
+  float* criterions;      // [iters] ([2 iters] for method 2)
+  void* const* iter_events;  // optional [iters + 1]
+};
+bool kmeans_sample_coordinates(int n, int D);
+size_t kmeans_run_workspace_bytes(const KMeansRun& p);
+cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st);
+cudaError_t kmeans_expand_centroids(const float* coef, const float* x, float* w, int T, int n, int K, int D,
+                                    cudaStream_t st);
 
 // ---- issue-rate microbenchmarks used as roofline denominators (probe.cu) ------------------------------------------
 cudaError_t probe_ffma(float* sink, int n_blocks, int iters, cudaStream_t st);   // 2 * 8 * 256 * iters * 64 flop / CTA... see probe.cu

@@ -44,6 +44,19 @@ class DirichletProblem(ctypes.Structure):
         ("iter_events", POINTER(c_void_p)),
         ("mm_events", POINTER(c_void_p)),
         ("mm_crit", c_void_p),
+        ("spec_probe", c_void_p),
+    ]
+
+
+class KMeansProblem(ctypes.Structure):
+    """Mirror of ``tclip_kmeans_problem`` (include/tclip_b200.h)."""
+    _fields_ = [
+        ("n_task", c_int), ("n_query", c_int), ("n_class", c_int), ("dim", c_int),
+        ("iters", c_int), ("method", c_int),
+        ("temperature", c_float), ("lambd", c_float),
+        ("x", c_void_p), ("u", c_void_p), ("v", c_void_p), ("labels", c_void_p), ("coef", c_void_p), ("w", c_void_p),
+        ("criterions", c_void_p),
+        ("iter_events", POINTER(c_void_p)),
     ]
 
 
@@ -53,6 +66,7 @@ SIGNATURES = {
     "tclip_last_error": (c_char_p, []),
     "tclip_device_check": (c_int, [c_int]),
     "tclip_mm_max_dim": (c_int, []),
+    "tclip_spec_rows_cap": (c_int, []),
     "tclip_launch_count": (c_longlong, []),
     "tclip_probe_issue_rate": (c_int, [c_int, c_void_p, c_int, c_int, POINTER(ctypes.c_double), c_void_p]),
     "tclip_log_features": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
@@ -88,6 +102,10 @@ SIGNATURES = {
     "tclip_kmeans_assign": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_int,
                                     c_int, c_int, c_int, c_void_p]),
     "tclip_kmeans_udiff": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
+    "tclip_kmeans_sample_coordinates": (c_int, [c_int, c_int]),
+    "tclip_kmeans_workspace_bytes": (c_size_t, [POINTER(KMeansProblem)]),
+    "tclip_kmeans_run": (c_int, [POINTER(KMeansProblem), c_void_p, c_size_t, c_void_p]),
+    "tclip_kmeans_expand_centroids": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tclip_dirichlet_em_workspace_bytes": (c_size_t, [POINTER(DirichletProblem)]),
     "tclip_dirichlet_em_run": (c_int, [POINTER(DirichletProblem), c_void_p, c_size_t, c_void_p]),
 }

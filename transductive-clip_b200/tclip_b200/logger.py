@@ -1,10 +1,45 @@
 """Minimal stand-in for the reference's ``Logger`` (``src/utils.py:171-221``): one ``logging`` logger per module
 name with a stream handler and, when a path is given, a file handler; ``del_logger`` drops the handlers
-(the reference method classes call it from ``__del__``, ``src/methods/zero_shot/em_dirichlet.py:129-130``)."""
+(the reference method classes call it from ``__del__``, ``src/methods/zero_shot/em_dirichlet.py:129-130``).
+
+A method object is built per batch (``src/eval_zero_shot.py:171``) and ``tclip_b200.pipeline`` keeps several alive at
+once on different host threads, all sharing the ``logging.Logger`` of their module name.  Handlers are therefore kept
+once per (logger name, sink) with a use count: every line is written once per sink however many instances are alive,
+and a sink is closed only when its last user calls ``del_logger``."""
 from __future__ import annotations
 
 import logging
 import os
+import threading
+
+_LOCK = threading.Lock()
+_SINKS: dict = {}   # (logger name, sink) -> [handler, use count]; sink = None for the console, else the absolute path
+
+
+def _acquire(logger: logging.Logger, key, make):
+    with _LOCK:
+        entry = _SINKS.get(key)
+        if entry is None:
+            handler = make()
+            handler.setFormatter(logging.Formatter("[%(name)s]: [%(levelname)s]: %(message)s"))
+            logger.addHandler(handler)
+            entry = _SINKS[key] = [handler, 0]
+        entry[1] += 1
+
+
+def _release(logger: logging.Logger, key):
+    with _LOCK:
+        entry = _SINKS.get(key)
+        if entry is None:
+            return
+        entry[1] -= 1
+        if entry[1] <= 0:
+            del _SINKS[key]
+            logger.removeHandler(entry[0])
+            try:
+                entry[0].close()
+            except Exception:
+                pass
 
 
 class Logger:
@@ -12,23 +47,19 @@ class Logger:
         self._logger = logging.getLogger(name)
         self._logger.setLevel(level)
         self._logger.propagate = False
-        self._handlers = []
-        fmt = logging.Formatter("[%(name)s]: [%(levelname)s]: %(message)s")
-        if not any(isinstance(h, logging.StreamHandler) and not isinstance(h, logging.FileHandler)
-                   for h in self._logger.handlers):
-            sh = logging.StreamHandler()
-            sh.setFormatter(fmt)
-            self._logger.addHandler(sh)
-            self._handlers.append(sh)
+        self._keys = []
+        key = (name, None)
+        _acquire(self._logger, key, logging.StreamHandler)
+        self._keys.append(key)
         if log_file:
             try:
-                d = os.path.dirname(log_file)
+                path = os.path.abspath(log_file)
+                d = os.path.dirname(path)
                 if d:
                     os.makedirs(d, exist_ok=True)
-                fh = logging.FileHandler(log_file)
-                fh.setFormatter(fmt)
-                self._logger.addHandler(fh)
-                self._handlers.append(fh)
+                key = (name, path)
+                _acquire(self._logger, key, lambda: logging.FileHandler(path))
+                self._keys.append(key)
             except OSError:
                 pass
 
@@ -42,10 +73,6 @@ class Logger:
         self._logger.debug(msg, *a)
 
     def del_logger(self):
-        for h in self._handlers:
-            self._logger.removeHandler(h)
-            try:
-                h.close()
-            except Exception:
-                pass
-        self._handlers = []
+        keys, self._keys = self._keys, []
+        for key in keys:
+            _release(self._logger, key)

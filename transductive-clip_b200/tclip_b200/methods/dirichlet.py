@@ -9,7 +9,7 @@ The callers are ``src/eval_zero_shot.py:113-138,171-177`` and ``src/eval_few_sho
 
 All arithmetic of ``run_method`` happens in CUDA kernels behind ``ops.dirichlet_em`` (one C-ABI call that enqueues the
 whole EM loop), the cluster -> class assignment included (``ops.match_clusters``: SciPy's shortest-augmenting-path
-algorithm restated for one warp per task; ``tclip_b200.matching`` keeps the SciPy form the tests compare it with).
+algorithm restated for one warp per task; ``tests/scipy_matching.py`` keeps the SciPy form the tests compare it with).
 """
 from __future__ import annotations
 

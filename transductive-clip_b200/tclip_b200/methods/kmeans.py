@@ -44,7 +44,8 @@ class _KMeansBase(object):
         self.init_info_lists()
         self.args = args
         self.eps = 1e-15
-        self.u = self.w = self.v = self.labels = None
+        self.u = self.v = self.labels = None
+        self._w = self._coef = self._query = None
 
     def __del__(self):
         try:
@@ -100,49 +101,50 @@ class _KMeansBase(object):
         cl = ops.cluster_prototypes(self.labels, query)
         probs = cl["proto"]
         if not self.args.use_softmax_feature:
-            # probs = softmax(T * normalize(prototype) @ text.T); only the rows of existing clusters are worth the GEMM
-            max_c = max(int(cl["n_clusters"].max().item()), 1)
-            probs = ops.kmeans_similarity(ops.normalize_rows(probs[:, :max_c].contiguous()), self._text_features,
-                                          float(self.args.T))
+            # probs = softmax(T * normalize(prototype) @ text.T) for all n prototype rows (rows beyond a task's cluster count
+            # are zero prototypes -> NaN after the normalisation, as upstream, and are never read by the matching): one
+            # tensor-core product, no host round trip for the cluster count
+            probs = ops.kmeans_similarity(ops.normalize_rows(probs), self._text_features, float(self.args.T))
         res = ops.match_clusters(probs, cl["n_clusters"], cl["sample_cluster"], y_q.contiguous(),
                                  graph_matching=(self.args.graph_matching == True))  # noqa: E712 (reference's test)
         self.new_labels = res["new_labels"]
         self.test_acc.append(res["acc"].unsqueeze(1))
 
     # ------------------------------------------------------------------------------------------------------------
+    @property
+    def w(self):
+        """Centroids [T,K,D].  The fused loop works in the coordinates of the task's own samples and never forms them
+        (csrc/kmeans_run.cu); they are produced from the coefficients the first time somebody asks."""
+        if self._w is None and self._coef is not None:
+            self._w = ops.kmeans_expand_centroids(self._coef, self._query)
+        return self._w
+
+    @w.setter
+    def w(self, value):
+        self._w = value
+
     def run_method(self, query, y_q):
+        """soft_kmeans.py:168-220 / hard_kmeans.py:153-211 / em_gaussian.py:171-229: one C-ABI call enqueues the whole loop
+        (w_init, ``iter`` x {w_update, u_update[, v_update]}), no host synchronisation inside."""
         self.logger.info(" ==> Executing {} with T = {}".format(self._title, self.args.T))
-        n_task, n_class = query.shape[0], self.args.num_classes_test
-        temperature = float(self.args.T)
+        n_task = query.shape[0]
         hard = self.mode == ops.KMEANS_HARD
-        self.u = self._initial_u(query)
-        if self.mode == ops.KMEANS_GAUSS:
-            self.v = torch.zeros(n_task, n_class, device=self.device)
-        # w_init (soft_kmeans.py:135-148; hard k-means has none: its first w_update zeroes empty clusters anyway)
-        self.w = None if hard else ops.kmeans_centroids(self.u, query, None, keep_old=False)
-        u_old = self.u.clone() if hard else None
-        zero = torch.zeros((), device=self.device)
-        for _ in range(self.iter):
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            self.w = ops.kmeans_centroids(self.u, query, self.w, keep_old=not hard)
-            self.u, self.labels = ops.kmeans_assign(query, self.w, self.mode, temperature, v=self.v,
-                                                    lambd=getattr(self, "lambd", 0.0))
-            if self.mode == ops.KMEANS_GAUSS:
-                # v_update after u_update (em_gaussian.py:212-218)
-                _, self.v, _ = ops.colsum_v(self.u, want_v=True, want_live=False)
-            if hard:
-                crit = ops.kmeans_udiff(u_old, self.u)[0]
-                u_old = self.u.clone()
-            else:
-                crit = zero  # the reference copies u_old *after* the update: its logged criterion is identically 0
-            t1.record()
-            t1.synchronize()
-            dt = t0.elapsed_time(t1) / 1000.0
-            if hard:
-                self.record_convergence(new_time=dt, criterions=crit)      # hard_kmeans.py:203 (un-normalised) ...
-            self.record_convergence(new_time=dt / n_task, criterions=crit)  # ... and :208-209
+        u0 = self._initial_u(query)
+        res = ops.kmeans_run(query, u0, self.mode, self.iter, float(self.args.T), lambd=float(getattr(self, "lambd", 0.0)),
+                             record_events=True)
+        self.u, self.labels, self.v = res["u"], res["labels"], res["v"]
+        self._coef, self._w, self._query = res["coef"], res["w"], query
+        crit, events = res["criterions"], res["events"]
         self.compute_acc_clustering(query, y_q)
+        # per-iteration device time (the reference logs un-synchronised wall time per iteration, soft_kmeans.py:203,216-218)
+        events[-1].synchronize()
+        for i in range(self.iter):
+            dt = events[i].elapsed_time(events[i + 1]) / 1000.0
+            if hard:
+                self.record_convergence(new_time=dt, criterions=crit[2 * i])           # hard_kmeans.py:203 (un-normalised) ...
+                self.record_convergence(new_time=dt / n_task, criterions=crit[2 * i + 1])   # ... and :208-209
+            else:
+                self.record_convergence(new_time=dt / n_task, criterions=crit[i])
 
 
 class SOFT_KMEANS(_KMeansBase):

@@ -13,7 +13,7 @@ from ._lib import DirichletProblem, TCLIP_MM_DENSE, TCLIP_MM_SKIP_DEAD, check
 
 __all__ = ["log_features", "colsum_v", "moments", "support_stats", "mm_update_alpha", "commit", "estep",
            "cluster_prototypes", "dirichlet_em", "device_check", "launch_count", "probe_issue_rate", "normalize_rows", "kmeans_similarity",
-           "kmeans_centroids", "kmeans_assign", "kmeans_udiff", "kmeans_precisions", "kmeans_assign_cov", "kmeans_assign_kl", "KMEANS_SOFT", "KMEANS_GAUSS", "KMEANS_HARD", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
+           "kmeans_centroids", "kmeans_run", "kmeans_expand_centroids", "kmeans_assign", "kmeans_udiff", "kmeans_precisions", "kmeans_assign_cov", "kmeans_assign_kl", "KMEANS_SOFT", "KMEANS_GAUSS", "KMEANS_HARD", "TCLIP_MM_DENSE", "TCLIP_MM_SKIP_DEAD"]
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -337,6 +337,58 @@ def kmeans_udiff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def kmeans_run(x: torch.Tensor, u0: torch.Tensor, method: int, iters: int, temperature: float, lambd: float = 0.0,
+               want_w: bool = False, record_events: bool = False) -> dict:
+    """The fused driver ``tclip_kmeans_run``: the whole soft k-means / EM-Gaussian / hard k-means loop enqueued on the
+    current stream.  ``u0`` [T,n,K] is the initial assignment (updated in place and returned as ``u``).  Returns device
+    tensors u, labels, v (EM-Gaussian), criterions, and either ``coef`` [T,n,K] (sample-coordinate form: the centroids
+    are ``kmeans_expand_centroids(coef, x)``) or ``w`` [T,K,D]."""
+    lib = _lib.load()
+    _need(x, torch.float32, "x"), _need(u0, torch.float32, "u0")
+    T, n, D = x.shape
+    K = u0.shape[2]
+    dev = x.device
+    coords = bool(lib.tclip_kmeans_sample_coordinates(n, D))
+    n_crit = (2 * iters) if method == KMEANS_HARD else iters
+    out = {
+        "u": u0,
+        "labels": torch.zeros(T, n, device=dev, dtype=torch.int32),
+        "v": torch.zeros(T, K, device=dev, dtype=torch.float32) if method == KMEANS_GAUSS else None,
+        "criterions": torch.zeros(max(n_crit, 1), device=dev, dtype=torch.float32)[:n_crit],
+        "coef": torch.empty(T, n, K, device=dev, dtype=torch.float32) if coords else None,
+        "w": torch.empty(T, K, D, device=dev, dtype=torch.float32) if (want_w or not coords) else None,
+    }
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)] if record_events else []
+    ev_arr = None
+    if events:
+        for e in events:
+            e.record()
+        ev_arr = (ctypes.c_void_p * (iters + 1))(*[e.cuda_event for e in events])
+    p = _lib.KMeansProblem(
+        n_task=T, n_query=n, n_class=K, dim=D, iters=int(iters), method=int(method), temperature=float(temperature),
+        lambd=float(lambd), x=_ptr(x), u=_ptr(u0), v=_ptr(out["v"]), labels=_ptr(out["labels"]), coef=_ptr(out["coef"]),
+        w=_ptr(out["w"]), criterions=_ptr(out["criterions"]),
+        iter_events=ctypes.cast(ev_arr, ctypes.POINTER(ctypes.c_void_p)) if ev_arr is not None else None)
+    nbytes = lib.tclip_kmeans_workspace_bytes(ctypes.byref(p))
+    if nbytes == 0:
+        check(-1)
+    ws = _workspace(nbytes, dev)
+    check(lib.tclip_kmeans_run(ctypes.byref(p), _ptr(ws), ws.numel(), _stream()))
+    out["events"] = events
+    return out
+
+
+def kmeans_expand_centroids(coef: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """w [T,K,D] = coef^T x per task (the centroids behind the coefficients ``kmeans_run`` returns)."""
+    lib = _lib.load()
+    _need(coef, torch.float32, "coef"), _need(x, torch.float32, "x")
+    T, n, K = coef.shape
+    D = x.shape[2]
+    w = torch.empty(T, K, D, device=x.device, dtype=torch.float32)
+    check(lib.tclip_kmeans_expand_centroids(_ptr(coef), _ptr(x), _ptr(w), T, n, K, D, _stream()))
+    return w
+
+
 _WORKSPACES: dict = {}
 _WORKSPACES_LOCK = threading.Lock()
 
@@ -363,9 +415,12 @@ def release_workspaces(stream_ids=None) -> None:
 
 def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lambd: float, hard: bool,
                  x_s: torch.Tensor | None = None, y_s: torch.Tensor | None = None, check_every: int = 50,
-                 tol: float = 1e-11, mm_mode: int = TCLIP_MM_DENSE, record_events: bool = False) -> dict:
+                 tol: float = 1e-11, mm_mode: int = TCLIP_MM_DENSE, record_events: bool = False,
+                 spec_probe: bool = False) -> dict:
     """The fused driver ``tclip_dirichlet_em_run``: the whole EM loop enqueued on the current stream.
-    Returns device tensors u, alpha, v, labels, criterions, mm_iters, n_live, mm_rows (+ ``events``)."""
+    Returns device tensors u, alpha, v, labels, criterions, mm_iters, n_live, mm_rows (+ ``events``).
+    ``spec_probe`` (measurement only) adds ``spec_probe`` int32 [iters, cap, 4]: per live row of the few-rows M-step kernel
+    {iterations executed, fixed-point iteration | -1, cycle-detection iteration | -1, period}."""
     lib = _lib.load()
     _need(x_q, torch.float32, "x_q")
     T, n, D = x_q.shape
@@ -388,6 +443,8 @@ def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lamb
         "mm_rows": torch.zeros(max(iters, 1), device=dev, dtype=torch.int64)[:iters],
         "mm_crit": torch.zeros(max(iters, 1), 2, device=dev, dtype=torch.float64)[:iters],
     }
+    if spec_probe:
+        out["spec_probe"] = torch.full((max(iters, 1), lib.tclip_spec_rows_cap(), 4), -2, device=dev, dtype=torch.int32)
     events = [torch.cuda.Event(enable_timing=True) for _ in range(iters)] if record_events else []
     mm_events = [torch.cuda.Event(enable_timing=True) for _ in range(2 * iters)] if record_events else []
     ev_arr = mm_arr = None
@@ -402,6 +459,7 @@ def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lamb
         x_q=_ptr(x_q), x_s=_ptr(x_s), y_s=_ptr(y_s), u=_ptr(out["u"]), alpha=_ptr(out["alpha"]), v=_ptr(out["v"]),
         labels=_ptr(out["labels"]), criterions=_ptr(out["criterions"]), mm_iters=_ptr(out["mm_iters"]),
         n_live=_ptr(out["n_live"]), mm_rows=_ptr(out["mm_rows"]), mm_crit=_ptr(out["mm_crit"]),
+        spec_probe=_ptr(out.get("spec_probe")),
         iter_events=ctypes.cast(ev_arr, ctypes.POINTER(ctypes.c_void_p)) if ev_arr is not None else None,
         mm_events=ctypes.cast(mm_arr, ctypes.POINTER(ctypes.c_void_p)) if mm_arr is not None else None)
     nbytes = lib.tclip_dirichlet_em_workspace_bytes(ctypes.byref(p))

@@ -209,6 +209,9 @@ class DeviceFewShotTaskSource:
         self.ls = self.labels_support_host.to(self.device).contiguous()
         self.fq = features_query.to(self.device, torch.float32).contiguous()
         self.lq = labels_query.to(self.device).long().contiguous()
+        # label_map must cover every label a gathered sample can carry: a query label that no support sample has maps to
+        # 0, as ``zeros_like`` does in the reference's get_task
+        self._max_label = max(int(self.labels_support_host.max()), int(labels_query.max()))
 
     def generate_tasks(self, sampler_support, sampler_query) -> dict:
         from . import ops
@@ -220,12 +223,12 @@ class DeviceFewShotTaskSource:
             if len({int(u.numel()) for u in uniq}) != 1:
                 raise ValueError("tasks of one batch must see the same number of support classes")
             col_perm = torch.stack(uniq)                                                         # [T, U]
-            n_labels = int(max(int(self.labels_support_host.max()), int(col_perm.max()))) + 1
+            n_labels = max(self._max_label, int(col_perm.max())) + 1
             label_map = torch.zeros(T, n_labels, dtype=torch.int64)                              # zeros_like in get_task
             label_map.scatter_(1, col_perm, torch.arange(col_perm.shape[1]).expand(T, -1))
         else:  # visual features: data and labels pass through unchanged
             col_perm = torch.arange(F).expand(T, -1).contiguous()
-            n_labels = int(self.labels_support_host.max()) + 1
+            n_labels = self._max_label + 1
             label_map = torch.arange(n_labels).expand(T, -1).contiguous()
         dev = self.device
         put = lambda x: x.contiguous().pin_memory().to(dev, non_blocking=True)
