@@ -135,6 +135,7 @@ class _KMeansBase(object):
         self.u, self.labels, self.v = res["u"], res["labels"], res["v"]
         self._coef, self._w, self._query = res["coef"], res["w"], query
         crit, events = res["criterions"], res["events"]
+        self._events = events
         self.compute_acc_clustering(query, y_q)
         # per-iteration device time (the reference logs un-synchronised wall time per iteration, soft_kmeans.py:203,216-218)
         events[-1].synchronize()

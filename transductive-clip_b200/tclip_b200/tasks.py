@@ -106,11 +106,18 @@ class ZeroShotQuerySampler:
     evaluator asks (``src/eval_zero_shot.py:153-154``)."""
 
     def __init__(self, n_batch: int, n_class: int, n_query: int, labels, force_query_size: bool = True):
-        import numpy as np
         self.n_batch, self.n_class, self.n_query = int(n_batch), int(n_class), int(n_query)
         self.force_query_size = force_query_size
+        # ``labels``: the label vector of the cached features, or the per-class index lists ``index_lists`` made of it (the
+        # evaluator builds a new sampler for every batch; the lists of a fixed label vector need to be made only once)
+        self.m_ind_query = labels if isinstance(labels, list) else self.index_lists(labels, self.n_class)
+
+    @staticmethod
+    def index_lists(labels, n_class: int) -> list:
+        """Per class the indices of its samples, ascending (``src/sampler_zero_shot.py:35-41``)."""
+        import numpy as np
         lab = np.asarray(labels.cpu() if isinstance(labels, torch.Tensor) else labels)
-        self.m_ind_query = [torch.from_numpy(np.argwhere(lab == i).reshape(-1)) for i in range(self.n_class)]
+        return [torch.from_numpy(np.argwhere(lab == i).reshape(-1)) for i in range(int(n_class))]
 
     def __len__(self):
         return self.n_batch
@@ -146,8 +153,12 @@ class DeviceTaskSource:
         self.labels = all_labels.to(self.device).long().contiguous()
 
     def generate_tasks(self, sampler) -> dict:
-        from . import ops
         idx = torch.stack([torch.as_tensor(i, dtype=torch.int64) for i in sampler])          # [T, n] on the host
+        return self.generate_from_indices(idx)
+
+    def generate_from_indices(self, idx: torch.Tensor) -> dict:
+        """``idx`` int64 [T, n] (host): the index lists a sampler produced for one batch."""
+        from . import ops
         idx = idx.pin_memory().to(self.device, non_blocking=True)
         x_q, y_q, bad = ops.gather_tasks(self.features, self.labels, idx)
         if int(bad.item()):
