@@ -34,6 +34,9 @@ CASES = [
     ("zs_hard_em_dirichlet_k20", "dirichlet", "HARD_EM_DIRICHLET", "zero_shot", 20, 3, 3, {}),
     ("zs_em_dirichlet_k100", "dirichlet", "EM_DIRICHLET", "zero_shot", 100, 2, 3, {}),
     ("zs_hard_em_dirichlet_k100", "dirichlet", "HARD_EM_DIRICHLET", "zero_shot", 100, 2, 3, {}),
+    # the reference's default outer iteration counts (config/methods_config/{em,hard_em}_dirichlet.yaml: iter 20 / 10)
+    ("zs_em_dirichlet_k100_iter20", "dirichlet", "EM_DIRICHLET", "zero_shot", 100, 8, 20, {}),
+    ("zs_hard_em_dirichlet_k100_iter10", "dirichlet", "HARD_EM_DIRICHLET", "zero_shot", 100, 8, 10, {}),
     ("fs_em_dirichlet_k20", "dirichlet", "EM_DIRICHLET", "few_shot", 20, 2, 3, {"shots": 2}),
     ("fs_hard_em_dirichlet_k20", "dirichlet", "HARD_EM_DIRICHLET", "few_shot", 20, 2, 3, {"shots": 2}),
     ("zs_soft_kmeans_k20", "kmeans", "SOFT_KMEANS", "zero_shot", 20, 3, 4, {"softmax": True}),

@@ -73,9 +73,12 @@ def test_golden_dirichlet(dev, golden_dir, name, mode):
     agree = (m.labels.cpu().long().numpy() == g["preds"]).mean()
     assert agree >= LABEL_AGREE, agree
     assert abs(float(logs["acc"].mean()) - float(g["acc"].mean())) <= ACC_TOL
-    # alpha vs the reference's own float32 result: bounded by the reference's fp32 noise (few outer iterations here)
+    # alpha vs the reference's own float32 result: bounded by the reference's fp32 noise — 2e-4 after a few outer iterations;
+    # at the default 20 / 10 outer iterations the reference's float32 is itself 2-3e-4 away from its float64 run on the
+    # diverging singleton clusters, and two float32 trajectories differ by about twice that
+    tol = 2e-4 if iters <= 6 else 8e-4
     for t in range(g["alpha"].shape[0]):
-        assert _rel(m.alpha[t].cpu(), torch.from_numpy(g["alpha"][t])) < 2e-4
+        assert _rel(m.alpha[t].cpu(), torch.from_numpy(g["alpha"][t])) < tol
     np.testing.assert_allclose(m.v.cpu().numpy(), g["v"], rtol=1e-3, atol=2e-2)   # v of near-empty clusters = log of ~1e-14 sums
     if not (setting == "few_shot" and method.startswith("HARD")):
         np.testing.assert_allclose(logs["criterions"], g["criterions"], rtol=2e-3, atol=1e-6)

@@ -281,3 +281,75 @@ def test_bench_reference_arm_and_no_gpu_behaviour():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          env=env, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# evaluator-level boundary: the restated call sequence == the live evaluator, and the live evaluator
+# reaches the drop-in classes through its own get_method_builder
+# ----------------------------------------------------------------------------------------------------------------------
+class _RecordingMethod:
+    """Stands in for a method class: keeps what the evaluator hands to run_task."""
+    seen = None
+
+    def __init__(self, model, device, log_file, args):
+        self.args = args
+
+    def run_task(self, task_dic):
+        type(self).seen.append({k: v.clone() for k, v in task_dic.items()})
+        n_task = task_dic["x_q"].shape[0]
+        acc = (task_dic["x_q"].argmax(-1) == task_dic["y_q"].squeeze(2)).float().mean(1, keepdim=True).numpy()
+        return {"acc": acc, "timestamps": 0.5 * n_task, "criterions": np.zeros(1)}
+
+
+def _evaluator_inputs():
+    K, per_class = 30, 30      # >= 25 per class: three classes must hold n_query samples or the sampler re-draws forever
+    g = torch.Generator().manual_seed(0)
+    labels = torch.arange(K).repeat_interleave(per_class)
+    feats = torch.softmax(3.0 * torch.randn(labels.numel(), K, generator=g) + 4.0 * torch.nn.functional.one_hot(labels, K), -1)
+    args = make_args(K, iters=2, name_method="EM_DIRICHLET", number_tasks=20, batch_size=5, used_test_set="test",
+                     dataset="synthetic", save_results=False)
+    return feats, labels, args
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["available"]).available(), reason="reference checkout not present")
+def test_evaluator_harness_equals_live_evaluator(tmp_path):
+    """The reference's own Evaluator_zero_shot.evaluate_tasks (imported unchanged) and tests/evaluator_harness.py hand the
+    same task dictionaries to run_task and return the same means, given the same seeds."""
+    import random
+
+    import evaluator_harness as H
+    from oracle import ref_loader
+    ev_mod = ref_loader.load("eval_zero_shot")
+    feats, labels, args = _evaluator_inputs()
+    live = type("Live", (_RecordingMethod,), {"seen": []})
+    mine = type("Mine", (_RecordingMethod,), {"seen": []})
+    ev = ev_mod.Evaluator_zero_shot(torch.device("cpu"), args, str(tmp_path / "log.txt"))
+    ev.get_method_builder = lambda model, device, args, log_file: live(model, device, log_file, args)
+    random.seed(11), torch.manual_seed(11)
+    acc_live, t_live = ev.evaluate_tasks(None, feats, labels)
+    random.seed(11), torch.manual_seed(11)
+    acc_mine, t_mine, _ = H.evaluate_tasks(args, torch.device("cpu"), feats, labels, build=lambda **kw: mine(**kw))
+    assert len(live.seen) == len(mine.seen) == 4
+    for a, b in zip(live.seen, mine.seen):
+        assert torch.equal(a["x_q"], b["x_q"]) and torch.equal(a["y_q"], b["y_q"])
+        assert a["x_q"].shape == (5, 75, 30) and a["y_q"].shape == (5, 75, 1) and a["y_q"].dtype == torch.int64
+    assert acc_live == acc_mine and t_live == t_mine
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["available"]).available(), reason="reference checkout not present")
+def test_live_evaluator_reaches_the_drop_in_class(tmp_path):
+    """The unchanged evaluator, with the drop-in class bound where its import statement would have bound the reference's
+    (src/eval_zero_shot.py:14): its own get_method_builder constructs the B200 class with its own keyword call and calls
+    run_task on the task_dic of its own task generator; without a GPU that call must refuse loudly (no CPU path)."""
+    from oracle import ref_loader
+    from tclip_b200.methods.dirichlet import EM_DIRICHLET
+    ev_mod = ref_loader.load("eval_zero_shot")
+    feats, labels, args = _evaluator_inputs()
+    ev = ev_mod.Evaluator_zero_shot(torch.device("cpu"), args, str(tmp_path / "log.txt"))
+    original = ev_mod.EM_DIRICHLET
+    ev_mod.EM_DIRICHLET = EM_DIRICHLET
+    try:
+        with pytest.raises(RuntimeError, match="B200 GPUs only"):
+            ev.evaluate_tasks(None, feats, labels)
+    finally:
+        ev_mod.EM_DIRICHLET = original

@@ -45,3 +45,23 @@ def test_kmeans_family_live(method, km, softmax):
                         contraction="broadcast")
     assert torch.equal(inst.u, r.u) and torch.equal(inst.w, r.w)
     assert np.array_equal(logs["acc"], r.acc) and np.array_equal(logs["criterions"], r.criterions, equal_nan=True)
+
+
+def test_einsum_mode_at_imagenet_shape_live():
+    """The ``einsum`` contraction mode of the restatement (the one every K = 1000 fixture and the CPU baseline use) against
+    the LIVE reference at K = D = 1000: one task, two outer iterations (51 + 1000 MM iterations; the second M-step and the
+    second E-step see moments / logits that went through the einsum path).  The reference forms the [T,n,K,D] broadcast
+    (300 MB per temporary at T = 1); einsum sums in a different order, so equality is to float32 rounding, not bitwise."""
+    K, T, iters = 1000, 1, 2
+    td, _ = tasks.make_zero_shot_batch(T, K, seed=2020, batch_index=31)
+    logs, inst = ref_loader.run_reference("EM_DIRICHLET", "zero_shot", td, ref_loader.make_args(K, iters=iters))
+    r = R.dirichlet_zero_shot(td["x_q"], td["y_q"], K, iters=iters, contraction="einsum")
+    assert r.mm_iters == [51, 1000]
+    assert torch.equal(inst.u.argmax(2), r.preds)
+    assert np.array_equal(logs["acc"], r.acc)
+    rel = ((inst.alpha.double() - r.alpha.double()).norm() / inst.alpha.double().norm()).item()
+    assert rel < 2e-5, rel
+    live = inst.u.sum(1) > 1e-15
+    assert torch.equal(live, r.u.sum(1) > 1e-15)
+    np.testing.assert_allclose(logs["criterions"], r.criterions, rtol=1e-4)
+    np.testing.assert_allclose(inst.u.numpy(), r.u.numpy(), atol=1e-4)
