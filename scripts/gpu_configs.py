@@ -43,10 +43,28 @@ timed("cfg2 Hard EM-Dirichlet zero-shot K=D=1000, batch 75, iter 10", lambda i: 
 a5 = make_args(1000, iters=20)
 timed("cfg5 EM-Dirichlet zero-shot K=D=1000, batch 75, iter 20", lambda i: pin(tasks.make_zero_shot_batch(75, 1000, seed=2020, batch_index=i)[0]),
       lambda td: D.EM_DIRICHLET(model=None, device=dev, log_file=None, args=a5).run_task(dict(td)), 75)
-# config 3: EM-Dirichlet 4-shot few-shot, ImageNet shape (every row live in every M-step)
+# config 3: EM-Dirichlet 4-shot few-shot, ImageNet shape (every row live in every M-step), at the evaluator's batch size 75:
+# 15 distinct tasks tiled 5 times (the float64 host generator needs ~1 s per 4000-sample support set)
 a3 = make_args(1000, iters=20, k_eff=5)
-timed("cfg3 EM-Dirichlet 4-shot few-shot K=D=1000 (S=4000), batch 8", lambda i: pin(tasks.make_few_shot_batch(8, 1000, shots=4, seed=2020, batch_index=i)[0]),
-      lambda td: D.FEW_SHOT_EM_DIRICHLET(model=None, device=dev, log_file=None, args=a3).run_task(dict(td), shot=4), 8, reps=2)
+_fs = {}
+def mk_few(i):
+    if i not in _fs:
+        td = tasks.make_few_shot_batch(15, 1000, shots=4, seed=2020, batch_index=i)[0]
+        _fs[i] = pin({k: v.repeat(5, *([1] * (v.dim() - 1))).contiguous() for k, v in td.items()})
+    return _fs[i]
+def run_few(td):
+    m = D.FEW_SHOT_EM_DIRICHLET(model=None, device=dev, log_file=None, args=a3)
+    logs = m.run_task(dict(td), shot=4)
+    run_few.updates = float(m.mm_iters.sum().item()) * 75 * 1000 * 1000
+    return logs
+t_before = time.time()
+timed("cfg3 EM-Dirichlet 4-shot few-shot K=D=1000 (S=4000), batch 75", mk_few, run_few, 75, reps=2)
+from tclip_b200 import ops
+n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+ops.probe_issue_rate("ffma", n_sm * 8, 4000); flop, ms = ops.probe_issue_rate("ffma", n_sm * 8, 4000)
+td = mk_few(1); torch.cuda.synchronize(); t0 = time.time(); run_few(td); torch.cuda.synchronize(); dt = time.time() - t0
+print(f"     cfg3 at T=75: {run_few.updates:.3e} element-updates per batch in {dt * 1e3:.1f} ms = "
+      f"{run_few.updates * 74 / dt / 1e12 / (flop / (ms * 1e-3) / 1e12):.2f} of the FP32 peak (whole run_task incl. 1.2 GB H2D)", flush=True)
 # config 4: soft k-means / EM-Gaussian on visual features D=1024, K=1000, batch 100
 for cls, nm in ((KM.SOFT_KMEANS, "soft k-means"), (KM.EM_GAUSSIAN, "EM-Gaussian"), (KM.HARD_KMEANS, "hard k-means (iter 10)")):
     a4 = make_args(1000, iters=10 if "hard" in nm else 20, use_softmax_feature=False)

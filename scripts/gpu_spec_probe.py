@@ -15,6 +15,7 @@ from tclip_b200 import tasks, ops
 dev = torch.device("cuda:0")
 K, T = int(os.environ.get("PT_K", 1000)), int(os.environ.get("PT_T", 75))
 NOISE = float(os.environ.get("PT_NOISE", tasks.NOISE_SCALE))
+KEFF = tuple(int(v) for v in os.environ.get("PT_KEFF", "3,10").split(","))
 
 
 def run(xq, iters, hard, probe):
@@ -29,14 +30,14 @@ def run(xq, iters, hard, probe):
 
 
 for hard, iters in ((False, 20), (True, 10)):
-    td, _ = tasks.make_zero_shot_batch(T, K, seed=2020, batch_index=1, noise=NOISE)
+    td, _ = tasks.make_zero_shot_batch(T, K, seed=2020, batch_index=1, noise=NOISE, k_eff_range=KEFF)
     xq = td["x_q"].to(dev)
     run(xq, iters, hard, False)                     # warm-up
     prod = run(xq, iters, hard, False)
     stat = run(xq, iters, hard, True)
     same_alpha = torch.equal(prod["alpha"], stat["alpha"])
     same_lab = torch.equal(prod["labels"], stat["labels"])
-    print(f"== hard={hard} K={K} T={T} noise={NOISE}: product == statistics build: alpha {same_alpha} labels {same_lab} "
+    print(f"== hard={hard} K={K} T={T} noise={NOISE} classes per task {KEFF}: product == statistics build: alpha {same_alpha} labels {same_lab} "
           f"mm_iters equal {torch.equal(prod['mm_iters'], stat['mm_iters'])}")
     n_live = prod["n_live"].cpu().tolist()
     pr = stat["spec_probe"].cpu().numpy()
@@ -68,6 +69,14 @@ for hard, iters in ((False, 20), (True, 10)):
     live_sizes = sizes[sizes > 0]
     q = pr[it][pr[it][:, 0] >= 0]
     if live_sizes.size == q.shape[0]:
+        cyc = q[:, 2] >= 0
+        for lo, hi in ((1, 1), (2, 2), (3, 4), (5, 8), (9, 1000)):
+            sel = (live_sizes >= lo) & (live_sizes <= hi)
+            if sel.any():
+                per = q[sel & cyc, 3]
+                print(f"   cluster size {lo}..{hi}: {int(sel.sum())} rows, periodic {int((sel & cyc).sum())}, periods "
+                      f"{dict(zip(*[a.tolist() for a in np.unique(per, return_counts=True)]))}, detected at (median) "
+                      f"{int(np.median(q[sel & cyc, 2])) if (sel & cyc).any() else -1}")
         never = q[:, 1] < 0
         print(f"   last iteration: cluster sizes of rows that never reach a fixed point: {np.bincount(live_sizes[never])[:8].tolist()} "
               f"(index = size), of rows that do: {np.bincount(live_sizes[~never])[:12].tolist()}")

@@ -353,3 +353,30 @@ def test_live_evaluator_reaches_the_drop_in_class(tmp_path):
             ev.evaluate_tasks(None, feats, labels)
     finally:
         ev_mod.EM_DIRICHLET = original
+
+
+def test_logger_handlers_are_shared_and_released_without_blocking(tmp_path):
+    """One handler per (logger name, sink) however many method objects are alive (a new one is built per batch, several at
+    once under tclip_b200.pipeline); a sink closes with its last user; a release arriving while the registry lock is held
+    (the garbage collector running __del__ inside the critical section) is queued instead of deadlocking."""
+    import logging
+
+    from tclip_b200 import logger as L
+    name, path = "tclip_test_logger", str(tmp_path / "log.txt")
+    a, b = L.Logger(name, path), L.Logger(name, path)
+    py = logging.getLogger(name)
+    assert len(py.handlers) == 2                         # console + file, not four
+    a.info("one line")
+    a.del_logger()
+    assert len(py.handlers) == 2                         # b still uses both
+    assert L._LOCK.acquire(blocking=False)               # as if __del__ ran inside _acquire's critical section ...
+    try:
+        b.del_logger()                                   # ... must return at once
+        assert len(py.handlers) == 2 and len(L._PENDING) == 2
+    finally:
+        L._LOCK.release()
+    c = L.Logger(name, None)                             # the next user of the registry applies the queued releases
+    assert [type(h) for h in py.handlers] == [logging.StreamHandler]
+    c.del_logger()
+    assert py.handlers == []
+    assert open(path).read().count("one line") == 1

@@ -37,18 +37,23 @@ constexpr int kKT = 128;      // classes per CTA of the iteration kernel
 constexpr int kMaxR = 96;     // largest coordinate count (and sample count) of the sample-coordinate form
 constexpr int kMaxPairs = (kMaxR * kMaxR + 255) / 256;
 
-// G[t] = X_t X_t^T in float64 (n <= kMaxR): one CTA per task, every thread owns <= kMaxPairs entries, D walked in slabs of
-// 32 columns staged through shared memory.
+// G[t] = X_t X_t^T in float64 (n <= kMaxR): kGramSplits CTAs per task, each over a contiguous range of the D columns walked
+// in slabs of 32 staged through shared memory; every thread owns <= kMaxPairs entries.  The partial matrices
+// G[t][split] are added in split order by chol_kernel (a fixed order: the factor is reproducible bit for bit).
+constexpr int kGramSplits = 4;
+
 __global__ void __launch_bounds__(256)
 gram_kernel(const float* __restrict__ x, double* __restrict__ G, int n, int D) {
   __shared__ float xs[kMaxR][33];
-  const int t = blockIdx.x;
+  const int t = blockIdx.x, split = blockIdx.y;
   const float* xb = x + (long)t * n * D;
   double acc[kMaxPairs];
 #pragma unroll
   for (int q = 0; q < kMaxPairs; ++q) acc[q] = 0.0;
   const int pairs = n * n;
-  for (int d0 = 0; d0 < D; d0 += 32) {
+  const int slabs = (D + 31) / 32, per = (slabs + kGramSplits - 1) / kGramSplits;
+  const int d_lo = split * per * 32, d_hi = min(D, (split + 1) * per * 32);
+  for (int d0 = d_lo; d0 < d_hi; d0 += 32) {
     for (int i = threadIdx.x; i < n * 32; i += 256) {
       const int r = i >> 5, c = i & 31;
       xs[r][c] = (d0 + c < D) ? xb[(long)r * D + d0 + c] : 0.0f;
@@ -70,7 +75,7 @@ gram_kernel(const float* __restrict__ x, double* __restrict__ G, int n, int D) {
 #pragma unroll
   for (int q = 0; q < kMaxPairs; ++q) {
     const int p = threadIdx.x + 256 * q;
-    if (p < pairs) G[(long)t * pairs + p] = acc[q];
+    if (p < pairs) G[((long)t * kGramSplits + split) * pairs + p] = acc[q];
   }
 }
 
@@ -82,12 +87,20 @@ __global__ void __launch_bounds__(256)
 chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) {
   extern __shared__ double A[];   // [n][n]
   __shared__ double piv;
+  __shared__ double diag[kMaxR];
   const int t = blockIdx.x;
-  for (int i = threadIdx.x; i < n * n; i += 256) A[i] = G[(long)t * n * n + i];
+  const double* gb = G + (long)t * kGramSplits * n * n;
+  for (int i = threadIdx.x; i < n * n; i += 256) {
+    double s = gb[i];
+#pragma unroll
+    for (int sp = 1; sp < kGramSplits; ++sp) s += gb[(long)sp * n * n + i];
+    A[i] = s;
+    if (i / n == i % n) diag[i / n] = s;
+  }
   __syncthreads();
   for (int j = 0; j < n; ++j) {
     if (threadIdx.x == 0) {
-      const double p = A[j * n + j], orig = G[(long)t * n * n + j * n + j];
+      const double p = A[j * n + j], orig = diag[j];
       piv = (p > 1e-9 * orig && p > 0.0) ? sqrt(p) : 0.0;
     }
     __syncthreads();
@@ -119,18 +132,22 @@ chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) 
 // mode 0 (w_init, soft_kmeans.py:135-148): w = sum u x / max(sum u, eps) for every cluster, no mask;
 // mode 1 (w_update of soft k-means / EM-Gaussian, soft_kmeans.py:150-166): clusters with sum u <= eps keep their centroid;
 // mode 2 (hard k-means, hard_kmeans.py:138-151): those clusters are zeroed.
-// Thread tile: 8 classes x MJ coordinates (centroids), 8 classes x MN samples (distances); MJ = ceil(r / 16),
+// Thread tile: 4 class PAIRS x MJ coordinates (centroids), 4 class pairs x MN samples (distances); all multiply-adds are
+// packed FFMA2 / FADD2 over the class pair (sm_100 issues two fp32 lanes per instruction).  MJ = ceil(r / 16),
 // MN = ceil(n / 16); rq = 16 MJ.
+constexpr int kUS = kKT + 4;    // row pitch of the u tile (keeps float4 alignment, spreads the staging stores over the banks)
+constexpr int kWS = kKT + 2;    // row pitch of the transposed centroid tile: 64-bit stores of 16 consecutive rows hit 16 bank pairs
+
 template <int MJ, int MN>
 __global__ void __launch_bounds__(256)
 kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__ u, float* __restrict__ coef,
                   float* __restrict__ wt, float* __restrict__ d2, int n, int K, int r, int mode, int want_d2) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
   extern __shared__ float sm[];
-  float* Zs = sm;                    // [NQ][ZP]  (rows >= n and columns >= r are zero)
-  float* us = Zs + NQ * ZP;          // [NQ][kKT] u tile, later the d2 tile
-  float* wts = us + NQ * kKT;        // [kKT][ZP]
-  float* cs = wts + kKT * ZP;        // [kKT] cluster sizes
+  float* Zs = sm;                    // [NQ][ZP]   samples (rows >= n and columns >= r are zero)
+  float* us = Zs + ((NQ * ZP + 3) & ~3);   // [NQ][kUS]  u tile, later the d2 tile (16-byte aligned for the float4 reads)
+  float* nwT = us + NQ * kUS;        // [RQ][kWS]  MINUS the centroids, coordinate-major (class pairs are contiguous)
+  float* cs = nwT + RQ * kWS;        // [kKT]      cluster sizes
   const int t = blockIdx.y, k0 = blockIdx.x * kKT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const float* zb = Z + (long)t * n * zs;
@@ -141,50 +158,56 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   }
   for (int i = tid; i < NQ * kKT; i += 256) {
     const int row = i / kKT, c = i - row * kKT;
-    us[i] = (row < n && k0 + c < K) ? ub[(long)row * K + k0 + c] : 0.0f;
+    us[row * kUS + c] = (row < n && k0 + c < K) ? ub[(long)row * K + k0 + c] : 0.0f;
   }
   __syncthreads();
   if (tid < kKT) {   // cluster sizes in sample order, like u.sum(1)
     float s = 0.0f;
-    for (int i = 0; i < n; ++i) s += us[i * kKT + tid];
+    for (int i = 0; i < n; ++i) s += us[i * kUS + tid];
     cs[tid] = s;
   }
   __syncthreads();
   // centroids of this tile: wt[k, j] = sum_n u[n, k] Z[n, j] / max(cs, eps)
   {
-    float acc[8][MJ];
+    float2 acc[4][MJ];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int m = 0; m < MJ; ++m) acc[i][m] = 0.0f;
+      for (int m = 0; m < MJ; ++m) acc[q][m] = make_float2(0.0f, 0.0f);
     for (int nn = 0; nn < n; ++nn) {
-      const float4 u0 = *reinterpret_cast<const float4*>(us + nn * kKT + ty * 8);
-      const float4 u1 = *reinterpret_cast<const float4*>(us + nn * kKT + ty * 8 + 4);
-      const float uv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-      float zv[MJ];
+      const float4 u0 = *reinterpret_cast<const float4*>(us + nn * kUS + ty * 8);
+      const float4 u1 = *reinterpret_cast<const float4*>(us + nn * kUS + ty * 8 + 4);
+      const float2 uv[4] = {make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y), make_float2(u1.z, u1.w)};
 #pragma unroll
-      for (int m = 0; m < MJ; ++m) zv[m] = Zs[nn * ZP + tx + 16 * m];
+      for (int m = 0; m < MJ; ++m) {
+        const float z = Zs[nn * ZP + tx + 16 * m];
+        const float2 zz = make_float2(z, z);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int m = 0; m < MJ; ++m) acc[i][m] = fmaf(uv[i], zv[m], acc[i][m]);
+        for (int q = 0; q < 4; ++q) acc[q][m] = __ffma2_rn(uv[q], zz, acc[q][m]);
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int kk = ty * 8 + i, k = k0 + kk;
-      const float c = cs[kk];
-      const bool form = (mode == 0) || (c > kEps);
-      float* wrow = wt + ((long)t * K + k) * RQ;
+    for (int q = 0; q < 4; ++q) {
+      const int kk = ty * 8 + 2 * q;
+      const float c0 = cs[kk], c1 = cs[kk + 1];
+      const bool f0 = (mode == 0) || (c0 > kEps), f1 = (mode == 0) || (c1 > kEps);
+      float* w0 = wt + ((long)t * K + k0 + kk) * RQ;
+      float* w1 = w0 + RQ;
 #pragma unroll
       for (int m = 0; m < MJ; ++m) {
         const int j = tx + 16 * m;
-        float val = 0.0f;
-        if (k < K) {
-          if (form) val = acc[i][m] / fmaxf(c, kEps);
-          else if (mode == 1) val = wrow[j];      // empty cluster keeps its centroid
-          if (form || mode == 2) wrow[j] = val;   // (mode 2: zeroed)
+        float v0 = 0.0f, v1 = 0.0f;
+        if (k0 + kk < K) {
+          if (f0) v0 = acc[q][m].x / fmaxf(c0, kEps);
+          else if (mode == 1) v0 = w0[j];       // empty cluster keeps its centroid
+          if (f0 || mode == 2) w0[j] = v0;      // (mode 2: zeroed)
         }
-        wts[kk * ZP + j] = val;
+        if (k0 + kk + 1 < K) {
+          if (f1) v1 = acc[q][m].y / fmaxf(c1, kEps);
+          else if (mode == 1) v1 = w1[j];
+          if (f1 || mode == 2) w1[j] = v1;
+        }
+        *reinterpret_cast<float2*>(nwT + j * kWS + kk) = make_float2(-v0, -v1);
       }
     }
   }
@@ -195,42 +218,43 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
       const int row = i / kKT, kk = i - row * kKT, k = k0 + kk;
       if (k >= K) continue;
       const float c = cs[kk];
-      if (mode == 0 || c > kEps) cb[(long)row * K + k] = us[i] / fmaxf(c, kEps);
+      if (mode == 0 || c > kEps) cb[(long)row * K + k] = us[row * kUS + kk] / fmaxf(c, kEps);
       else if (mode == 2) cb[(long)row * K + k] = 0.0f;
     }
   }
   if (!want_d2) return;
   __syncthreads();
-  // distances: d2[n, k] = sum_j (wt[k, j] - Z[n, j])^2, the reference's direct-difference form
-  float acc[8][MN];
+  // distances: d2[n, k] = sum_j (Z[n, j] - wt[k, j])^2, the reference's direct-difference form
+  float2 acc[4][MN];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int m = 0; m < MN; ++m) acc[i][m] = 0.0f;
+    for (int m = 0; m < MN; ++m) acc[q][m] = make_float2(0.0f, 0.0f);
   for (int j = 0; j < r; ++j) {
-    float wv[8], zv[MN];
+    float2 nw[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) wv[i] = wts[(ty * 8 + i) * ZP + j];
+    for (int q = 0; q < 4; ++q) nw[q] = *reinterpret_cast<const float2*>(nwT + j * kWS + ty * 8 + 2 * q);
 #pragma unroll
-    for (int m = 0; m < MN; ++m) zv[m] = Zs[(tx + 16 * m) * ZP + j];
+    for (int m = 0; m < MN; ++m) {
+      const float z = Zs[(tx + 16 * m) * ZP + j];
+      const float2 zz = make_float2(z, z);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int m = 0; m < MN; ++m) {
-        const float df = wv[i] - zv[m];
-        acc[i][m] = fmaf(df, df, acc[i][m]);
+      for (int q = 0; q < 4; ++q) {
+        const float2 df = __fadd2_rn(zz, nw[q]);
+        acc[q][m] = __ffma2_rn(df, df, acc[q][m]);
       }
+    }
   }
   // through shared memory (the u tile is dead) so that the rows go out coalesced
 #pragma unroll
   for (int m = 0; m < MN; ++m)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) us[(tx + 16 * m) * kKT + ty * 8 + i] = acc[i][m];
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(us + (tx + 16 * m) * kUS + ty * 8 + 2 * q) = acc[q][m];
   __syncthreads();
   float* db = d2 + (long)t * n * K;
   for (int i = tid; i < n * kKT; i += 256) {
     const int row = i / kKT, kk = i - row * kKT;
-    if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[i];
+    if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[row * kUS + kk];
   }
 }
 
@@ -238,7 +262,7 @@ template <int MJ, int MN>
 cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
                         int r, int mode, int want_d2, cudaStream_t st) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
-  const size_t smem = sizeof(float) * ((size_t)NQ * ZP + (size_t)NQ * kKT + (size_t)kKT * ZP + kKT);
+  const size_t smem = sizeof(float) * ((size_t)NQ * ZP + 4 + (size_t)NQ * kUS + (size_t)RQ * kWS + kKT);
   static PerDeviceFlags attr_set;
   const int slot = current_device_slot();
   if (smem > 48 * 1024 && (slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0)) {
@@ -344,7 +368,7 @@ size_t kmeans_run_workspace_bytes(const KMeansRun& p) {
     const size_t rq = coord_pitch(p.n, p.D);
     b += align_up(sizeof(float) * T * K * rq);           // wt
     if (D > n) {
-      b += align_up(sizeof(double) * T * n * n);         // G
+      b += align_up(sizeof(double) * T * kGramSplits * n * n);   // G (partial sums)
       b += align_up(sizeof(float) * T * n * rq);         // Z
     }
   } else if (!p.w) {
@@ -387,9 +411,9 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
     const int rq = coord_pitch(n, D);
     wt = static_cast<float*>(take(sizeof(float) * (size_t)T * K * rq));
     if (D > n) {
-      double* G = static_cast<double*>(take(sizeof(double) * (size_t)T * n * n));
+      double* G = static_cast<double*>(take(sizeof(double) * (size_t)T * kGramSplits * n * n));
       float* Zc = static_cast<float*>(take(sizeof(float) * (size_t)T * n * rq));
-      gram_kernel<<<T, 256, 0, st>>>(p.x, G, n, D);
+      gram_kernel<<<dim3(T, kGramSplits), 256, 0, st>>>(p.x, G, n, D);
       const size_t smem = sizeof(double) * (size_t)n * n;
       if (smem > 48 * 1024) KM_TRY(cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       chol_kernel<<<T, 256, smem, st>>>(G, Zc, n, rq);

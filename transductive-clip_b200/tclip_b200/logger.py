@@ -8,16 +8,41 @@ once per (logger name, sink) with a use count: every line is written once per si
 and a sink is closed only when its last user calls ``del_logger``."""
 from __future__ import annotations
 
+import collections
 import logging
 import os
 import threading
 
 _LOCK = threading.Lock()
 _SINKS: dict = {}   # (logger name, sink) -> [handler, use count]; sink = None for the console, else the absolute path
+# Releases come from ``__del__`` (the reference's classes close their logger there), i.e. from the garbage collector, which
+# can run inside ANY allocation — also inside the critical section below, on the same thread.  A release therefore never
+# blocks: it is queued, and applied by whoever holds the lock next (a blocking acquire there would deadlock on itself).
+_PENDING: collections.deque = collections.deque()
+
+
+def _drain_locked():
+    while True:
+        try:
+            logger, key = _PENDING.popleft()
+        except IndexError:
+            return
+        entry = _SINKS.get(key)
+        if entry is None:
+            continue
+        entry[1] -= 1
+        if entry[1] <= 0:
+            del _SINKS[key]
+            logger.removeHandler(entry[0])
+            try:
+                entry[0].close()
+            except Exception:
+                pass
 
 
 def _acquire(logger: logging.Logger, key, make):
     with _LOCK:
+        _drain_locked()
         entry = _SINKS.get(key)
         if entry is None:
             handler = make()
@@ -28,18 +53,12 @@ def _acquire(logger: logging.Logger, key, make):
 
 
 def _release(logger: logging.Logger, key):
-    with _LOCK:
-        entry = _SINKS.get(key)
-        if entry is None:
-            return
-        entry[1] -= 1
-        if entry[1] <= 0:
-            del _SINKS[key]
-            logger.removeHandler(entry[0])
-            try:
-                entry[0].close()
-            except Exception:
-                pass
+    _PENDING.append((logger, key))
+    if _LOCK.acquire(blocking=False):
+        try:
+            _drain_locked()
+        finally:
+            _LOCK.release()
 
 
 class Logger:
