@@ -661,7 +661,8 @@ def bench_kmeans(a):
     h.close()
 
 
-KM_TRAFFIC = {}   # (K, T, D) -> dram bytes per kproj_iter_kernel launch, filled in from profiles/r2_kmeans.md
+KM_TRAFFIC = {(1000, 100, 1024): 72.65e6}   # (K, T, D) -> dram__bytes_read.sum + dram__bytes_write.sum of one kproj_iter_kernel
+                                             # launch (ncu --set full, profiles/r2_kmeans.md)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
