@@ -731,7 +731,7 @@ def bench_config5(a):
             t0 = time.time()
             idx = draw(b)
             t_draw += time.time() - t0
-            futures.append(h.pipe._pool.submit(h.pipe._run, run_batch, idx))
+            futures.append(h.pipe.submit(run_batch, idx))
         accs = [f.result() for f in futures]
     else:
         accs = []

@@ -677,8 +677,7 @@ int tclip_kmeans_run(const tclip_kmeans_problem* p, void* workspace, size_t work
   tclip::KMeansRun r{};
   if (int rc = kmeans_validate(p, &r)) return rc;
   const bool coords = tclip::kmeans_sample_coordinates(r.n, r.D);
-  if (!p->x || !p->u || !p->labels || !p->criterions || (p->method == 1 && !p->v) || (coords && !p->coef) ||
-      (!coords && !p->w && false))
+  if (!p->x || !p->u || !p->labels || !p->criterions || (p->method == 1 && !p->v) || (coords && !p->coef))
     return fail(TCLIP_ERR_INVALID, "tclip_kmeans_run: x/u/labels/criterions (+ v for EM-Gaussian, coef in sample coordinates) must be set");
   const size_t need = tclip::kmeans_run_workspace_bytes(r);
   if (!workspace || workspace_bytes < need)

@@ -45,9 +45,14 @@ class BatchPipeline:
             self._local.stream.synchronize()  # the batch is complete (and its scratch reusable) when the call returns
         return out
 
+    def submit(self, fn: Callable, item):
+        """Queue one call; returns a ``concurrent.futures.Future`` (for callers that produce their batches one by one, e.g. an
+        index sampler that must draw in order on the submitting thread)."""
+        return self._pool.submit(self._run, fn, item)
+
     def map(self, fn: Callable, items: Iterable) -> List:
         """``[fn(item) for item in items]`` with up to ``streams`` calls in flight; results in submission order."""
-        futures = [self._pool.submit(self._run, fn, it) for it in items]
+        futures = [self.submit(fn, it) for it in items]
         return [f.result() for f in futures]
 
     def close(self):
