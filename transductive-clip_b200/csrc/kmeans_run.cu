@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "tclip_kernels.cuh"
 
@@ -33,7 +34,6 @@ namespace tclip {
 namespace {
 
 constexpr float kEps = 1e-15f;
-constexpr int kKT = 128;      // classes per CTA of the iteration kernel
 constexpr int kMaxR = 96;     // largest coordinate count (and sample count) of the sample-coordinate form
 constexpr int kMaxPairs = (kMaxR * kMaxR + 255) / 256;
 
@@ -123,7 +123,7 @@ chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) 
   }
 }
 
-// One outer iteration's M-step and distances for a tile of kKT classes of one task, in sample coordinates.
+// One outer iteration's M-step and distances for a tile of KT classes of one task, in sample coordinates.
 //   Z    [T, n, zs]   coordinates of the samples (Cholesky rows, or the features themselves), r used columns
 //   u    [T, n, K]    responsibilities the centroids are formed from
 //   coef [T, n, K]    out: u / max(colsum, eps) for the clusters whose centroid is (re)formed; kept / zeroed otherwise
@@ -135,20 +135,21 @@ chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) 
 // Thread tile: 4 class PAIRS x MJ coordinates (centroids), 4 class pairs x MN samples (distances); all multiply-adds are
 // packed FFMA2 / FADD2 over the class pair (sm_100 issues two fp32 lanes per instruction).  MJ = ceil(r / 16),
 // MN = ceil(n / 16); rq = 16 MJ.
-constexpr int kUS = kKT + 4;    // row pitch of the u tile (keeps float4 alignment, spreads the staging stores over the banks)
-constexpr int kWS = kKT + 2;    // row pitch of the transposed centroid tile: 64-bit stores of 16 consecutive rows hit 16 bank pairs
-
-template <int MJ, int MN>
+// KT classes per CTA (128: 4 class pairs per thread, 107 KB of shared memory = 2 CTAs per SM at RN50 shape; 64: 2 pairs, 69 KB =
+// 3 CTAs per SM).  kUS: row pitch of the u tile (keeps float4 / float2 alignment, spreads the staging stores over the banks);
+// kWS: row pitch of the transposed centroid tile (64-bit stores of 16 consecutive rows hit 16 bank pairs).
+template <int MJ, int MN, int KT>
 __global__ void __launch_bounds__(256)
 kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__ u, float* __restrict__ coef,
                   float* __restrict__ wt, float* __restrict__ d2, int n, int K, int r, int mode, int want_d2) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
+  constexpr int kUS = KT + 4, kWS = KT + 2, CPT = KT / 16, PQ = CPT / 2;   // classes / class pairs per thread
   extern __shared__ float sm[];
   float* Zs = sm;                    // [NQ][ZP]   samples (rows >= n and columns >= r are zero)
   float* us = Zs + ((NQ * ZP + 3) & ~3);   // [NQ][kUS]  u tile, later the d2 tile (16-byte aligned for the float4 reads)
   float* nwT = us + NQ * kUS;        // [RQ][kWS]  MINUS the centroids, coordinate-major (class pairs are contiguous)
-  float* cs = nwT + RQ * kWS;        // [kKT]      cluster sizes
-  const int t = blockIdx.y, k0 = blockIdx.x * kKT;
+  float* cs = nwT + RQ * kWS;        // [KT]      cluster sizes
+  const int t = blockIdx.y, k0 = blockIdx.x * KT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const float* zb = Z + (long)t * n * zs;
   const float* ub = u + (long)t * n * K;
@@ -156,12 +157,12 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
     const int row = i / RQ, c = i - row * RQ;
     Zs[row * ZP + c] = (row < n && c < r) ? zb[(long)row * zs + c] : 0.0f;
   }
-  for (int i = tid; i < NQ * kKT; i += 256) {
-    const int row = i / kKT, c = i - row * kKT;
+  for (int i = tid; i < NQ * KT; i += 256) {
+    const int row = i / KT, c = i - row * KT;
     us[row * kUS + c] = (row < n && k0 + c < K) ? ub[(long)row * K + k0 + c] : 0.0f;
   }
   __syncthreads();
-  if (tid < kKT) {   // cluster sizes in sample order, like u.sum(1)
+  if (tid < KT) {   // cluster sizes in sample order, like u.sum(1)
     float s = 0.0f;
     for (int i = 0; i < n; ++i) s += us[i * kUS + tid];
     cs[tid] = s;
@@ -169,26 +170,30 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   __syncthreads();
   // centroids of this tile: wt[k, j] = sum_n u[n, k] Z[n, j] / max(cs, eps)
   {
-    float2 acc[4][MJ];
+    float2 acc[PQ][MJ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < PQ; ++q)
 #pragma unroll
       for (int m = 0; m < MJ; ++m) acc[q][m] = make_float2(0.0f, 0.0f);
     for (int nn = 0; nn < n; ++nn) {
-      const float4 u0 = *reinterpret_cast<const float4*>(us + nn * kUS + ty * 8);
-      const float4 u1 = *reinterpret_cast<const float4*>(us + nn * kUS + ty * 8 + 4);
-      const float2 uv[4] = {make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y), make_float2(u1.z, u1.w)};
+      float2 uv[PQ];
+#pragma unroll
+      for (int q = 0; q < PQ; q += 2) {
+        const float4 u4 = *reinterpret_cast<const float4*>(us + nn * kUS + ty * CPT + 2 * q);
+        uv[q] = make_float2(u4.x, u4.y);
+        uv[q + 1] = make_float2(u4.z, u4.w);
+      }
 #pragma unroll
       for (int m = 0; m < MJ; ++m) {
         const float z = Zs[nn * ZP + tx + 16 * m];
         const float2 zz = make_float2(z, z);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q][m] = __ffma2_rn(uv[q], zz, acc[q][m]);
+        for (int q = 0; q < PQ; ++q) acc[q][m] = __ffma2_rn(uv[q], zz, acc[q][m]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int kk = ty * 8 + 2 * q;
+    for (int q = 0; q < PQ; ++q) {
+      const int kk = ty * CPT + 2 * q;
       const float c0 = cs[kk], c1 = cs[kk + 1];
       const bool f0 = (mode == 0) || (c0 > kEps), f1 = (mode == 0) || (c1 > kEps);
       float* w0 = wt + ((long)t * K + k0 + kk) * RQ;
@@ -214,8 +219,8 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   // coefficients of the centroids in terms of the samples (what tclip_kmeans_expand_centroids turns into w)
   {
     float* cb = coef + (long)t * n * K;
-    for (int i = tid; i < n * kKT; i += 256) {
-      const int row = i / kKT, kk = i - row * kKT, k = k0 + kk;
+    for (int i = tid; i < n * KT; i += 256) {
+      const int row = i / KT, kk = i - row * KT, k = k0 + kk;
       if (k >= K) continue;
       const float c = cs[kk];
       if (mode == 0 || c > kEps) cb[(long)row * K + k] = us[row * kUS + kk] / fmaxf(c, kEps);
@@ -225,21 +230,21 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   if (!want_d2) return;
   __syncthreads();
   // distances: d2[n, k] = sum_j (Z[n, j] - wt[k, j])^2, the reference's direct-difference form
-  float2 acc[4][MN];
+  float2 acc[PQ][MN];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < PQ; ++q)
 #pragma unroll
     for (int m = 0; m < MN; ++m) acc[q][m] = make_float2(0.0f, 0.0f);
   for (int j = 0; j < r; ++j) {
-    float2 nw[4];
+    float2 nw[PQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) nw[q] = *reinterpret_cast<const float2*>(nwT + j * kWS + ty * 8 + 2 * q);
+    for (int q = 0; q < PQ; ++q) nw[q] = *reinterpret_cast<const float2*>(nwT + j * kWS + ty * CPT + 2 * q);
 #pragma unroll
     for (int m = 0; m < MN; ++m) {
       const float z = Zs[(tx + 16 * m) * ZP + j];
       const float2 zz = make_float2(z, z);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < PQ; ++q) {
         const float2 df = __fadd2_rn(zz, nw[q]);
         acc[q][m] = __ffma2_rn(df, df, acc[q][m]);
       }
@@ -249,30 +254,43 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
 #pragma unroll
   for (int m = 0; m < MN; ++m)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(us + (tx + 16 * m) * kUS + ty * 8 + 2 * q) = acc[q][m];
+    for (int q = 0; q < PQ; ++q) *reinterpret_cast<float2*>(us + (tx + 16 * m) * kUS + ty * CPT + 2 * q) = acc[q][m];
   __syncthreads();
   float* db = d2 + (long)t * n * K;
-  for (int i = tid; i < n * kKT; i += 256) {
-    const int row = i / kKT, kk = i - row * kKT;
+  for (int i = tid; i < n * KT; i += 256) {
+    const int row = i / KT, kk = i - row * KT;
     if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[row * kUS + kk];
   }
 }
 
-template <int MJ, int MN>
-cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
-                        int r, int mode, int want_d2, cudaStream_t st) {
-  constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
-  const size_t smem = sizeof(float) * ((size_t)NQ * ZP + 4 + (size_t)NQ * kUS + (size_t)RQ * kWS + kKT);
+template <int MJ, int MN, int KT>
+cudaError_t launch_iter_kt(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
+                           int r, int mode, int want_d2, cudaStream_t st) {
+  constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1, kUS = KT + 4, kWS = KT + 2;
+  const size_t smem = sizeof(float) * ((size_t)NQ * ZP + 4 + (size_t)NQ * kUS + (size_t)RQ * kWS + KT);
   static PerDeviceFlags attr_set;
   const int slot = current_device_slot();
   if (smem > 48 * 1024 && (slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0)) {
-    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
   }
-  kproj_iter_kernel<MJ, MN><<<dim3((K + kKT - 1) / kKT, T), 256, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2);
+  kproj_iter_kernel<MJ, MN, KT><<<dim3((K + KT - 1) / KT, T), 256, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2);
   note_launch();
   return cudaGetLastError();
+}
+
+// classes per CTA: 128; TCLIP_KM_TILE=64 selects the 64-class tile (3 CTAs per SM at RN50 shape instead of 2) — measured equal
+// (0.172 vs 0.173 ms per iteration, profiles/r2_kmeans.md): the kernel is not limited by occupancy
+template <int MJ, int MN>
+cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
+                        int r, int mode, int want_d2, cudaStream_t st) {
+  static const int tile = [] {
+    const char* e = std::getenv("TCLIP_KM_TILE");
+    return (e && std::atoi(e) == 64) ? 64 : 128;
+  }();
+  if (tile == 128) return launch_iter_kt<MJ, MN, 128>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+  return launch_iter_kt<MJ, MN, 64>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
 }
 
 template <int MJ>
