@@ -60,6 +60,7 @@ MUFU_PER_UPDATE = 5.0       # this kernel: rcp X, rcp P, lg2 P, sqrt, rcp (tclip
 SEED = 2020                 # the reference's default seed (config/datasets_config/*.yaml:10)
 CPU_SAMPLE_TASKS = 2         # tasks in the bounded CPU sample (one run_task batch)
 CPU_SAMPLE_STEADY = 2        # full 1000-iteration outer iterations timed after outer iteration 0
+REF_SAMPLE_TASKS = 2         # tasks per step of the `--impl reference` arm (one batch; outer iteration 0 + one full one)
 KM_CLASSES, KM_DIM, KM_TASKS_PER_BATCH = 1000, 1024, 100   # BASELINE config 4
 
 
@@ -83,9 +84,14 @@ def parse():
     ap.add_argument("--classes", type=int, default=None)
     ap.add_argument("--tasks-per-batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--classes-per-task", default="3,10",
+                    help="lo,hi: true classes per synthetic task, uniform (3,10 = the reference's sampler, src/sampler_zero_shot.py:54, "
+                         "and the metric's workload; e.g. 20,30 keeps ~25 clusters per task alive: profiles/r2_workload_sweep.md)")
+    ap.add_argument("--noise", type=float, default=None, help="noise scale of the synthetic embeddings (default 9, SURVEY.md §8(d))")
     ap.add_argument("--streams", type=int, default=4,
                     help="run_task batches in flight per GPU (own CUDA stream + host thread each); 1 = strictly serial")
     a = ap.parse_args()
+    a.k_eff_range = tuple(int(v) for v in a.classes_per_task.split(","))
     km = a.method in KMEANS
     if a.classes is None:
         a.classes = KM_CLASSES if km else K_CLASSES
@@ -101,8 +107,17 @@ def workload_name(a):
                 f"batch_size {a.tasks_per_batch} tasks per run_task, iter {it})"), it
     it = 20 if a.method == "em" else 10
     nm = "EM-Dirichlet" if a.method == "em" else "Hard EM-Dirichlet"
+    variant = "" if (a.k_eff_range == (3, 10) and a.noise is None) else \
+        f"; NOT the metric's generator: {a.k_eff_range[0]}..{a.k_eff_range[1]} classes per task, noise {a.noise if a.noise is not None else 9.0}"
     return (f"{nm} zero-shot, synthetic ImageNet-shape softmax features (K=D={a.classes}, n_query={N_QUERY}, "
-            f"batch_size {a.tasks_per_batch} tasks per run_task, iter {it}, iter_mm 1000)"), it
+            f"batch_size {a.tasks_per_batch} tasks per run_task, iter {it}, iter_mm 1000{variant})"), it
+
+
+def gen_kwargs(a):
+    kw = {"k_eff_range": a.k_eff_range}
+    if a.noise is not None:
+        kw["noise"] = a.noise
+    return kw
 
 
 def metric_name(a):
@@ -191,7 +206,7 @@ def cpu_sample(a, iters_full: int, n_tasks: int = CPU_SAMPLE_TASKS, n_steady: in
                 "sample": (f"oracle/restated.py kmeans_family (torch CPU fp32, {cores} threads, feature-space loop as the reference) on "
                            f"one batch of {n_tasks} tasks D={KM_DIM} K={a.classes}, all {iters_full} iterations + accuracy: {wall:.1f} s"),
                 "seconds_measured": wall}
-    td, _ = tasks.make_zero_shot_batch(n_tasks, a.classes, n_query=N_QUERY, seed=SEED, batch_index=10_000)
+    td, _ = tasks.make_zero_shot_batch(n_tasks, a.classes, n_query=N_QUERY, seed=SEED, batch_index=10_000, **gen_kwargs(a))
     t0 = time.time()
     n_it = min(1 + n_steady, iters_full)
     r = restated.dirichlet_zero_shot(td["x_q"], td["y_q"], a.classes, iters=n_it, hard=(a.method == "hard"))
@@ -213,9 +228,9 @@ def cpu_sample(a, iters_full: int, n_tasks: int = CPU_SAMPLE_TASKS, n_steady: in
 
 
 def run_reference(a):
-    """``--impl reference``: every step is one bounded CPU sample (1 task, outer iteration 0 + one full 1000-iteration outer
-    iteration for the Dirichlet methods; 1 task, all iterations for the k-means family), all ``--steps`` of them are run, the
-    line's value is their median."""
+    """``--impl reference``: every step is one bounded CPU sample (one batch of 2 tasks; outer iteration 0 + one full
+    1000-iteration outer iteration for the Dirichlet methods, all iterations for the k-means family), all ``--steps`` of them
+    are run, the line's value is their median."""
     import statistics
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -223,7 +238,7 @@ def run_reference(a):
     name, iters_full = workload_name(a)
     vals, last = [], None
     for i in range(min(a.warmup, 1) + a.steps):          # one real warm-up (thread pool, allocator) is enough on the CPU
-        last = cpu_sample(a, iters_full, n_tasks=1, n_steady=1)
+        last = cpu_sample(a, iters_full, n_tasks=REF_SAMPLE_TASKS, n_steady=1)
         if i >= min(a.warmup, 1):
             vals.append(last["value"])
     v = statistics.median(vals)
@@ -233,8 +248,8 @@ def run_reference(a):
         "impl": "reference", "metric": metric_name(a), "value": v, "unit": "tasks/s",
         "n_gpus": a.gpus, "steps": len(vals), "warmup": a.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "note": "CPU arm: one step = one bounded sample (1 task; Dirichlet: outer iteration 0 + one "
-                   "full outer iteration, extrapolated per task); value = median over the steps; host cores only, no GPU"},
+        "config": {"workload": name, "note": "CPU arm: one step = one bounded sample (one batch of %d tasks; Dirichlet: outer iteration 0 + one "
+                   "full outer iteration, extrapolated per task); value = median over the steps; host cores only, no GPU" % REF_SAMPLE_TASKS},
         "cpu_baseline": last,
         "e2e": {"value": v, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -378,7 +393,7 @@ def bench_dirichlet(a):
     # synthetic batches, one per step and rank, generated before anything is timed; pinned host memory
     host = []
     for s in range(n_steps):
-        td, _ = tasks.make_zero_shot_batch(T, K, n_query=N_QUERY, seed=SEED, batch_index=s * world + rank)
+        td, _ = tasks.make_zero_shot_batch(T, K, n_query=N_QUERY, seed=SEED, batch_index=s * world + rank, **gen_kwargs(a))
         host.append({k: v.pin_memory() for k, v in td.items()})
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
 
