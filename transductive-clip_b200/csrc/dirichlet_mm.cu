@@ -707,7 +707,9 @@ constexpr auto make_table(std::integer_sequence<int, I...>) {
 // NP = ceil(D / 64) pairs dealt to W = min(4, NP) warps, NPW = ceil(NP / W) pairs each.  The kernel is issue-bound on the
 // SMs that hold two rows, and every warp repeats the row total and psi(s): 4 warps x 4 pairs measured 1.1 ms per
 // 1000-iteration M-step of 224 rows, 8 x 2 1.3 ms, 16 x 1 1.8 ms, 2 x 8 1.4 ms (profiles/r1_spec_kernel.md; measured
-// through an environment knob that commit 565e2b8 still has, removed since).
+// through an environment knob that commit 565e2b8 still has, removed since).  Round 2, with 4 batches in flight (where the
+// SMs' issue rate, not the dependent chain, is the limit): 2 x 8 (12 % fewer instructions per row-iteration, 255 registers)
+// 2929 tasks/s against 3108 for 4 x 4 — fewer, fatter warps lose there too.
 SpecFn spec_fn(int np) {
   switch (np) {
     case 1: return &launch_spec<1, 1>;
