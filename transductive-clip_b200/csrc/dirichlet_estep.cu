@@ -11,6 +11,8 @@
 //
 // Layouts (all row-major, innermost last): u [T,n,K], logz [T,n,D], alpha/y/work [T,K,D], colsum/v [T,K].
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <math_constants.h>
 
 #include <cstdlib>
@@ -240,25 +242,25 @@ __global__ void __launch_bounds__(128)
 commit_kernel(float* __restrict__ alpha, const float* __restrict__ work, const int* __restrict__ live,
               const int* __restrict__ dead_age, double2* __restrict__ rowstat, int rows, int D) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  // a cluster that was already empty in the previous outer iteration has the same alpha row as then: its
-  // (0, ||alpha||^2) entry written by that commit is still right
-  if (dead_age && dead_age[row] >= 2) return;
-  const bool lv = live ? live[row] != 0 : true;
-  float* a = alpha + (long)row * D;
-  const float* w = work + (long)row * D;
-  float dsq = 0.0f, osq = 0.0f;
-  for (int d = lane; d < D; d += 32) {
-    const float o = a[d];
-    const float nw = lv ? w[d] : o;
-    const float df = o - nw;
-    dsq = fmaf(df, df, dsq);
-    osq = fmaf(o, o, osq);
-    if (lv) a[d] = nw;
+  for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 4) {   // capped grid, warps stride
+    // a cluster that was already empty in the previous outer iteration has the same alpha row as then: its
+    // (0, ||alpha||^2) entry written by that commit is still right
+    if (dead_age && dead_age[row] >= 2) continue;
+    const bool lv = live ? live[row] != 0 : true;
+    float* a = alpha + (long)row * D;
+    const float* w = work + (long)row * D;
+    float dsq = 0.0f, osq = 0.0f;
+    for (int d = lane; d < D; d += 32) {
+      const float o = a[d];
+      const float nw = lv ? w[d] : o;
+      const float df = o - nw;
+      dsq = fmaf(df, df, dsq);
+      osq = fmaf(o, o, osq);
+      if (lv) a[d] = nw;
+    }
+    const double ds = warp_sum_f64((double)dsq), os = warp_sum_f64((double)osq);
+    if (lane == 0) rowstat[row] = make_double2(ds, os);
   }
-  const double ds = warp_sum_f64((double)dsq), os = warp_sum_f64((double)osq);
-  if (lane == 0) rowstat[row] = make_double2(ds, os);
 }
 
 // criterion[t] = ||alpha_old - alpha||_F / ||alpha_old||_F: one CTA per task (fixed reduction tree), then the mean over
@@ -301,47 +303,22 @@ __global__ void criterion_mean_kernel(const float* __restrict__ task_crit, float
 __global__ void __launch_bounds__(128)
 lognorm_kernel(const float* __restrict__ alpha, double* __restrict__ norm, const int* __restrict__ live, int rows,
                int D, const int* __restrict__ gate) {
-  if (!dense_selected(gate)) return;  // few live rows: lognorm_rows_kernel
+  if (!dense_selected(gate)) return;  // few live rows: estep_task_kernel
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  if (live && !live[row]) return;  // empty cluster: alpha row unchanged, norm[row] of the previous E-step still holds
-  const float* a = alpha + (long)row * D;
-  double s = 0.0, lg = 0.0;
-  for (int d = lane; d < D; d += 32) {
-    const double v = (double)a[d];
-    s += v;
-    lg += lgamma(v);
+  // warps stride over the rows (a capped grid: when the gate is closed the launch costs a few hundred CTAs, not rows / 4)
+  for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 4) {
+    if (live && !live[row]) continue;  // empty cluster: alpha row unchanged, norm[row] of the previous E-step still holds
+    const float* a = alpha + (long)row * D;
+    double s = 0.0, lg = 0.0;
+    for (int d = lane; d < D; d += 32) {
+      const double v = (double)a[d];
+      s += v;
+      lg += lgamma(v);
+    }
+    s = warp_sum_f64(s);
+    lg = warp_sum_f64(lg);
+    if (lane == 0) norm[row] = lgamma(s) - lg;
   }
-  s = warp_sum_f64(s);
-  lg = warp_sum_f64(lg);
-  if (lane == 0) norm[row] = lgamma(s) - lg;
-}
-
-// Few live rows (skip-dead schedule): one CTA per live row, its D lgamma evaluations dealt to four warps.
-__global__ void __launch_bounds__(128)
-lognorm_rows_kernel(const float* __restrict__ alpha, double* __restrict__ norm, const int* __restrict__ rows,
-                    const int* __restrict__ n_rows, int D, const int* __restrict__ gate) {
-  if (dense_selected(gate)) return;
-  if ((int)blockIdx.x >= *n_rows) return;
-  __shared__ double ps[4], pl[4];
-  const int row = rows[blockIdx.x];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* a = alpha + (long)row * D;
-  double s = 0.0, lg = 0.0;
-  for (int d = threadIdx.x; d < D; d += 128) {
-    const double v = (double)a[d];
-    s += v;
-    lg += lgamma(v);
-  }
-  s = warp_sum_f64(s);
-  lg = warp_sum_f64(lg);
-  if (lane == 0) {
-    ps[warp] = s;
-    pl[warp] = lg;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) norm[row] = lgamma((ps[0] + ps[1]) + (ps[2] + ps[3])) - ((pl[0] + pl[1]) + (pl[2] + pl[3]));
 }
 
 // ---- contraction l3[t,n,k] = sum_d logz[t,n,d] (alpha[t,k,d] - 1): [n x D] . [D x K] per task ---------------------
@@ -403,53 +380,15 @@ logits_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, f
   }
 }
 
-// Row-wise form for the skip-dead schedule: only the columns of live clusters change between E-steps (an empty cluster
-// keeps its alpha row, hence its column of l3), so one CTA per live row recomputes l3[t, :, k].
-__global__ void __launch_bounds__(256)
-logits_rows_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, float* __restrict__ l3,
-                   const int* __restrict__ rows, const int* __restrict__ n_rows, int n, int K, int D,
-                   const int* __restrict__ gate) {
-  if (dense_selected(gate)) return;
-  if ((int)blockIdx.x >= *n_rows) return;
-  extern __shared__ float am1[];  // [D] alpha - 1
-  const int row = rows[blockIdx.x];
-  const int t = row / K, k = row % K;
-  const float* a = alpha + (long)row * D;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) am1[d] = a[d] - 1.0f;
-  __syncthreads();
-  // a warp takes four queries at a time: lanes stride over d (coalesced 128-byte reads of log z), four independent
-  // accumulators, one shuffle tree each
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  for (int n0 = warp * 4; n0 < n; n0 += n_warps * 4) {
-    const float* z0 = logz + ((long)t * n + n0) * D;
-    const int nq = min(4, n - n0);
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 4
-    for (int d = lane; d < D; d += 32) {
-      const float b = am1[d];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < nq) acc[q] = fmaf(z0[(long)q * D + d], b, acc[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float tot = warp_sum_f32(acc[q]);
-      if (lane == 0 && q < nq) l3[((long)t * n + n0 + q) * K + k] = tot;
-    }
-  }
-}
-
 // ---- responsibilities: u = softmax_k(norm + l3 + lambda v / n); optional argmax -> one-hot ------------------------
 // One warp per (task, query).  labels = argmax of the *softmaxed* float32 values, first index wins
 // (hard_em_dirichlet.py:256-258).  `u` may alias `l3` (each warp reads its row before overwriting it).
 // K <= 1024: the 32 logits of a lane stay in registers (one pass over l3 / norm / v, one expf per element); same
 // arithmetic and the same per-lane summation order as the general kernel below => identical results.
-__global__ void __launch_bounds__(128)
-softmax_reg_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
-                   float* u, int* __restrict__ labels, int rows, int n, int K, int hard) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+// (l3, norm: no __restrict__ — estep_task_kernel writes both earlier in the same kernel and must read them coherently)
+__device__ __forceinline__ void softmax_row_reg(const float* l3, const double* norm, const float* __restrict__ v,
+                                                float lambd, float* u, int* __restrict__ labels, int row, int lane, int n,
+                                                int K, int hard) {
   const int t = row / n;
   const float* x = l3 + (long)row * K;
   const double* nm = norm + (long)t * K;
@@ -505,12 +444,20 @@ softmax_reg_kernel(const float* l3, const double* __restrict__ norm, const float
   if (lane == 0 && labels) labels[row] = best_k;
 }
 
+// `gate`: in the skip-dead schedule the dense E-step kernels run iff more live rows than the row-wise cap (else
+// estep_task_kernel takes the whole E-step of a task)
 __global__ void __launch_bounds__(128)
-softmax_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
-               float* u, int* __restrict__ labels, int rows, int n, int K, int hard) {
-  const int lane = threadIdx.x & 31;
+softmax_reg_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
+                   float* u, int* __restrict__ labels, int rows, int n, int K, int hard, const int* __restrict__ gate) {
+  if (!dense_selected(gate)) return;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  softmax_row_reg(l3, norm, v, lambd, u, labels, row, threadIdx.x & 31, n, K, hard);
+}
+
+__device__ __forceinline__ void softmax_row_gen(const float* l3, const double* norm, const float* __restrict__ v,
+                                                float lambd, float* u, int* __restrict__ labels, int row, int lane, int n,
+                                                int K, int hard) {
   const int t = row / n;
   const float* x = l3 + (long)row * K;
   const double* nm = norm + (long)t * K;
@@ -554,6 +501,119 @@ softmax_kernel(const float* l3, const double* __restrict__ norm, const float* __
     for (int k = lane; k < K; k += 32) out[k] = (k == best_k) ? 1.0f : 0.0f;
   }
   if (lane == 0 && labels) labels[row] = best_k;
+}
+
+__global__ void __launch_bounds__(128)
+softmax_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
+               float* u, int* __restrict__ labels, int rows, int n, int K, int hard, const int* __restrict__ gate) {
+  if (!dense_selected(gate)) return;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  softmax_row_gen(l3, norm, v, lambd, u, labels, row, threadIdx.x & 31, n, K, hard);
+}
+
+// ---- the whole E-step of one task in ONE kernel, for the skip-dead schedule with few live rows --------------------------
+// get_logits + u_update (em_dirichlet.py:28-40,132-143; hard arg-max hard_em_dirichlet.py:256-258) for the clusters that are
+// alive: an empty cluster keeps its alpha row, hence its log-normaliser and its column of l3, so per task only the live
+// classes are recomputed — log-normaliser (float64 lgamma sums), contraction column l3[t, :, k] — and then the soft-max rows of
+// the task's queries are formed from the persistent l3 / norm.  One launch (a CTA of 512 threads per task and slice of 16
+// queries: every slice recomputes the task's few log-normalisers, writes identical values, and owns its queries' l3 entries and
+// soft-max rows) replaces three (log-normaliser and contraction with one CTA per live row, then the soft-max of all rows);
+// every value is produced by the same per-thread operation sequence as in the dense kernels (same lane partition, same
+// shuffle trees), so the results are bit-identical to them.
+constexpr int kTaskThreads = 512;
+constexpr int kTaskWarps = kTaskThreads / 32;
+constexpr int kTaskRowsPerPass = 8;   // live classes whose alpha - 1 rows are staged in shared memory at a time
+constexpr int kTaskSlice = 16;        // queries per CTA (a multiple of the 4-query groups of the contraction)
+
+__global__ void __launch_bounds__(kTaskThreads)
+estep_task_kernel(const float* __restrict__ alpha, const float* __restrict__ logz, const float* __restrict__ v, float lambd,
+                  double* __restrict__ norm, float* l3, float* u, int* __restrict__ labels, const int* __restrict__ live,
+                  int n, int K, int D, int hard, const int* __restrict__ gate) {
+  if (dense_selected(gate)) return;
+  extern __shared__ float am1[];               // [kTaskRowsPerPass][D] alpha - 1 of the classes of this pass
+  __shared__ int cls[1024];                    // live classes of this task (K <= 1024 or the general soft-max: see launcher)
+  __shared__ int n_cls;
+  __shared__ double ps[kTaskWarps], pl[kTaskWarps];
+  const int t = blockIdx.x;
+  const int q_lo = blockIdx.y * kTaskSlice, q_hi = min(n, q_lo + kTaskSlice);   // this CTA's queries
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) n_cls = 0;
+  __syncthreads();
+  for (int k = tid; k < K; k += kTaskThreads)
+    if (live[(long)t * K + k]) cls[atomicAdd(&n_cls, 1)] = k;   // any order: every class is handled independently
+  __syncthreads();
+  const int nc = n_cls;
+  // log-normalisers: four warps per class (the partition of lognorm_rows_kernel), four classes at a time
+  {
+    const int grp = warp >> 2, gtid = tid & 127, gwarp = warp & 3;
+    for (int c0 = 0; c0 < nc; c0 += kTaskWarps / 4) {
+      const int c = c0 + grp;
+      double s = 0.0, lg = 0.0;
+      if (c < nc) {
+        const float* a = alpha + ((long)t * K + cls[c]) * D;
+        for (int d = gtid; d < D; d += 128) {
+          const double x = (double)a[d];
+          s += x;
+          lg += lgamma(x);
+        }
+      }
+      s = warp_sum_f64(s);
+      lg = warp_sum_f64(lg);
+      if (lane == 0) {
+        ps[warp] = s;
+        pl[warp] = lg;
+      }
+      __syncthreads();
+      if (c < nc && gwarp == 0 && lane == 0) {
+        const int w0 = grp * 4;
+        norm[(long)t * K + cls[c]] = lgamma((ps[w0] + ps[w0 + 1]) + (ps[w0 + 2] + ps[w0 + 3])) -
+                                     ((pl[w0] + pl[w0 + 1]) + (pl[w0 + 2] + pl[w0 + 3]));
+      }
+      __syncthreads();
+    }
+  }
+  // contraction columns: l3[t, q, k] = sum_d logz[t, q, d] (alpha[t, k, d] - 1) for the live classes, a warp per (class, four
+  // queries): lanes stride over d, one shuffle tree per query (the arithmetic of logits_rows_kernel)
+  for (int c0 = 0; c0 < nc; c0 += kTaskRowsPerPass) {
+    const int np = min(kTaskRowsPerPass, nc - c0);
+    for (int i = tid; i < np * D; i += kTaskThreads) {
+      const int c = i / D, d = i - c * D;
+      am1[i] = alpha[((long)t * K + cls[c0 + c]) * D + d] - 1.0f;
+    }
+    __syncthreads();
+    const int n_groups = (q_hi - q_lo + 3) / 4;
+    for (int item = warp; item < np * n_groups; item += kTaskWarps) {
+      const int c = item / n_groups, n0 = q_lo + (item - c * n_groups) * 4;
+      const int k = cls[c0 + c];
+      const float* z0 = logz + ((long)t * n + n0) * D;
+      const float* b_row = am1 + c * D;
+      const int nq = min(4, q_hi - n0);
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+      for (int d = lane; d < D; d += 32) {
+        const float b = b_row[d];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nq) acc[q] = fmaf(z0[(long)q * D + d], b, acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float tot = warp_sum_f32(acc[q]);
+        if (lane == 0 && q < nq) l3[((long)t * n + n0 + q) * K + k] = tot;
+      }
+    }
+    __syncthreads();
+  }
+  // the norm / l3 entries written above by other threads of this CTA are read below: make them visible
+  __threadfence_block();
+  __syncthreads();
+  // responsibilities of the task's queries, one warp per query
+  for (int q = q_lo + warp; q < q_hi; q += kTaskWarps) {
+    const int row = t * n + q;
+    if (K <= 1024) softmax_row_reg(l3, norm, v, lambd, u, labels, row, lane, n, K, hard);
+    else softmax_row_gen(l3, norm, v, lambd, u, labels, row, lane, n, K, hard);
+  }
 }
 
 // ---- label matching inputs -----------------------------------------------------------------------------------------
@@ -669,7 +729,7 @@ cudaError_t support_stats(const float* log_support, const long long* y_s, float*
 cudaError_t commit(float* alpha, const float* work, const int* live, const int* dead_age, double2* rowstat,
                    float* task_crit, float* crit_out, int T, int K, int D, cudaStream_t st) {
   const int rows = T * K;
-  commit_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, work, live, dead_age, rowstat, rows, D);
+  commit_kernel<<<std::min((rows + 3) / 4, 148 * 32), 128, 0, st>>>(alpha, work, live, dead_age, rowstat, rows, D);
   criterion_task_kernel<<<T, 256, 0, st>>>(rowstat, task_crit, K);
   criterion_mean_kernel<<<1, 1, 0, st>>>(task_crit, crit_out, T);
   note_launch(3);
@@ -703,28 +763,27 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
   const int rows = T * K;
   float* dst = l3 ? l3 : u;
   const int* gate = (sp && l3) ? sp->gate : nullptr;
-  lognorm_kernel<<<(rows + 3) / 4, 128, 0, st>>>(alpha, norm, l3 ? live : nullptr, rows, D, gate);
-  if (gate) {
-    lognorm_rows_kernel<<<sp->cap, 128, 0, st>>>(alpha, norm, sp->rows_live, sp->n_live, D, gate);
-    note_launch(1);
-  }
+  lognorm_kernel<<<std::min((rows + 3) / 4, 148 * 32), 128, 0, st>>>(alpha, norm, l3 ? live : nullptr, rows, D, gate);
   note_launch(1);
   if (use_tensor_cores(logz, alpha, n, K, D)) {
     if (cudaError_t e = logits_tc(logz, alpha, dst, T, n, K, D, gate, false, st)) return e;
   } else {
     if (cudaError_t e = logits_simt(logz, alpha, dst, T, n, K, D, gate, st)) return e;
   }
-  if (gate) {
-    logits_rows_kernel<<<sp->cap, 256, D * sizeof(float), st>>>(logz, alpha, dst, sp->rows_live, sp->n_live, n, K, D,
-                                                                gate);
-    note_launch(1);
-  }
   const int qrows = T * n;
   if (K <= 1024)
-    softmax_reg_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard);
+    softmax_reg_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard, gate);
   else
-    softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard);
+    softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard, gate);
   note_launch(1);
+  if (gate) {
+    // few live rows: the whole E-step of a task in one kernel (the dense kernels above returned at once)
+    const size_t smem = (size_t)kTaskRowsPerPass * D * sizeof(float);
+    if (K > 1024) return cudaErrorInvalidValue;   // (the class list of a task lives in a 1024-entry shared array; D = K <= 1024)
+    estep_task_kernel<<<dim3(T, (n + kTaskSlice - 1) / kTaskSlice), kTaskThreads, smem, st>>>(alpha, logz, v, lambd, norm, dst, u,
+                                                                                            labels, live, n, K, D, hard, gate);
+    note_launch(1);
+  }
   return cudaGetLastError();
 }
 
