@@ -65,6 +65,15 @@ int tclip_dirichlet_colsum_v(const float* u, float* colsum, float* v, int* live,
 int tclip_dirichlet_moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
                             const float* support_count, float* y, int T, int n, int K, int D, void* stream);
 
+/* The same moments on the tensor cores: u^T and (log z)^T are staged as K-major operands ([T,K,np], [T,D,np], np = n rounded
+ * up to 4) of the 3 x TF32 tcgen05 kernel (fp32 round-to-nearest running sum outside the tensor core), the division / support
+ * terms / -10 fill run in its epilogue.  What tclip_dirichlet_em_run uses for outer iteration 0 and for the few-shot setting
+ * (DESIGN.md §3.6).  `workspace`: tclip_dirichlet_moments_tc_workspace_bytes bytes, 256-byte aligned. */
+size_t tclip_dirichlet_moments_tc_workspace_bytes(int T, int n, int K, int D);
+int tclip_dirichlet_moments_tc(const float* u, const float* logz, const float* colsum, const float* support_sum,
+                               const float* support_count, float* y, int T, int n, int K, int D, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* Few-shot, iteration-invariant: support_count[t,k] = #{s: y_s[t,s] == k}, support_sum[t,k,:] = sum of
  * log_support[t,s,:] over those s.  Replaces the [T,S,K,D] one-hot product of few_shot/em_dirichlet.py:182,199.
  * y_s is int64 [T,S]. */

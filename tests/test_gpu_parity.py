@@ -247,7 +247,9 @@ def test_check_spacing_schedules_agree(dev, check_every, iter_mm):
     assert d["mm_iters"].cpu().tolist() == s_["mm_iters"].cpu().tolist()
     assert d["n_live"].cpu().tolist() == s_["n_live"].cpu().tolist()
     assert (d["labels"] == s_["labels"]).all()
-    assert _rel(s_["alpha"], d["alpha"]) < 1e-5
+    # same arithmetic per element, but the few-rows kernel keeps one psi(s) anchor per M-step and the chunked kernel one per
+    # chunk (~1 ulp of psi(s)): 4e-9 after one outer iteration, amplified by the diverging singleton rows to ~1e-5 after five
+    assert _rel(s_["alpha"], d["alpha"]) < 3e-5
     np.testing.assert_allclose(s_["mm_crit"].cpu().numpy()[:, 1], d["mm_crit"].cpu().numpy()[:, 1], rtol=1e-4)
 
 
@@ -330,6 +332,42 @@ def test_stage_estep_moments(dev):
             assert (uu.sum(2) == 1).all()
         else:
             np.testing.assert_allclose(uu.cpu().numpy(), sm.numpy(), atol=2e-4)
+
+
+@pytest.mark.parametrize("T,n,K,D,few", [(2, 75, 20, 20, False), (3, 75, 100, 100, True), (2, 75, 1000, 1000, False),
+                                         (2, 75, 1000, 1000, True), (2, 40, 136, 100, False), (1, 13, 7, 33, True)])
+def test_stage_moments_tensor_cores(dev, T, n, K, D, few):
+    """The moments u^T log z on tcgen05 (3 x TF32, fp32 round-to-nearest running sum; u^T and (log z)^T staged as K-major
+    operands, division / support terms / -10 fill in the epilogue) against float64 and against the CUDA-core kernel."""
+    from tclip_b200 import ops
+    g = torch.Generator().manual_seed(100 + K + n)
+    z = torch.softmax(5 * torch.randn(T, n, D, generator=g), -1)
+    logz = ops.log_features(z.to(dev))
+    u = torch.softmax(6 * torch.randn(T, n, K, generator=g), -1)
+    u[:, :, min(3, K - 1)] = 0.0                               # an empty cluster
+    colsum, _, _ = ops.colsum_v(u.to(dev))
+    ssum = scount = None
+    if few:
+        ssum = (-5.0 * torch.rand(T, K, D, generator=g) * 4).to(dev)
+        scount = torch.full((T, K), 4.0).to(dev)
+    y_tc = ops.moments(u.to(dev), logz, colsum, ssum, scount, tensor_cores=True).cpu().double()
+    y_cc = ops.moments(u.to(dev), logz, colsum, ssum, scount).cpu().double()
+    acc = torch.einsum("tnk,tnd->tkd", u.double(), logz.cpu().double())
+    if few:
+        y_ref = (ssum.cpu().double() + acc) / (scount.cpu().double() + u.double().sum(1))[..., None]
+    else:
+        y_ref = acc / u.double().sum(1).clamp(min=1e-15)[..., None]
+        y_ref[:, min(3, K - 1), :] = -10.0
+        assert (y_tc[:, min(3, K - 1), :] == -10.0).all()
+    err_tc = ((y_tc - y_ref).abs() / y_ref.abs().clamp(min=1e-3)).max().item()
+    err_cc = ((y_cc - y_ref).abs() / y_ref.abs().clamp(min=1e-3)).max().item()
+    # measured: rms 1.3-2.2e-7 relative against 1.0-1.4e-7 for the CUDA-core kernel (inside a 32-long block the tensor core adds
+    # with truncation); what counts is the alpha it leads to, which the parity tests bound by the reference's own float32 error
+    # (profiles/r2_moments_tc.md: no measurable difference)
+    assert err_tc <= max(3.0 * err_cc, 1e-6), (err_tc, err_cc)
+    rms_tc = ((y_tc - y_ref) / y_ref.abs().clamp(min=1e-3)).pow(2).mean().sqrt().item()
+    rms_cc = ((y_cc - y_ref) / y_ref.abs().clamp(min=1e-3)).pow(2).mean().sqrt().item()
+    assert rms_tc <= max(2.0 * rms_cc, 3e-7), (rms_tc, rms_cc)
 
 
 @pytest.mark.parametrize("T,n,K,D", [(2, 75, 20, 20), (3, 75, 100, 100), (2, 75, 136, 100), (2, 40, 1000, 1000),

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <string>
 
@@ -91,6 +92,9 @@ struct EmWorkspace {
   float* log_support;
   float* support_sum;
   float* support_count;
+  float* logzT;         // [T, D, np] (log z)^T, K-major operand of the tensor-core moments
+  float* uT;            // [T, K, np] u^T, rewritten before every tensor-core moments call
+  int np;               // n rounded up to a multiple of 4 (TMA row pitch)
   // skip-dead mode
   int* cache_valid;
   double2* cache;       // [n_checks, rows]
@@ -137,6 +141,9 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
     w.support_sum = c.take<float>(rows * D);
     w.support_count = c.take<float>(rows);
   }
+  w.np = (int)((n + 3) & ~size_t(3));
+  w.logzT = c.take<float>(T * D * (size_t)w.np);
+  w.uT = c.take<float>(T * K * (size_t)w.np);
   if (p.mm_mode == TCLIP_MM_SKIP_DEAD && S == 0) {
     const size_t nc = num_checks(p.iter_mm, p.check_every);
     w.cache_valid = c.take<int>(rows);
@@ -463,6 +470,34 @@ int tclip_dirichlet_support_stats(const float* log_support, const long long* y_s
   return TCLIP_OK;
 }
 
+size_t tclip_dirichlet_moments_tc_workspace_bytes(int T, int n, int K, int D) {
+  if (T < 1 || n < 1 || K < 1 || D < 1) return 0;
+  const size_t np = ((size_t)n + 3) & ~size_t(3);
+  return align_up(sizeof(float) * (size_t)T * D * np) + align_up(sizeof(float) * (size_t)T * K * np);
+}
+
+int tclip_dirichlet_moments_tc(const float* u, const float* logz, const float* colsum, const float* support_sum,
+                               const float* support_count, float* y, int T, int n, int K, int D, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!u || !logz || !colsum || !y || T < 1 || n < 1 || K < 1 || D < 1)
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_moments_tc: bad arguments");
+  if ((support_sum == nullptr) != (support_count == nullptr))
+    return fail(TCLIP_ERR_INVALID, "tclip_dirichlet_moments_tc: support_sum and support_count go together");
+  if (!workspace || workspace_bytes < tclip_dirichlet_moments_tc_workspace_bytes(T, n, K, D) ||
+      (reinterpret_cast<unsigned long long>(workspace) & 255ull) != 0)
+    return fail(TCLIP_ERR_WORKSPACE, "tclip_dirichlet_moments_tc: workspace too small or not 256-byte aligned");
+  if (int rc = current_device_ok()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(workspace);
+  const int np = (n + 3) & ~3;
+  float* logzT = c.take<float>((size_t)T * D * np);
+  float* uT = c.take<float>((size_t)T * K * np);
+  TCLIP_CUDA(tclip::transpose_pad(logz, logzT, T, n, D, np, nullptr, st));
+  const tclip::MomentsTc mtc{uT, logzT, np};
+  TCLIP_CUDA(tclip::moments(u, logz, colsum, support_sum, support_count, y, T, n, K, D, nullptr, st, &mtc));
+  return TCLIP_OK;
+}
+
 size_t tclip_dirichlet_mm_workspace_bytes(int n_rows) {
   if (n_rows < 1) return 0;
   return align_up(sizeof(double2) * (size_t)tclip::mm_num_blocks(n_rows)) + align_up(sizeof(tclip::MMState));
@@ -730,6 +765,18 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     TCLIP_CUDA(tclip::log_features(p->x_s, w.log_support, (long)T * S * D, st));
     TCLIP_CUDA(tclip::support_stats(w.log_support, p->y_s, w.support_sum, w.support_count, T, S, K, D, st));
   }
+  // The moments u^T log z have a tensor-core form (tclip_dirichlet_moments_tc).  Measured (profiles/r2_moments_tc.md): the
+  // alpha it leads to is as close to float64 as with the CUDA-core kernel, but it is SLOWER — 0.5 against 0.4 ms per dense
+  // call: the contraction is only n = 75 long, so a 128 x 128 output tile is three 32-deep blocks and the kernel is all
+  // prologue, epilogue and the transposition of u — so the CUDA-core kernel stays the default.  TCLIP_MOMENTS=tc selects the
+  // tensor-core form where no row-wise kernel has to reproduce the result bit for bit: outer iteration 0 (every schedule
+  // takes the dense form there) and the few-shot setting (always dense).
+  static const bool moments_simt = [] {
+    const char* e = std::getenv("TCLIP_MOMENTS");
+    return !(e && std::string(e) == "tc");
+  }();
+  const tclip::MomentsTc mtc{w.uT, w.logzT, w.np};
+  if (!moments_simt) TCLIP_CUDA(tclip::transpose_pad(w.logz, w.logzT, T, n, D, w.np, nullptr, st));
   if (skip) {
     zero_int_kernel<<<(rows + 255) / 256, 256, 0, st>>>(w.cache_valid, rows);
     zero_int_kernel<<<(rows + 255) / 256, 256, 0, st>>>(w.dead_age, rows);
@@ -760,7 +807,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       sp.cap = kSparseCap;
     }
     TCLIP_CUDA(tclip::moments(p->u, w.logz, w.colsum, w.support_sum, w.support_count, w.y, T, n, K, D,
-                              sparse ? &sp : nullptr, st));
+                              sparse ? &sp : nullptr, st, (!moments_simt && (it == 0 || few)) ? &mtc : nullptr));
 
     if (p->mm_events && p->mm_events[2 * it]) TCLIP_CUDA(cudaEventRecord((cudaEvent_t)p->mm_events[2 * it], st));
     tclip::MMLaunch l{};

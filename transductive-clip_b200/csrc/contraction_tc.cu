@@ -137,7 +137,8 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)
 template <bool kExternalAcc>
 __global__ void __launch_bounds__(kThreads, 1)
 logits_tc_kernel(const __grid_constant__ CUtensorMap map_logz, const __grid_constant__ CUtensorMap map_alpha,
-                 float* __restrict__ l3, int n, int K, int D, const int* __restrict__ gate, float b_shift, int b_shared) {
+                 float* __restrict__ l3, int n, int K, int D, const int* __restrict__ gate, float b_shift, int b_shared,
+                 const TcEpilogue ep) {
   if (gate != nullptr && !(gate[0] > gate[1])) return;  // the row-wise kernels take this E-step (skip-dead schedule)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -271,6 +272,22 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_logz, const __grid_cons
       tc_fence_before();
       mbar_arrive(accempty0 + 8 * b);
     }
+    if (row < n && ep.mode != 0) {
+      // moments epilogue (rows are classes here): the arithmetic of moments_kernel (dirichlet_estep.cu)
+      const long r = (long)t * n + row;
+      const float cs = ep.colsum[r];
+      if (ep.mode == 1) {          // zero-shot: sum u log z / max(sum u, eps), -10 for an empty cluster (em_dirichlet.py:219-222)
+        const bool lv = cs > 1e-15f;
+        const float den = fmaxf(cs, 1e-15f);
+#pragma unroll
+        for (int j = 0; j < kTileN; ++j) acc[j] = lv ? acc[j] / den : -10.0f;
+      } else {                     // few-shot: (1 / (count_s + sum u)) * (support_sum + sum u log z) (few_shot/em_dirichlet.py:196-200)
+        const float f = 1.0f / (ep.support_count[r] + cs);
+        const float* ss = ep.support_sum + r * K + k0;
+#pragma unroll
+        for (int j = 0; j < kTileN; ++j) acc[j] = (k0 + j < K) ? f * (ss[j] + acc[j]) : 0.0f;
+      }
+    }
     if (row < n) {
       float* out = l3 + ((long)t * n + row) * K + k0;
       if (k0 + kTileN <= K && (K & 3) == 0) {
@@ -332,7 +349,8 @@ bool logits_tc_supported(int n, int K, int D) {
 // C[t, m, k] = sum_d A[t, m, d] * (B[tb, k, d] - b_shift), tb = t or 0 (b_tasks == 1): 3 x TF32 on tcgen05, fp32
 // round-to-nearest running sum outside the tensor core.  A [T, M, D], B [b_tasks, N, D], C [T, M, N].
 cudaError_t gemm_nt_tc(const float* a, const float* b, float* c, int T, int M, int N, int D, int b_tasks, float b_shift,
-                       const int* gate, bool accumulate_in_tmem, cudaStream_t st) {
+                       const int* gate, bool accumulate_in_tmem, cudaStream_t st, const TcEpilogue* epilogue) {
+  const TcEpilogue ep = epilogue ? *epilogue : TcEpilogue{};
   if (M < 1 || N < 1 || D < 4 || (D % 4) != 0 || (b_tasks != 1 && b_tasks != T)) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) return cudaErrorMisalignedAddress;
   // cudaFuncSetAttribute is per device: opt in once per device of this process (idempotent, so a race between two host
@@ -352,9 +370,9 @@ cudaError_t gemm_nt_tc(const float* a, const float* b, float* c, int T, int M, i
   if (m_tiles > 65535 || T > 65535) return cudaErrorInvalidValue;
   dim3 grid((N + kTileN - 1) / kTileN, m_tiles, T);
   if (accumulate_in_tmem)
-    logits_tc_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, c, M, N, D, gate, b_shift, b_tasks == 1 && T > 1);
+    logits_tc_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, c, M, N, D, gate, b_shift, b_tasks == 1 && T > 1, ep);
   else
-    logits_tc_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, c, M, N, D, gate, b_shift, b_tasks == 1 && T > 1);
+    logits_tc_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, c, M, N, D, gate, b_shift, b_tasks == 1 && T > 1, ep);
   note_launch();
   return cudaGetLastError();
 }

@@ -205,6 +205,26 @@ moments_rows_kernel(const float* __restrict__ u, const float* __restrict__ logz,
   }
 }
 
+// dst[t, c, r] = src[t, r, c], rows r >= R of the padded pitch Rp zero: 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+transpose_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C, int Rp, const int* __restrict__ gate) {
+  if (!dense_selected(gate)) return;
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* sb = src + (long)t * R * C;
+  float* db = dst + (long)t * C * Rp;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? sb[(long)r * C + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < Rp) db[(long)c * Rp + r] = tile[tx][i];
+  }
+}
+
 // ---- few-shot support statistics (iteration invariant): per-class count and per-class sum of log-features -------
 __global__ void support_stats_kernel(const float* __restrict__ log_support, const long long* __restrict__ y_s,
                                      float* __restrict__ support_sum, float* __restrict__ support_count, int S,
@@ -702,14 +722,33 @@ cudaError_t colsum_v(const float* u, float* colsum, float* v, int* live, int T, 
   return cudaGetLastError();
 }
 
+cudaError_t transpose_pad(const float* src, float* dst, int T, int R, int C, int Rp, const int* gate, cudaStream_t st) {
+  transpose_pad_kernel<<<dim3((C + 31) / 32, (Rp + 31) / 32, T), 256, 0, st>>>(src, dst, R, C, Rp, gate);
+  note_launch(1);
+  return cudaGetLastError();
+}
+
+// The dense form is a [K x n] . [n x D] product per task: with `tc` it runs on the tensor cores (u^T and (log z)^T as
+// K-major operands of the 3 x TF32 tcgen05 kernel of contraction_tc.cu, the division / support terms / -10 fill in its
+// epilogue), else on the CUDA cores in the summation order the row-wise kernel reproduces bit for bit.
 cudaError_t moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
                     const float* support_count, float* y, int T, int n, int K, int D, const SparseRows* sp,
-                    cudaStream_t st) {
+                    cudaStream_t st, const MomentsTc* tc) {
   const int few = support_sum != nullptr;
   const int* gate = sp ? sp->gate : nullptr;
-  moments_kernel<<<dim3((D + kMomTile - 1) / kMomTile, (K + kMomTile - 1) / kMomTile, T), 256, 0, st>>>(
-      u, logz, colsum, support_sum, support_count, y, n, K, D, few, gate);
-  note_launch(1);
+  if (tc) {
+    if (cudaError_t e = transpose_pad(u, tc->uT, T, n, K, tc->np, gate, st)) return e;
+    TcEpilogue ep;
+    ep.mode = few ? 2 : 1;
+    ep.colsum = colsum;
+    ep.support_sum = support_sum;
+    ep.support_count = support_count;
+    if (cudaError_t e = gemm_nt_tc(tc->uT, tc->logzT, y, T, K, D, tc->np, T, 0.0f, gate, false, st, &ep)) return e;
+  } else {
+    moments_kernel<<<dim3((D + kMomTile - 1) / kMomTile, (K + kMomTile - 1) / kMomTile, T), 256, 0, st>>>(
+        u, logz, colsum, support_sum, support_count, y, n, K, D, few, gate);
+    note_launch(1);
+  }
   if (sp) {
     moments_rows_kernel<<<sp->cap, 256, n * sizeof(float), st>>>(u, logz, colsum, y, sp->rows_live, sp->n_live, 0, n, K, D,
                                                                gate);

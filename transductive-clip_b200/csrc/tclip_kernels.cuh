@@ -87,9 +87,15 @@ struct SparseRows {
   const int* gate;
   int cap;
 };
+// Tensor-core form of the dense moments: u^T and (log z)^T staged as [T, K, np] / [T, D, np] (np = n rounded up to 4)
+struct MomentsTc {
+  float* uT;            // scratch [T, K, np], rewritten by every call
+  const float* logzT;   // [T, D, np], made once per batch (transpose_pad of logz)
+  int np;
+};
 cudaError_t moments(const float* u, const float* logz, const float* colsum, const float* support_sum,
                     const float* support_count, float* y, int T, int n, int K, int D, const SparseRows* sp,
-                    cudaStream_t st);
+                    cudaStream_t st, const MomentsTc* tc = nullptr);
 cudaError_t support_stats(const float* log_support, const long long* y_s, float* support_sum, float* support_count,
                           int T, int S, int K, int D, cudaStream_t st);
 cudaError_t commit(float* alpha, const float* work, const int* live, const int* dead_age, double2* rowstat,
@@ -106,8 +112,18 @@ cudaError_t logits_tc(const float* logz, const float* alpha, float* l3, int T, i
                       bool accumulate_in_tmem, cudaStream_t st);
 // the same kernel as a general batched "NT" product: C[t,m,k] = sum_d A[t,m,d] (B[tb,k,d] - b_shift), B shared by all
 // tasks when b_tasks == 1 (needs D % 4 == 0 and 16-byte aligned operands)
+// optional epilogue on the rows of C: mode 1 / 2 = the zero-shot / few-shot moments (rows are classes; see moments_tc)
+struct TcEpilogue {
+  int mode = 0;
+  const float* colsum = nullptr;         // [T, M]
+  const float* support_sum = nullptr;    // [T, M, N]  (mode 2)
+  const float* support_count = nullptr;  // [T, M]     (mode 2)
+};
 cudaError_t gemm_nt_tc(const float* a, const float* b, float* c, int T, int M, int N, int D, int b_tasks, float b_shift,
-                       const int* gate, bool accumulate_in_tmem, cudaStream_t st);
+                       const int* gate, bool accumulate_in_tmem, cudaStream_t st, const TcEpilogue* epilogue = nullptr);
+// dst[t, c, r] = src[t, r, c] for r < R, 0 for R <= r < Rp (Rp = R rounded up to a multiple of 4: a TMA-addressable row pitch);
+// the K-major operand layout the tensor-core kernel needs for a contraction over the LEADING index of src
+cudaError_t transpose_pad(const float* src, float* dst, int T, int R, int C, int Rp, const int* gate, cudaStream_t st);
 cudaError_t cluster_prototypes(const int* labels, const float* feats, int* cluster_label, int* cluster_size,
                                int* sample_cluster, int* n_clusters, float* proto, int T, int n, int D,
                                cudaStream_t st);

@@ -73,6 +73,9 @@ SIGNATURES = {
     "tclip_dirichlet_colsum_v": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tclip_dirichlet_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                         c_int, c_int, c_void_p]),
+    "tclip_dirichlet_moments_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tclip_dirichlet_moments_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                           c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tclip_dirichlet_support_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                               c_void_p]),
     "tclip_dirichlet_mm_workspace_bytes": (c_size_t, [c_int]),

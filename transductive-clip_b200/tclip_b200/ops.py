@@ -60,7 +60,8 @@ def colsum_v(u: torch.Tensor, want_v: bool = True, want_live: bool = True):
     return colsum, v, live
 
 
-def moments(u, logz, colsum, support_sum=None, support_count=None) -> torch.Tensor:
+def moments(u, logz, colsum, support_sum=None, support_count=None, tensor_cores: bool = False) -> torch.Tensor:
+    """y_cst [T,K,D]; ``tensor_cores`` selects the tcgen05 form the EM driver uses for outer iteration 0 / few-shot."""
     lib = _lib.load()
     _need(u, torch.float32, "u"), _need(logz, torch.float32, "logz"), _need(colsum, torch.float32, "colsum")
     T, n, K = u.shape
@@ -68,6 +69,12 @@ def moments(u, logz, colsum, support_sum=None, support_count=None) -> torch.Tens
     if support_sum is not None:
         _need(support_sum, torch.float32, "support_sum"), _need(support_count, torch.float32, "support_count")
     y = torch.empty(T, K, D, device=u.device, dtype=torch.float32)
+    if tensor_cores:
+        nbytes = lib.tclip_dirichlet_moments_tc_workspace_bytes(T, n, K, D)
+        ws = torch.empty(nbytes, device=u.device, dtype=torch.uint8)
+        check(lib.tclip_dirichlet_moments_tc(_ptr(u), _ptr(logz), _ptr(colsum), _ptr(support_sum), _ptr(support_count),
+                                             _ptr(y), T, n, K, D, _ptr(ws), nbytes, _stream()))
+        return y
     check(lib.tclip_dirichlet_moments(_ptr(u), _ptr(logz), _ptr(colsum), _ptr(support_sum), _ptr(support_count),
                                       _ptr(y), T, n, K, D, _stream()))
     return y
