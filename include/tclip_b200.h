@@ -67,8 +67,9 @@ int tclip_dirichlet_moments(const float* u, const float* logz, const float* cols
 
 /* The same moments on the tensor cores: u^T and (log z)^T are staged as K-major operands ([T,K,np], [T,D,np], np = n rounded
  * up to 4) of the 3 x TF32 tcgen05 kernel (fp32 round-to-nearest running sum outside the tensor core), the division / support
- * terms / -10 fill run in its epilogue.  What tclip_dirichlet_em_run uses for outer iteration 0 and for the few-shot setting
- * (DESIGN.md §3.6).  `workspace`: tclip_dirichlet_moments_tc_workspace_bytes bytes, 256-byte aligned. */
+ * terms / -10 fill run in its epilogue.  Equally accurate at the level of alpha but measured slower than the CUDA-core kernel
+ * (contraction length 75: DESIGN.md §3.6), so tclip_dirichlet_em_run uses it only when TCLIP_MOMENTS=tc is set (outer
+ * iteration 0 and the few-shot setting).  `workspace`: tclip_dirichlet_moments_tc_workspace_bytes bytes, 256-byte aligned. */
 size_t tclip_dirichlet_moments_tc_workspace_bytes(int T, int n, int K, int D);
 int tclip_dirichlet_moments_tc(const float* u, const float* logz, const float* colsum, const float* support_sum,
                                const float* support_count, float* y, int T, int n, int K, int D, void* workspace,

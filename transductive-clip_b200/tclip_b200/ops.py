@@ -61,7 +61,8 @@ def colsum_v(u: torch.Tensor, want_v: bool = True, want_live: bool = True):
 
 
 def moments(u, logz, colsum, support_sum=None, support_count=None, tensor_cores: bool = False) -> torch.Tensor:
-    """y_cst [T,K,D]; ``tensor_cores`` selects the tcgen05 form the EM driver uses for outer iteration 0 / few-shot."""
+    """y_cst [T,K,D]; ``tensor_cores`` selects the tcgen05 form (measured slower than the CUDA-core kernel at n = 75; the EM
+    driver uses it only under TCLIP_MOMENTS=tc)."""
     lib = _lib.load()
     _need(u, torch.float32, "u"), _need(logz, torch.float32, "logz"), _need(colsum, torch.float32, "colsum")
     T, n, K = u.shape
