@@ -88,7 +88,7 @@ def parse():
                     help="lo,hi: true classes per synthetic task, uniform (3,10 = the reference's sampler, src/sampler_zero_shot.py:54, "
                          "and the metric's workload; e.g. 20,30 keeps ~25 clusters per task alive: profiles/r2_workload_sweep.md)")
     ap.add_argument("--noise", type=float, default=None, help="noise scale of the synthetic embeddings (default 9, SURVEY.md §8(d))")
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=8,
                     help="run_task batches in flight per GPU (own CUDA stream + host thread each); 1 = strictly serial")
     a = ap.parse_args()
     a.k_eff_range = tuple(int(v) for v in a.classes_per_task.split(","))

@@ -568,6 +568,21 @@ def test_batches_in_flight_equal_serial(dev):
         assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
 
 
+def test_in_flight_tail_kernel_is_bit_identical(dev):
+    """TCLIP_FLAG_IN_FLIGHT (set by the method classes inside a BatchPipeline worker) swaps the few-rows M-step kernel of the
+    skip-dead schedule for its register-lean form at D > 768: plain update instead of the two-phase one, which is the same
+    arithmetic operation for operation (tests/test_math_host.py) — the results must be equal to the last bit."""
+    from tclip_b200 import ops, tasks
+    K, T, iters = 1000, 5, 4
+    td, _ = tasks.make_zero_shot_batch(T, K, seed=2020, batch_index=3)
+    xq = td["x_q"].to(dev)
+    out = [ops.dirichlet_em(xq, K, iters=iters, iter_mm=1000, lambd=float(int(K / 5) * 75), hard=False,
+                            mm_mode=ops.TCLIP_MM_SKIP_DEAD, in_flight=flag) for flag in (False, True)]
+    assert max(out[0]["n_live"].cpu().tolist()[1:]) <= 1480          # the few-rows kernel ran
+    assert torch.equal(out[0]["alpha"], out[1]["alpha"]) and torch.equal(out[0]["u"], out[1]["u"])
+    assert torch.equal(out[0]["mm_iters"], out[1]["mm_iters"]) and torch.equal(out[0]["labels"], out[1]["labels"])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # BASELINE sizes (K = D = 1000, n = 75): size-independent properties
 # ------------------------------------------------------------------------------------------------------------------

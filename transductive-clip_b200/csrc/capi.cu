@@ -848,6 +848,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       l.spec_snap = w.spec_snap;
       l.work_ctr = w.work_ctr;
       l.spec_probe = p->spec_probe ? reinterpret_cast<int4*>(p->spec_probe) + (size_t)it * kSplitCap : nullptr;
+      l.spec_lean = (p->flags & TCLIP_FLAG_IN_FLIGHT) != 0;
       l.n_rows = rows;
       l.n_blocks = tclip::mm_num_blocks(rows, true);
       TCLIP_CUDA(tclip::mm_run(l, p->iter_mm, p->check_every, p->tol, nc > 0 ? w.extra : nullptr, st));

@@ -425,6 +425,7 @@ mm_chunk_kernel(const ChunkArgs g) {
 // mm_spec_resolve_kernel then evaluates the checks in order with the terms of ALL rows (+ the cached dead rows) and, in
 // the rare case that one fires, mm_spec_apply_kernel restores the snapshot of that check.  Same arithmetic, same result,
 // no launch per 50 iterations.  Runs iff split_gate[0] <= split_gate[1].
+constexpr int kSpecLeanMinBlocks = 6;   // CTAs per SM the register-lean few-rows kernel is compiled for (80 registers)
 struct SpecArgs {
   const float* alpha_in;
   float* alpha_out;
@@ -456,7 +457,7 @@ struct SpecArgs {
 // So, unlike the empty clusters (mm_chunk_kernel<FR>), live rows offer no exact early stop worth its cost: carrying the
 // per-iteration vote in the product kernel made it 14 % slower, and it is therefore compiled into this build only.
 template <int W, int NPW, bool PIPE, bool PROBE>
-__global__ void __launch_bounds__(32 * W)
+__global__ void __launch_bounds__(32 * W, (!PIPE && W == 4 && NPW == 4) ? kSpecLeanMinBlocks : 1)
 mm_spec_kernel(const SpecArgs g) {
   if (!(g.split_gate[0] <= g.split_gate[1])) return;
   if ((int)blockIdx.x >= *g.n_rows_dev) return;  // CTA-uniform
@@ -710,7 +711,12 @@ constexpr auto make_table(std::integer_sequence<int, I...>) {
 // through an environment knob that commit 565e2b8 still has, removed since).  Round 2, with 4 batches in flight (where the
 // SMs' issue rate, not the dependent chain, is the limit): 2 x 8 (12 % fewer instructions per row-iteration, 255 registers)
 // 2929 tasks/s against 3108 for 4 x 4 — fewer, fatter warps lose there too.
-SpecFn spec_fn(int np) {
+// `lean`: the caller keeps several batches in flight.  The two-phase (software-pipelined) update holds 88 registers of
+// look-ahead state per thread (168 in total): three CTAs per SM, i.e. the tails of only two batches fit on the GPU at once and
+// those of the others queue behind them.  The plain update (bit-identical results, tests/test_math_host.py) needs 80
+// registers, six CTAs per SM: 1.7 % slower alone, 9 % more tasks/s with 8 batches in flight (profiles/r2_in_flight.md).
+SpecFn spec_fn(int np, bool lean) {
+  if (lean && np > 12) return &launch_spec<4, 4, false>;
   switch (np) {
     case 1: return &launch_spec<1, 1>;
     case 2: return &launch_spec<1, 2>;   // D <= 128: one warp, no cross-warp traffic on the serial path
@@ -833,7 +839,7 @@ cudaError_t mm_run(MMLaunch p, int iter_mm, int check_every, float tol, const do
     g.extra = extra_checks;
     g.tol = tol;
     g.state = p.state;
-    spec_fn(np)(g, st);
+    spec_fn(np, p.spec_lean)(g, st);
     mm_spec_resolve_kernel<<<1, 32 * std::max(1, std::min(g.n_checks, 32)), 0, st>>>(g);
     mm_spec_apply_kernel<<<g.cap, 256, 0, st>>>(g);
     note_launch(3);

@@ -68,6 +68,7 @@ struct MMLaunch {
   double2* spec_terms;    // [n_checks][split_cap]
   float* spec_snap;       // [n_checks][split_cap][D]
   int4* spec_probe;       // optional [split_cap]: per-row convergence statistics (selects the measurement build of the kernel)
+  bool spec_lean;         // register-lean few-rows kernel (several batches in flight): same results, more CTAs per SM
 };
 
 int mm_max_dim();

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("TCLIP_LIB") or os.path.join(_HERE, "libtclip_b200.so"
 TCLIP_OK = 0
 TCLIP_MM_DENSE = 0
 TCLIP_MM_SKIP_DEAD = 1
+TCLIP_FLAG_IN_FLIGHT = 1
 
 
 class TclipLibraryError(RuntimeError):
@@ -45,6 +46,7 @@ class DirichletProblem(ctypes.Structure):
         ("mm_events", POINTER(c_void_p)),
         ("mm_crit", c_void_p),
         ("spec_probe", c_void_p),
+        ("flags", c_int),
     ]
 
 

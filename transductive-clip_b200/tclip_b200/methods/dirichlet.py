@@ -20,6 +20,7 @@ import torch
 
 from .. import ops
 from ..logger import Logger
+from ..pipeline import batches_in_flight
 
 _MM_MODES = {"dense": ops.TCLIP_MM_DENSE, "skip_dead": ops.TCLIP_MM_SKIP_DEAD}
 
@@ -116,7 +117,8 @@ class _DirichletBase(object):
         start = torch.cuda.Event(enable_timing=True)
         start.record()
         res = ops.dirichlet_em(query, self.args.num_classes_test, self.iter, self.iter_mm, float(self.lambd), self.hard,
-                               x_s=support, y_s=y_s, mm_mode=_MM_MODES[self.mm_mode], record_events=True)
+                               x_s=support, y_s=y_s, mm_mode=_MM_MODES[self.mm_mode], record_events=True,
+                               in_flight=batches_in_flight() > 1)
         self.u, self.alpha, self.v, self.labels = res["u"], res["alpha"], res["v"], res["labels"]
         self.mm_iters, self.n_live, self.mm_rows = res["mm_iters"], res["n_live"], res["mm_rows"]
         self.mm_crit = res["mm_crit"]

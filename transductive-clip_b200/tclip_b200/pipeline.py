@@ -21,6 +21,15 @@ from typing import Callable, Iterable, List
 import torch
 
 
+_IN_FLIGHT = threading.local()
+
+
+def batches_in_flight() -> int:
+    """How many batches the calling thread's pipeline keeps in flight (1 outside a ``BatchPipeline`` worker).  The method
+    classes read it to tell the library (``TCLIP_FLAG_IN_FLIGHT``) that kernels of several batches share the GPU."""
+    return getattr(_IN_FLIGHT, "streams", 1)
+
+
 class BatchPipeline:
     def __init__(self, device, streams: int = 3):
         self.device = torch.device(device)
@@ -36,6 +45,7 @@ class BatchPipeline:
 
     def _run(self, fn: Callable, item):
         if getattr(self._local, "stream", None) is None:
+            _IN_FLIGHT.streams = self.streams
             torch.cuda.set_device(self.device)
             self._local.stream = torch.cuda.Stream(device=self.device)
             with self._lock:
