@@ -14,7 +14,7 @@ MM early exit is batch-global); ``value`` = tasks of all ranks / max-over-ranks 
   value        inputs already resident in HBM (``run_method``), timed with CUDA events;
   e2e          the reference-facing call ``run_task(task_dic)`` with pinned HOST tensors: H2D + EM + D2H of the
                accuracies inside the timed region;
-               both legs keep ``--streams`` (default 4) whole batches in flight per GPU — every batch is one unchanged
+               both legs keep ``--streams`` (default 8) whole batches in flight per GPU — every batch is one unchanged
                ``run_method`` / ``run_task`` call on its own CUDA stream and host thread (``tclip_b200.pipeline``), because
                half of a batch is a latency-bound tail that leaves the SMs idle; ``serial`` inside ``value``'s line and
                inside ``e2e`` is the same leg strictly one batch after the other (the reference's evaluator loop);
