@@ -233,6 +233,10 @@ int tclip_gather_tasks_remap(const float* features, const long long* labels, con
  * that the tails of all batches in flight fit on the GPU together).  Same results bit for bit; 1.7 % slower for one batch
  * alone, 9 % more tasks/s with 8 batches in flight. */
 #define TCLIP_FLAG_IN_FLIGHT 1
+/* Skip-dead schedule with few live rows: by default the soft-max of a query only visits the live classes once a bound proves
+ * that every dead class underflows to exactly 0 (bit-identical to the soft-max over all K classes).  This bit
+ * keeps the pass over all classes (cross-checks, measurements). */
+#define TCLIP_FLAG_FULL_SOFTMAX 2
 typedef struct tclip_dirichlet_problem {
   int n_task, n_query, n_class, dim; /* T, n, K, D (D == K: softmax features) */
   int n_support;                     /* S; 0 = zero-shot */

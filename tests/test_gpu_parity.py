@@ -568,6 +568,29 @@ def test_batches_in_flight_equal_serial(dev):
         assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
 
 
+@pytest.mark.parametrize("K,T,iters,hard,k_eff,noise", [
+    (1000, 6, 7, False, (3, 10), 9.0), (1000, 6, 6, True, (3, 10), 9.0), (1000, 4, 5, False, (20, 30), 6.0),
+    (100, 8, 8, False, (3, 10), 9.0), (100, 8, 8, True, (3, 10), 9.0), (50, 5, 6, False, (3, 10), 3.0),
+])
+def test_sparse_softmax_is_bit_identical(dev, K, T, iters, hard, k_eff, noise):
+    """The sparse regime's soft-max visits only the live classes of a query once a bound proves that every dead class
+    underflows to exactly +0.0f (estep_task_kernel); TCLIP_FLAG_FULL_SOFTMAX keeps the pass over all K classes.  Both must give
+    the same u, labels, v and alpha to the last bit, through changes of the set of dead classes, in the soft and the hard
+    variant (which only moves the 1 of a one-hot row)."""
+    from tclip_b200 import ops, tasks
+    td, _ = tasks.make_zero_shot_batch(T, K, seed=31, batch_index=K + iters, k_eff_range=k_eff, noise=noise)
+    xq = td["x_q"].to(dev)
+    out = [ops.dirichlet_em(xq, K, iters=iters, iter_mm=1000, lambd=float(int(K / 5) * 75), hard=hard,
+                            mm_mode=ops.TCLIP_MM_SKIP_DEAD, full_softmax=flag) for flag in (True, False)]
+    assert min(out[0]["n_live"].cpu().tolist()[1:]) <= 4096          # the row-wise E-step ran
+    for key in ("u", "labels", "v", "alpha", "mm_iters", "n_live", "criterions"):
+        assert torch.equal(out[0][key], out[1][key]), key
+    if hard:
+        u = out[1]["u"]
+        assert ((u == 0) | (u == 1)).all() and (u.sum(2) == 1).all()
+        assert torch.equal(u.argmax(2).int(), out[1]["labels"])
+
+
 def test_in_flight_tail_kernel_is_bit_identical(dev):
     """TCLIP_FLAG_IN_FLIGHT (set by the method classes inside a BatchPipeline worker) swaps the few-rows M-step kernel of the
     skip-dead schedule for its register-lean form at D > 768: plain update instead of the two-phase one, which is the same

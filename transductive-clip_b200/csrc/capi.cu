@@ -112,6 +112,9 @@ struct EmWorkspace {
   int* list_new;
   int* counts;          // [0] = live rows, [1] = newly dead rows
   unsigned long long* work_ctr;  // row-iterations executed by the free-running pass of this outer iteration
+  float* dead_max;      // [T, n] bound of the sparse soft-max (estep_task_kernel)
+  int* last_full;       // [2, T]
+  int* ss_state;        // {set_iter, a_iter, last_dense}
   size_t bytes;
 };
 
@@ -162,6 +165,9 @@ EmWorkspace carve(const tclip_dirichlet_problem& p, void* ws) {
     w.counts = c.take<int>(4);
     w.tile_counts = c.take<int4>((rows + 1023) / 1024);
     w.work_ctr = c.take<unsigned long long>(1);
+    w.dead_max = c.take<float>(T * n);
+    w.last_full = c.take<int>(2 * T);
+    w.ss_state = c.take<int>(4);
   }
   w.bytes = c.off;
   return w;
@@ -191,6 +197,11 @@ __global__ void fill_kernel(float* p, float v, long n) {
   } else {
     for (long j = i; j < n && j < i + 4; ++j) p[j] = v;  // this thread's four elements only (tail / unaligned buffer)
   }
+}
+__global__ void init_sparse_softmax_kernel(int* s) {   // {set_iter, a_iter, last_dense}
+  s[0] = 0;
+  s[1] = -1;
+  s[2] = -1;
 }
 __global__ void zero_int_kernel(int* p, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,7 +259,8 @@ __global__ void __launch_bounds__(1024)
 classify_write_kernel(const int* __restrict__ live, int* __restrict__ cache_valid, int* __restrict__ frozen,
                       int* __restrict__ dead_age, const int4* __restrict__ tile_counts, int* __restrict__ list_live,
                       int* __restrict__ list_new, int* __restrict__ counts, int* __restrict__ gate, int cap,
-                      int* __restrict__ split_gate, int split_cap, unsigned long long* __restrict__ work_ctr, int rows) {
+                      int* __restrict__ split_gate, int split_cap, unsigned long long* __restrict__ work_ctr, int rows,
+                      int it, int* __restrict__ set_iter) {
   __shared__ int wl[32], wn[32];
   __shared__ int4 red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -320,6 +332,7 @@ classify_write_kernel(const int* __restrict__ live, int* __restrict__ cache_vali
     counts[0] = tot_l;
     counts[1] = tot_n;
     counts[2] = (changed || tot_n > 0) ? 1 : 0;
+    if (changed || tot_n > 0) *set_iter = it;   // the set of dead rows differs from the previous outer iteration's
     gate[0] = tot_l;            // rows the row-wise kernels have to recompute (newly dead rows only get their y filled)
     gate[1] = cap;
     split_gate[0] = tot_l;
@@ -775,6 +788,11 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     const char* e = std::getenv("TCLIP_MOMENTS");
     return !(e && std::string(e) == "tc");
   }();
+  // TCLIP_SPARSE_SOFTMAX=0: the sparse regime always soft-maxes over all classes (measurements, cross-checks)
+  static const bool sparse_softmax_off = [] {
+    const char* e = std::getenv("TCLIP_SPARSE_SOFTMAX");
+    return e && std::string(e) == "0";
+  }();
   const tclip::MomentsTc mtc{w.uT, w.logzT, w.np};
   if (!moments_simt) TCLIP_CUDA(tclip::transpose_pad(w.logz, w.logzT, T, n, D, w.np, nullptr, st));
   if (skip) {
@@ -782,6 +800,9 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     zero_int_kernel<<<(rows + 255) / 256, 256, 0, st>>>(w.dead_age, rows);
     tclip::note_launch(2);
     TCLIP_CUDA(cudaMemsetAsync(w.state_free, 0, sizeof(tclip::MMState), st));
+    TCLIP_CUDA(cudaMemsetAsync(w.last_full, 0xff, sizeof(int) * 2 * (size_t)T, st));          // -1: never
+    init_sparse_softmax_kernel<<<1, 1, 0, st>>>(w.ss_state);
+    tclip::note_launch();
     TCLIP_CUDA(cudaMemsetAsync(w.extra, 0, sizeof(double2) * (size_t)(nc ? nc : 1), st));  // no dead rows yet
   }
 
@@ -797,7 +818,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       classify_count_kernel<<<n_tiles, 1024, 0, st>>>(w.live, w.cache_valid, w.dead_age, w.tile_counts, rows);
       classify_write_kernel<<<n_tiles, 1024, 0, st>>>(w.live, w.cache_valid, w.frozen, w.dead_age, w.tile_counts, w.list_live,
                                                      w.list_new, w.counts, w.gate, kSparseCap, w.split_gate, kSplitCap,
-                                                     w.work_ctr, rows);
+                                                     w.work_ctr, rows, it, w.ss_state);
       tclip::note_launch(2);
       sp.rows_live = w.list_live;
       sp.n_live = w.counts;
@@ -805,6 +826,15 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       sp.n_new = w.counts + 1;
       sp.gate = w.gate;
       sp.cap = kSparseCap;
+      sp.it = it;
+      if (!sparse_softmax_off && !(p->flags & TCLIP_FLAG_FULL_SOFTMAX)) {
+        sp.changed = w.counts + 2;
+        sp.set_iter = w.ss_state;
+        sp.a_iter = w.ss_state + 1;
+        sp.last_dense = w.ss_state + 2;
+        sp.dead_max = w.dead_max;
+        sp.last_full = w.last_full;
+      }
     }
     TCLIP_CUDA(tclip::moments(p->u, w.logz, w.colsum, w.support_sum, w.support_count, w.y, T, n, K, D,
                               sparse ? &sp : nullptr, st, (!moments_simt && (it == 0 || few)) ? &mtc : nullptr));

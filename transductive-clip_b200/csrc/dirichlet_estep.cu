@@ -406,9 +406,12 @@ logits_kernel(const float* __restrict__ logz, const float* __restrict__ alpha, f
 // K <= 1024: the 32 logits of a lane stay in registers (one pass over l3 / norm / v, one expf per element); same
 // arithmetic and the same per-lane summation order as the general kernel below => identical results.
 // (l3, norm: no __restrict__ — estep_task_kernel writes both earlier in the same kernel and must read them coherently)
+// live_t / dead_max_row (optional): also leave max over the dead classes of float(norm + l3) for this query (the bound of the
+// sparse soft-max below).
 __device__ __forceinline__ void softmax_row_reg(const float* l3, const double* norm, const float* __restrict__ v,
                                                 float lambd, float* u, int* __restrict__ labels, int row, int lane, int n,
-                                                int K, int hard) {
+                                                int K, int hard, const int* __restrict__ live_t = nullptr,
+                                                float* dead_max_row = nullptr) {
   const int t = row / n;
   const float* x = l3 + (long)row * K;
   const double* nm = norm + (long)t * K;
@@ -416,16 +419,22 @@ __device__ __forceinline__ void softmax_row_reg(const float* l3, const double* n
   float* out = u + (long)row * K;
   const float fn = (float)n;
   float lg[32];
-  float mx = -CUDART_INF_F;
+  float mx = -CUDART_INF_F, dm = -CUDART_INF_F;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int k = lane + 32 * j;
     if (k < K) {
-      lg[j] = (float)(nm[k] + (double)x[k]) + (lambd * vv[k]) / fn;
+      const float base = (float)(nm[k] + (double)x[k]);
+      if (live_t && !live_t[k]) dm = fmaxf(dm, base);
+      lg[j] = base + (lambd * vv[k]) / fn;
       mx = fmaxf(mx, lg[j]);
     }
   }
   mx = warp_max_f32(mx);
+  if (dead_max_row) {
+    dm = warp_max_f32(dm);
+    if (lane == 0) *dead_max_row = dm;
+  }
   float sum = 0.0f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -468,8 +477,10 @@ __device__ __forceinline__ void softmax_row_reg(const float* l3, const double* n
 // estep_task_kernel takes the whole E-step of a task)
 __global__ void __launch_bounds__(128)
 softmax_reg_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
-                   float* u, int* __restrict__ labels, int rows, int n, int K, int hard, const int* __restrict__ gate) {
+                   float* u, int* __restrict__ labels, int rows, int n, int K, int hard, const int* __restrict__ gate,
+                   int it, int* __restrict__ last_dense) {
   if (!dense_selected(gate)) return;
+  if (last_dense && blockIdx.x == 0 && threadIdx.x == 0) *last_dense = it;   // full rows were written: see estep_task_kernel
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   softmax_row_reg(l3, norm, v, lambd, u, labels, row, threadIdx.x & 31, n, K, hard);
@@ -525,8 +536,10 @@ __device__ __forceinline__ void softmax_row_gen(const float* l3, const double* n
 
 __global__ void __launch_bounds__(128)
 softmax_kernel(const float* l3, const double* __restrict__ norm, const float* __restrict__ v, float lambd,
-               float* u, int* __restrict__ labels, int rows, int n, int K, int hard, const int* __restrict__ gate) {
+               float* u, int* __restrict__ labels, int rows, int n, int K, int hard, const int* __restrict__ gate,
+               int it, int* __restrict__ last_dense) {
   if (!dense_selected(gate)) return;
+  if (last_dense && blockIdx.x == 0 && threadIdx.x == 0) *last_dense = it;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   softmax_row_gen(l3, norm, v, lambd, u, labels, row, threadIdx.x & 31, n, K, hard);
@@ -546,25 +559,99 @@ constexpr int kTaskWarps = kTaskThreads / 32;
 constexpr int kTaskRowsPerPass = 8;   // live classes whose alpha - 1 rows are staged in shared memory at a time
 constexpr int kTaskSlice = 16;        // queries per CTA (a multiple of the 4-query groups of the contraction)
 
-__global__ void __launch_bounds__(kTaskThreads)
+// Exact sparse soft-max.  In the tail of the EM ~3 of the K classes of a task are alive; the logits of the dead ones are
+// frozen (their alpha row, log-normaliser and l3 column do not change while they stay dead; their v is log(~1e-15) + 1), far
+// below the live ones.  A soft-max over all K classes gives them exp(logit - max) = +0.0f exactly whenever logit - max <= -104,
+// and adding +0.0f leaves every partial sum unchanged, so the row equals the soft-max over the live classes alone — bit for
+// bit, as long as each lane still sums its own classes in increasing order.  Per query the bound is
+// float(dead_max + max_dead float(float(lambda v) / n)) >= every dead logit (rounding is monotone), with dead_max = max over
+// the dead classes of float(norm + l3), recomputed by a pass over all classes whenever the set of dead classes changes.  A row
+// whose bound is not 106 below its live maximum takes the full pass.  Rows written by a full pass may hold non-zero
+// responsibilities of dead classes: the next sparse pass of that task zeroes its rows first (soft variant; the hard variant
+// only moves the 1 of the one-hot row).
+constexpr int kSparseMaxLive = 64;       // more live classes per task: full rows
+constexpr float kExpUnderflow = -106.0f;  // expf(x) == +0.0f for x <= -104 (exp(-104) = 6.8e-46 < half the smallest denormal)
+
+// returns false (warp-uniform) if the bound does not hold: the caller then runs the full row
+__device__ __forceinline__ bool softmax_row_sparse(const float* l3, const double* norm, const float* lterm, float* u,
+                                                   int* __restrict__ labels, int row, int lane, int n, int K, int hard,
+                                                   const int* cls, int nc, float bound, bool zero_row) {
+  const int t = row / n;
+  const float* x = l3 + (long)row * K;
+  const double* nm = norm + (long)t * K;
+  float* out = u + (long)row * K;
+  float mx = -CUDART_INF_F;
+  for (int i = 0; i < nc; ++i) {
+    const int k = cls[i];
+    if ((k & 31) == lane) mx = fmaxf(mx, (float)(nm[k] + (double)x[k]) + lterm[k]);
+  }
+  mx = warp_max_f32(mx);
+  if (!(bound - mx <= kExpUnderflow)) return false;   // (also taken when anything is NaN)
+  float sum = 0.0f;
+  for (int i = 0; i < nc; ++i) {          // cls is ascending: every lane adds its classes in the order of the full pass
+    const int k = cls[i];
+    if ((k & 31) == lane) sum += expf(((float)(nm[k] + (double)x[k]) + lterm[k]) - mx);
+  }
+  sum = warp_sum_f32(sum);
+  const int prev = (hard && labels) ? labels[row] : -1;
+  if (zero_row && !hard) {
+    for (int k = lane; k < K; k += 32) out[k] = 0.0f;   // (the live entries below are written by the same lane afterwards)
+  }
+  float best = -1.0f;
+  int best_k = 0x7fffffff;
+  for (int i = 0; i < nc; ++i) {
+    const int k = cls[i];
+    if ((k & 31) == lane) {
+      const float p = expf(((float)(nm[k] + (double)x[k]) + lterm[k]) - mx) / sum;
+      if (p > best) {
+        best = p;
+        best_k = k;
+      }
+      if (!hard) out[k] = p;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    if (ob > best || (ob == best && ok < best_k)) {
+      best = ob;
+      best_k = ok;
+    }
+  }
+  if (lane == 0) {
+    if (hard) {
+      if (prev >= 0 && prev < K) out[prev] = 0.0f;
+      out[best_k] = 1.0f;
+    }
+    if (labels) labels[row] = best_k;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kTaskThreads, 2)
 estep_task_kernel(const float* __restrict__ alpha, const float* __restrict__ logz, const float* __restrict__ v, float lambd,
-                  double* __restrict__ norm, float* l3, float* u, int* __restrict__ labels, const int* __restrict__ live,
-                  int n, int K, int D, int hard, const int* __restrict__ gate) {
-  if (dense_selected(gate)) return;
+                  double* __restrict__ norm, float* l3, float* u, int* labels, const int* __restrict__ live,
+                  int n, int K, int D, int hard, const SparseRows sp) {
+  if (dense_selected(sp.gate)) return;
   extern __shared__ float am1[];               // [kTaskRowsPerPass][D] alpha - 1 of the classes of this pass
-  __shared__ int cls[1024];                    // live classes of this task (K <= 1024 or the general soft-max: see launcher)
+  __shared__ int cls[1024];                    // live classes of this task (K <= 1024: see the launcher)
+  __shared__ int sorted[kSparseMaxLive];
+  __shared__ float lterm[1024];                // float(float(lambda v) / n) per class
   __shared__ int n_cls;
   __shared__ double ps[kTaskWarps], pl[kTaskWarps];
+  __shared__ float wmax[kTaskWarps];
   const int t = blockIdx.x;
   const int q_lo = blockIdx.y * kTaskSlice, q_hi = min(n, q_lo + kTaskSlice);   // this CTA's queries
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int* live_t = live + (long)t * K;
   if (tid == 0) n_cls = 0;
   __syncthreads();
   for (int k = tid; k < K; k += kTaskThreads)
-    if (live[(long)t * K + k]) cls[atomicAdd(&n_cls, 1)] = k;   // any order: every class is handled independently
+    if (live_t[k]) cls[atomicAdd(&n_cls, 1)] = k;   // any order: every class is handled independently
   __syncthreads();
   const int nc = n_cls;
-  // log-normalisers: four warps per class (the partition of lognorm_rows_kernel), four classes at a time
+  // log-normalisers: four warps per class (the partition of the dense kernel's warp, four times), four classes at a time
   {
     const int grp = warp >> 2, gtid = tid & 127, gwarp = warp & 3;
     for (int c0 = 0; c0 < nc; c0 += kTaskWarps / 4) {
@@ -594,7 +681,7 @@ estep_task_kernel(const float* __restrict__ alpha, const float* __restrict__ log
     }
   }
   // contraction columns: l3[t, q, k] = sum_d logz[t, q, d] (alpha[t, k, d] - 1) for the live classes, a warp per (class, four
-  // queries): lanes stride over d, one shuffle tree per query (the arithmetic of logits_rows_kernel)
+  // queries): lanes stride over d, one shuffle tree per query
   for (int c0 = 0; c0 < nc; c0 += kTaskRowsPerPass) {
     const int np = min(kTaskRowsPerPass, nc - c0);
     for (int i = tid; i < np * D; i += kTaskThreads) {
@@ -625,14 +712,55 @@ estep_task_kernel(const float* __restrict__ alpha, const float* __restrict__ log
     }
     __syncthreads();
   }
+  // ---- which soft-max this launch takes (uniform over the whole grid: every CTA reads the same device words, and the only
+  // word written during the launch, a_iter <- it, reads as "not valid yet" whether a CTA sees the old or the new value)
+  bool sparse = sp.dead_max != nullptr && nc <= kSparseMaxLive && (labels != nullptr || !hard);
+  bool need_zero = false;
+  if (sparse) {
+    const int a_it = *sp.a_iter, s_it = *sp.set_iter;
+    sparse = (*sp.changed == 0) && (s_it <= a_it) && (a_it < sp.it);
+    // (last_full is double-buffered by the parity of the iteration: slices of this task that take a full row during this
+    // launch write the other half)
+    need_zero = (sp.last_full[((sp.it - 1) & 1) * (int)gridDim.x + t] == sp.it - 1) || (*sp.last_dense == sp.it - 1);
+  }
+  // per class the v term of the logit, and its maximum over the dead classes
+  float dv = -CUDART_INF_F;
+  const float fn = (float)n;
+  for (int k = tid; k < K; k += kTaskThreads) {
+    const float term = (lambd * v[(long)t * K + k]) / fn;
+    lterm[k] = term;
+    if (!live_t[k]) dv = fmaxf(dv, term);
+  }
+  dv = warp_max_f32(dv);
+  if (lane == 0) wmax[warp] = dv;
+  if (sparse) {   // ascending order of the live classes (rank sort; nc <= kSparseMaxLive)
+    for (int i = tid; i < nc; i += kTaskThreads) {
+      int rank = 0;
+      for (int j = 0; j < nc; ++j) rank += cls[j] < cls[i];
+      sorted[rank] = cls[i];
+    }
+  }
   // the norm / l3 entries written above by other threads of this CTA are read below: make them visible
   __threadfence_block();
   __syncthreads();
+  float dead_v = wmax[0];
+#pragma unroll
+  for (int w = 1; w < kTaskWarps; ++w) dead_v = fmaxf(dead_v, wmax[w]);
   // responsibilities of the task's queries, one warp per query
+  bool any_full = false;
   for (int q = q_lo + warp; q < q_hi; q += kTaskWarps) {
     const int row = t * n + q;
-    if (K <= 1024) softmax_row_reg(l3, norm, v, lambd, u, labels, row, lane, n, K, hard);
-    else softmax_row_gen(l3, norm, v, lambd, u, labels, row, lane, n, K, hard);
+    bool done = false;
+    if (sparse) done = softmax_row_sparse(l3, norm, lterm, u, labels, row, lane, n, K, hard, sorted, nc,
+                                          sp.dead_max[row] + dead_v, need_zero);
+    if (!done) {
+      softmax_row_reg(l3, norm, v, lambd, u, labels, row, lane, n, K, hard, live_t, sp.dead_max ? sp.dead_max + row : nullptr);
+      any_full = true;
+    }
+  }
+  if (sp.dead_max) {
+    if (any_full && lane == 0) sp.last_full[(sp.it & 1) * (int)gridDim.x + t] = sp.it;   // (every writer writes the same value)
+    if (!sparse && tid == 0) *sp.a_iter = sp.it;                  // dead_max of every row was recomputed in this launch
   }
 }
 
@@ -810,17 +938,19 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
     if (cudaError_t e = logits_simt(logz, alpha, dst, T, n, K, D, gate, st)) return e;
   }
   const int qrows = T * n;
+  int* last_dense = gate ? sp->last_dense : nullptr;
+  const int it = gate ? sp->it : 0;
   if (K <= 1024)
-    softmax_reg_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard, gate);
+    softmax_reg_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard, gate, it, last_dense);
   else
-    softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard, gate);
+    softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard, gate, it, last_dense);
   note_launch(1);
   if (gate) {
     // few live rows: the whole E-step of a task in one kernel (the dense kernels above returned at once)
     const size_t smem = (size_t)kTaskRowsPerPass * D * sizeof(float);
     if (K > 1024) return cudaErrorInvalidValue;   // (the class list of a task lives in a 1024-entry shared array; D = K <= 1024)
     estep_task_kernel<<<dim3(T, (n + kTaskSlice - 1) / kTaskSlice), kTaskThreads, smem, st>>>(alpha, logz, v, lambd, norm, dst, u,
-                                                                                            labels, live, n, K, D, hard, gate);
+                                                                                            labels, live, n, K, D, hard, *sp);
     note_launch(1);
   }
   return cudaGetLastError();

@@ -87,6 +87,14 @@ struct SparseRows {
   const int* n_new;
   const int* gate;
   int cap;
+  // state of the exact sparse soft-max of estep_task_kernel (all device pointers; nullptr = always the full rows)
+  int it;                 // outer iteration of this call
+  const int* changed;     // != 0: the set of dead rows changed at this outer iteration
+  const int* set_iter;    // last outer iteration at which it changed
+  int* a_iter;            // outer iteration at which dead_max was last computed
+  float* dead_max;        // [T, n] per query: max over the dead classes of float(norm + l3)
+  int* last_full;         // [2, T] (by iteration parity) last outer iteration in which a query of the task took a full row
+  int* last_dense;        // last outer iteration whose E-step ran through the dense kernels
 };
 // Tensor-core form of the dense moments: u^T and (log z)^T staged as [T, K, np] / [T, D, np] (np = n rounded up to 4)
 struct MomentsTc {

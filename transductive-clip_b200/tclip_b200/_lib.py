@@ -17,6 +17,7 @@ TCLIP_OK = 0
 TCLIP_MM_DENSE = 0
 TCLIP_MM_SKIP_DEAD = 1
 TCLIP_FLAG_IN_FLIGHT = 1
+TCLIP_FLAG_FULL_SOFTMAX = 2
 
 
 class TclipLibraryError(RuntimeError):

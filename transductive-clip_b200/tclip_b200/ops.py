@@ -424,7 +424,7 @@ def release_workspaces(stream_ids=None) -> None:
 def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lambd: float, hard: bool,
                  x_s: torch.Tensor | None = None, y_s: torch.Tensor | None = None, check_every: int = 50,
                  tol: float = 1e-11, mm_mode: int = TCLIP_MM_DENSE, record_events: bool = False,
-                 spec_probe: bool = False, in_flight: bool = False) -> dict:
+                 spec_probe: bool = False, in_flight: bool = False, full_softmax: bool = False) -> dict:
     """The fused driver ``tclip_dirichlet_em_run``: the whole EM loop enqueued on the current stream.
     Returns device tensors u, alpha, v, labels, criterions, mm_iters, n_live, mm_rows (+ ``events``).
     ``spec_probe`` (measurement only) adds ``spec_probe`` int32 [iters, cap, 4]: per live row of the few-rows M-step kernel
@@ -468,7 +468,7 @@ def dirichlet_em(x_q: torch.Tensor, n_class: int, iters: int, iter_mm: int, lamb
         x_q=_ptr(x_q), x_s=_ptr(x_s), y_s=_ptr(y_s), u=_ptr(out["u"]), alpha=_ptr(out["alpha"]), v=_ptr(out["v"]),
         labels=_ptr(out["labels"]), criterions=_ptr(out["criterions"]), mm_iters=_ptr(out["mm_iters"]),
         n_live=_ptr(out["n_live"]), mm_rows=_ptr(out["mm_rows"]), mm_crit=_ptr(out["mm_crit"]),
-        spec_probe=_ptr(out.get("spec_probe")), flags=_lib.TCLIP_FLAG_IN_FLIGHT if in_flight else 0,
+        spec_probe=_ptr(out.get("spec_probe")), flags=(_lib.TCLIP_FLAG_IN_FLIGHT if in_flight else 0) | (_lib.TCLIP_FLAG_FULL_SOFTMAX if full_softmax else 0),
         iter_events=ctypes.cast(ev_arr, ctypes.POINTER(ctypes.c_void_p)) if ev_arr is not None else None,
         mm_events=ctypes.cast(mm_arr, ctypes.POINTER(ctypes.c_void_p)) if mm_arr is not None else None)
     nbytes = lib.tclip_dirichlet_em_workspace_bytes(ctypes.byref(p))
