@@ -457,7 +457,7 @@ struct SpecArgs {
 // So, unlike the empty clusters (mm_chunk_kernel<FR>), live rows offer no exact early stop worth its cost: carrying the
 // per-iteration vote in the product kernel made it 14 % slower, and it is therefore compiled into this build only.
 template <int W, int NPW, bool PIPE, bool PROBE>
-__global__ void __launch_bounds__(32 * W, (!PIPE && W == 4 && NPW == 4) ? kSpecLeanMinBlocks : 1)
+__global__ void __launch_bounds__(32 * W, (W == 4 && NPW == 4) ? (PIPE ? 3 : kSpecLeanMinBlocks) : 0)
 mm_spec_kernel(const SpecArgs g) {
   if (!(g.split_gate[0] <= g.split_gate[1])) return;
   if ((int)blockIdx.x >= *g.n_rows_dev) return;  // CTA-uniform
@@ -605,6 +605,11 @@ mm_spec_kernel(const SpecArgs g) {
     if (dys[j] < D) aout[dys[j]] = a[j].y;
   }
 }
+
+// (Tried in round 2 and removed: deciding on the device which form runs and launching the up to 20 chunk kernels from there —
+// CUDA dynamic parallelism, tail-launch stream — instead of enqueueing 20 launches that return at once when this kernel is
+// selected (64 us of a tail iteration).  Correct, but device-side launches of these grids are far slower than the host's:
+// outer iteration 0 went 9.3 -> 14.0 ms, a tail iteration 0.99 -> 1.10 ms, a batch with 1900 live rows 114 -> 178 ms.)
 
 // One CTA: the checks in order, each over the terms of all speculated rows (fixed summation order) plus the cached dead
 // rows; the first one below tol fires.  state->iters_done and state->fired are what the reference would have ended with.
