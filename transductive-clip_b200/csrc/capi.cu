@@ -793,6 +793,9 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
     const char* e = std::getenv("TCLIP_SPARSE_SOFTMAX");
     return e && std::string(e) == "0";
   }();
+  // the per-task E-step kernel keeps a task's class list in a 1024-entry shared array: more classes than that always take the
+  // dense E-step (a cap of 0 never selects the row-wise kernels)
+  const int sparse_cap = (K <= 1024) ? kSparseCap : 0;
   const tclip::MomentsTc mtc{w.uT, w.logzT, w.np};
   if (!moments_simt) TCLIP_CUDA(tclip::transpose_pad(w.logz, w.logzT, T, n, D, w.np, nullptr, st));
   if (skip) {
@@ -817,7 +820,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       const int n_tiles = (rows + 1023) / 1024;
       classify_count_kernel<<<n_tiles, 1024, 0, st>>>(w.live, w.cache_valid, w.dead_age, w.tile_counts, rows);
       classify_write_kernel<<<n_tiles, 1024, 0, st>>>(w.live, w.cache_valid, w.frozen, w.dead_age, w.tile_counts, w.list_live,
-                                                     w.list_new, w.counts, w.gate, kSparseCap, w.split_gate, kSplitCap,
+                                                     w.list_new, w.counts, w.gate, sparse_cap, w.split_gate, kSplitCap,
                                                      w.work_ctr, rows, it, w.ss_state);
       tclip::note_launch(2);
       sp.rows_live = w.list_live;
@@ -825,7 +828,7 @@ int tclip_dirichlet_em_run(const tclip_dirichlet_problem* p, void* workspace, si
       sp.rows_new = w.list_new;
       sp.n_new = w.counts + 1;
       sp.gate = w.gate;
-      sp.cap = kSparseCap;
+      sp.cap = kSparseCap;   // (grid size of the row-wise kernels; the gate itself compares with sparse_cap)
       sp.it = it;
       if (!sparse_softmax_off && !(p->flags & TCLIP_FLAG_FULL_SOFTMAX)) {
         sp.changed = w.counts + 2;

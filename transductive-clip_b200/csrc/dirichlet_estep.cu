@@ -945,10 +945,10 @@ cudaError_t estep(const float* alpha, const float* logz, const float* v, float l
   else
     softmax_kernel<<<(qrows + 3) / 4, 128, 0, st>>>(dst, norm, v, lambd, u, labels, qrows, n, K, hard, gate, it, last_dense);
   note_launch(1);
-  if (gate) {
+  if (gate && K <= 1024) {   // (K > 1024: the driver's gate never selects the row-wise form, the class list of a task lives
+                             // in a 1024-entry shared array)
     // few live rows: the whole E-step of a task in one kernel (the dense kernels above returned at once)
     const size_t smem = (size_t)kTaskRowsPerPass * D * sizeof(float);
-    if (K > 1024) return cudaErrorInvalidValue;   // (the class list of a task lives in a 1024-entry shared array; D = K <= 1024)
     estep_task_kernel<<<dim3(T, (n + kTaskSlice - 1) / kTaskSlice), kTaskThreads, smem, st>>>(alpha, logz, v, lambd, norm, dst, u,
                                                                                             labels, live, n, K, D, hard, *sp);
     note_launch(1);
