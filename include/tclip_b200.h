@@ -172,7 +172,7 @@ int tclip_kmeans_udiff(const float* a, const float* b, float* task_norm, float* 
 
 /* ---- fused driver of the k-means family: the whole run_method loop of soft k-means (soft_kmeans.py:168-220), EM-Gaussian
  * with identity covariance (em_gaussian.py:171-229) or hard k-means (hard_kmeans.py:153-211), up to but excluding the
- * accuracy, enqueued on one stream without host synchronisation.  When min(n_query, dim) <= 96 the loop runs in the
+ * accuracy, enqueued on one stream without host synchronisation.  With n_query <= 96 the loop runs in the
  * coordinates of the task's own samples (Cholesky factor of the n x n Gram matrix; every centroid is a combination of the
  * task's samples and only distances to those samples are ever needed): same direct-difference distances as the reference,
  * in <= n dimensions instead of D, and w itself is never formed inside the loop — `coef` receives its coefficients and

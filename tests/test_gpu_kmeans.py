@@ -118,7 +118,7 @@ def test_sample_coordinates_equal_feature_space(dev):
     the feature-space kernels (tclip_kmeans_centroids / tclip_kmeans_assign), incl. a task with duplicated samples (singular
     Gram matrix) and n > D."""
     from tclip_b200 import ops, tasks
-    for (K, D, n, seed) in ((60, 256, 75, 5), (40, 90, 33, 6), (30, 24, 75, 7)):
+    for (K, D, n, seed) in ((60, 256, 75, 5), (40, 90, 33, 6), (30, 24, 75, 7), (30, 40, 120, 8), (20, 200, 96, 9)):   # n = 120: fallback
         td, _ = tasks.make_zero_shot_batch(3, K, n_query=n, seed=seed, softmax_feature=False, embed_dim=D)
         x = td["x_q"].to(dev)
         x[1, 5] = x[1, 2]                      # duplicated sample: rank-deficient Gram matrix
@@ -138,7 +138,10 @@ def test_sample_coordinates_equal_feature_space(dev):
             assert (res["labels"] == labels).float().mean().item() >= 0.999
             np.testing.assert_allclose(res["u"].cpu().numpy(), u.cpu().numpy(), atol=2e-4)
             np.testing.assert_allclose(res["w"].cpu().numpy(), w.cpu().numpy(), rtol=1e-3, atol=2e-5)
-            np.testing.assert_allclose(ops.kmeans_expand_centroids(res["coef"], x).cpu().numpy(), res["w"].cpu().numpy(), atol=1e-6)
+            if res["coef"] is not None:
+                np.testing.assert_allclose(ops.kmeans_expand_centroids(res["coef"], x).cpu().numpy(), res["w"].cpu().numpy(), atol=1e-6)
+            else:
+                assert n > 96    # the feature-space fallback of the driver
 
 
 def test_kmeans_rn50_shape_properties(dev):

@@ -16,8 +16,8 @@
 // the w-space loop by 8 MB of HBM traffic per task and iteration).  The coefficients c ("coef", laid out like u) are kept
 // so that w = coef^T x can be produced when somebody asks for it (tclip_kmeans_expand_centroids).
 //
-// When D <= n the features are used as they are (Z = x, r = D); when min(n, D) > kMaxR the loop falls back to the
-// feature-space kernels of kmeans.cu.
+// When D <= n the features are used as they are (Z = x, r = D); with more than kMaxR = 96 samples per task the loop falls
+// back to the feature-space kernels of kmeans.cu.
 //
 // One outer iteration = kproj_iter_kernel (cluster sizes, centroids in sample coordinates with the reference's
 // empty-cluster rule, coefficients, squared distances) + assign_kernel (soft-max / arg-min rows, kmeans.cu)
@@ -370,7 +370,8 @@ inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
 }  // namespace
 
-bool kmeans_sample_coordinates(int n, int D) { return std::min(n, D) <= kMaxR; }
+// the iteration kernel holds all n samples of a task (and min(n, D) coordinates) in shared memory
+bool kmeans_sample_coordinates(int n, int D) { return n <= kMaxR && D >= 1; }
 
 // rq: row pitch of the sample-coordinate arrays
 static int coord_pitch(int n, int D) { return 16 * ((std::min(n, D) + 15) / 16); }
