@@ -187,3 +187,22 @@ def test_feature_extraction_epilogue(dev):
         np.testing.assert_allclose(got_v.numpy(), want_v.numpy(), rtol=2e-6, atol=1e-7)
         np.testing.assert_allclose(got_s.numpy(), want_s.numpy(), rtol=2e-4, atol=1e-7)
         assert torch.allclose(got_s.sum(-1), torch.ones(N), atol=1e-5)
+
+
+def test_cluster_fused_softmax_matches(dev):
+    """TCLIP_KM_FUSED=1 (the soft-max finished inside the iteration kernel, class tiles of a task in one thread-block cluster,
+    row statistics exchanged through distributed shared memory) gives what the default separate kernels give.  The knob is
+    read once per process, so the fused run is a child process: the golden fixtures, config-4 shape and the rank-deficient
+    sample-coordinate cases of this file."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("TCLIP_KM_FUSED") == "1":
+        pytest.skip("already the fused child")
+    env = dict(os.environ, TCLIP_KM_FUSED="1")
+    sel = "golden or vs_oracle or sample_coordinates"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel,
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout

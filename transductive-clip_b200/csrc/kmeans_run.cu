@@ -22,7 +22,9 @@
 // One outer iteration = kproj_iter_kernel (cluster sizes, centroids in sample coordinates with the reference's
 // empty-cluster rule, coefficients, squared distances) + assign_kernel (soft-max / arg-min rows, kmeans.cu)
 // [+ colsum_v for EM-Gaussian's v, + the logged criterion of hard k-means].
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <math_constants.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -138,10 +140,26 @@ chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) 
 // KT classes per CTA (128: 4 class pairs per thread, 107 KB of shared memory = 2 CTAs per SM at RN50 shape; 64: 2 pairs, 69 KB =
 // 3 CTAs per SM).  kUS: row pitch of the u tile (keeps float4 / float2 alignment, spreads the staging stores over the banks);
 // kWS: row pitch of the transposed centroid tile (64-bit stores of 16 consecutive rows hit 16 bank pairs).
-template <int MJ, int MN, int KT>
+// What the fused form needs to turn the distances into responsibilities inside the same launch
+struct AssignArgs {
+  float* u_out;        // [T, n, K] (may be the u the centroids were formed from: a CTA reads and writes its own class tile only)
+  int* labels;         // [T, n]
+  float* v;            // [T, K] EM-Gaussian: read (old v) for the logits, rewritten from the new u; nullptr otherwise
+  float temperature;
+  float lambd;
+  int method;          // 0 soft k-means, 1 EM-Gaussian, 2 hard k-means
+};
+
+// FUSED: the class tiles of a task form ONE thread-block cluster (K <= 8 * KT), and the soft-max / arg-min over all K classes
+// of every query is finished inside the launch: per-tile row maxima, sums and arg-extrema are exchanged through distributed
+// shared memory (three cluster barriers), u [and v, labels] are written directly and the distances never go to global
+// memory.  Replaces kproj_iter_kernel + assign_kernel [+ colsum_v_kernel] and the d2 round trip (2 x 30 MB per iteration at
+// RN50 shape).
+template <int MJ, int MN, int KT, bool FUSED>
 __global__ void __launch_bounds__(256)
-kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__ u, float* __restrict__ coef,
-                  float* __restrict__ wt, float* __restrict__ d2, int n, int K, int r, int mode, int want_d2) {
+kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* u, float* __restrict__ coef,
+                  float* __restrict__ wt, float* __restrict__ d2, int n, int K, int r, int mode, int want_d2,
+                  const AssignArgs as) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
   constexpr int kUS = KT + 4, kWS = KT + 2, CPT = KT / 16, PQ = CPT / 2;   // classes / class pairs per thread
   extern __shared__ float sm[];
@@ -256,66 +274,256 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
 #pragma unroll
     for (int q = 0; q < PQ; ++q) *reinterpret_cast<float2*>(us + (tx + 16 * m) * kUS + ty * CPT + 2 * q) = acc[q][m];
   __syncthreads();
-  float* db = d2 + (long)t * n * K;
-  for (int i = tid; i < n * KT; i += 256) {
-    const int row = i / KT, kk = i - row * KT;
-    if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[row * kUS + kk];
+  if constexpr (!FUSED) {
+    float* db = d2 + (long)t * n * K;
+    for (int i = tid; i < n * KT; i += 256) {
+      const int row = i / KT, kk = i - row * KT;
+      if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[row * kUS + kk];
+    }
+  } else {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int n_tiles = (int)cluster.num_blocks();
+    constexpr int LPT = KT / 32;                  // logits per lane and row
+    // per-row exchange slots of this CTA (read by the other CTAs of the cluster through distributed shared memory)
+    float* xmax = cs + KT;                        // [NQ] row maximum over this tile
+    float* xsum = xmax + NQ;                      // [NQ] row sum of exp over this tile
+    float* xbest = xsum + NQ;                     // [NQ] best (arg-max / arg-min) probability of this tile
+    int* xbestk = reinterpret_cast<int*>(xbest + NQ);   // [NQ] its class
+    float* gstat = reinterpret_cast<float*>(xbestk + NQ);   // [NQ] cluster-wide maximum, then sum
+    const int lane = tid & 31, warp = tid >> 5;
+    const float fn = (float)n;
+    const bool hard = as.method == 2;
+    // logits of this tile (assign_kernel's formulas), classes beyond K never count
+    for (int i = tid; i < n * KT; i += 256) {
+      const int row = i / KT, kk = i - row * KT, k = k0 + kk;
+      const float d = us[row * kUS + kk];
+      float l = -CUDART_INF_F;
+      if (k < K) {
+        if (hard) l = d;
+        else {
+          l = as.temperature * (-0.5f * d);
+          if (as.method == 1) l += (as.lambd * as.v[(long)t * K + k]) / fn;
+        }
+      }
+      us[row * kUS + kk] = l;
+    }
+    __syncthreads();
+    for (int row = warp; row < n; row += 8) {
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < LPT; ++j) mx = fmaxf(mx, us[row * kUS + lane + 32 * j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) xmax[row] = mx;
+    }
+    cluster.sync();
+    for (int row = tid; row < n; row += 256) {
+      float mx = -CUDART_INF_F;
+      for (int rk = 0; rk < n_tiles; ++rk) mx = fmaxf(mx, cluster.map_shared_rank(xmax, rk)[row]);
+      gstat[row] = mx;
+    }
+    __syncthreads();
+    for (int row = warp; row < n; row += 8) {
+      const float mx = gstat[row];
+      float sum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < LPT; ++j) {
+        const float e = expf(us[row * kUS + lane + 32 * j] - mx);   // exp(-inf) = 0 for the padding classes
+        us[row * kUS + lane + 32 * j] = e;
+        sum += e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) xsum[row] = sum;
+    }
+    cluster.sync();
+    __syncthreads();
+    for (int row = tid; row < n; row += 256) {
+      float sum = 0.0f;
+      for (int rk = 0; rk < n_tiles; ++rk) sum += cluster.map_shared_rank(xsum, rk)[row];   // rank order: reproducible
+      gstat[row] = sum;
+    }
+    __syncthreads();
+    // probabilities and the tile's arg-extremum (arg-max of u; hard k-means: arg-min of softmax(+d2), lowest class on ties)
+    for (int row = warp; row < n; row += 8) {
+      const float sum = gstat[row];
+      float best = hard ? CUDART_INF_F : -1.0f;
+      int best_k = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < LPT; ++j) {
+        const int kk = lane + 32 * j, k = k0 + kk;
+        const float p = us[row * kUS + kk] / sum;
+        us[row * kUS + kk] = p;
+        if (k < K && (hard ? p < best : p > best)) {
+          best = p;
+          best_k = k;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        if ((hard ? ob < best : ob > best) || (ob == best && ok < best_k)) {
+          best = ob;
+          best_k = ok;
+        }
+      }
+      if (lane == 0) {
+        xbest[row] = best;
+        xbestk[row] = best_k;
+      }
+    }
+    cluster.sync();
+    int* gk = reinterpret_cast<int*>(gstat);
+    __syncthreads();
+    for (int row = tid; row < n; row += 256) {
+      float best = hard ? CUDART_INF_F : -1.0f;
+      int best_k = 0x7fffffff;
+      for (int rk = 0; rk < n_tiles; ++rk) {
+        const float ob = cluster.map_shared_rank(xbest, rk)[row];
+        const int ok = cluster.map_shared_rank(xbestk, rk)[row];
+        if ((hard ? ob < best : ob > best) || (ob == best && ok < best_k)) {
+          best = ob;
+          best_k = ok;
+        }
+      }
+      gk[row] = best_k;
+      if (blockIdx.x == 0 && as.labels) as.labels[(long)t * n + row] = best_k;
+    }
+    __syncthreads();
+    float* ub_out = as.u_out + (long)t * n * K;
+    for (int i = tid; i < n * KT; i += 256) {
+      const int row = i / KT, kk = i - row * KT, k = k0 + kk;
+      if (k >= K) continue;
+      const float p = hard ? (k == gk[row] ? 1.0f : 0.0f) : us[row * kUS + kk];
+      if (hard) us[row * kUS + kk] = p;
+      ub_out[(long)row * K + k] = p;
+    }
+    if (as.method == 1) {   // v_update from the new u (em_gaussian.py:130-136): column sums in query order, as colsum_v_kernel
+      __syncthreads();
+      if (tid < KT && k0 + tid < K) {
+        float sm_ = 0.0f;
+        for (int i = 0; i < n; ++i) sm_ += us[i * kUS + tid];
+        as.v[(long)t * K + k0 + tid] = logf(sm_ / fn + kEps) + 1.0f;
+      }
+    }
+    cluster.sync();   // no CTA may leave while another still reads its exchange slots
   }
 }
 
+// The fused form needs every class tile of a task in one (portable) cluster
+constexpr int kMaxClusterTiles = 8;
+
 template <int MJ, int MN, int KT>
 cudaError_t launch_iter_kt(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
-                           int r, int mode, int want_d2, cudaStream_t st) {
+                           int r, int mode, int want_d2, const AssignArgs* as, cudaStream_t st) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1, kUS = KT + 4, kWS = KT + 2;
-  const size_t smem = sizeof(float) * ((size_t)NQ * ZP + 4 + (size_t)NQ * kUS + (size_t)RQ * kWS + KT);
+  const size_t smem_plain = sizeof(float) * ((size_t)NQ * ZP + 4 + (size_t)NQ * kUS + (size_t)RQ * kWS + KT);
+  const int tiles = (K + KT - 1) / KT;
   static PerDeviceFlags attr_set;
   const int slot = current_device_slot();
-  if (smem > 48 * 1024 && (slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0)) {
-    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool first = slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0;
+  if constexpr (KT == 128) {
+    if (as) {
+      const size_t smem = smem_plain + sizeof(float) * 5 * NQ;   // + the exchange slots
+      auto kern = kproj_iter_kernel<MJ, MN, KT, true>;
+      if (first) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem_plain);
+        if (e != cudaSuccess) return e;
+        if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(tiles, T);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = tiles;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      note_launch();
+      return cudaLaunchKernelEx(&cfg, kern, Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, *as);
+    }
+  }
+  if (as) return cudaErrorInvalidValue;   // the caller checks kmeans_fused_assign() first
+  if (smem_plain > 48 * 1024 && first) {
+    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_plain);
     if (e != cudaSuccess) return e;
+    if constexpr (KT == 128) {
+      e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(smem_plain + sizeof(float) * 5 * NQ));
+      if (e != cudaSuccess) return e;
+    }
     if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
   }
-  kproj_iter_kernel<MJ, MN, KT><<<dim3((K + KT - 1) / KT, T), 256, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2);
+  kproj_iter_kernel<MJ, MN, KT, false><<<dim3(tiles, T), 256, smem_plain, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2,
+                                                                                AssignArgs{});
   note_launch();
   return cudaGetLastError();
 }
 
 // classes per CTA: 128; TCLIP_KM_TILE=64 selects the 64-class tile (3 CTAs per SM at RN50 shape instead of 2) — measured equal
 // (0.172 vs 0.173 ms per iteration, profiles/r2_kmeans.md): the kernel is not limited by occupancy
-template <int MJ, int MN>
-cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
-                        int r, int mode, int want_d2, cudaStream_t st) {
+int km_tile() {
   static const int tile = [] {
     const char* e = std::getenv("TCLIP_KM_TILE");
     return (e && std::atoi(e) == 64) ? 64 : 128;
   }();
-  if (tile == 128) return launch_iter_kt<MJ, MN, 128>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-  return launch_iter_kt<MJ, MN, 64>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+  return tile;
+}
+
+// TCLIP_KM_FUSED=1 finishes the soft-max inside the iteration kernel when the class tiles of a task fit one cluster
+// (K <= 1024).  Off by default — measured SLOWER at the RN50 shape (profiles/r2_kmeans.md, "cluster-fused soft-max"): only
+// 33 clusters of 8 x 107 KB CTAs are resident (264 of the 296 CTA slots), so the 100 tasks of a batch take 4 quantised waves
+// of 56 us (224 us under ncu) where the separate kernels take 143 + 35 us; and per resident cluster the three exchange rounds
+// cost what the whole assign kernel costs (1.70 vs 1.73 us per task-iteration at any batch size).  Same results
+// (tests/test_gpu_kmeans.py::test_cluster_fused_softmax_matches).
+bool kmeans_fused_assign(int K) {
+  static const bool on = [] {
+    const char* e = std::getenv("TCLIP_KM_FUSED");
+    return e && std::atoi(e) == 1;
+  }();
+  return on && km_tile() == 128 && (K + 127) / 128 <= kMaxClusterTiles;
+}
+
+template <int MJ, int MN>
+cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
+                        int r, int mode, int want_d2, const AssignArgs* as, cudaStream_t st) {
+  if (km_tile() == 128) return launch_iter_kt<MJ, MN, 128>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+  return launch_iter_kt<MJ, MN, 64>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
 }
 
 template <int MJ>
 cudaError_t launch_iter_mn(int mn, const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n,
-                           int K, int r, int mode, int want_d2, cudaStream_t st) {
+                           int K, int r, int mode, int want_d2, const AssignArgs* as, cudaStream_t st) {
   switch (mn) {
-    case 1: return launch_iter<MJ, 1>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    case 2: return launch_iter<MJ, 2>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    case 3: return launch_iter<MJ, 3>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    case 4: return launch_iter<MJ, 4>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    case 5: return launch_iter<MJ, 5>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    default: return launch_iter<MJ, 6>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 1: return launch_iter<MJ, 1>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 2: return launch_iter<MJ, 2>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 3: return launch_iter<MJ, 3>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 4: return launch_iter<MJ, 4>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 5: return launch_iter<MJ, 5>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    default: return launch_iter<MJ, 6>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
   }
 }
 
 cudaError_t iterate(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K, int r,
-                    int mode, int want_d2, cudaStream_t st) {
+                    int mode, int want_d2, const AssignArgs* as, cudaStream_t st) {
   const int mj = (r + 15) / 16, mn = (n + 15) / 16;
   switch (mj) {
-    case 1: return launch_iter_mn<1>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    case 2: return launch_iter_mn<2>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    case 3: return launch_iter_mn<3>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    case 4: return launch_iter_mn<4>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    case 5: return launch_iter_mn<5>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
-    default: return launch_iter_mn<6>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, st);
+    case 1: return launch_iter_mn<1>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 2: return launch_iter_mn<2>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 3: return launch_iter_mn<3>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 4: return launch_iter_mn<4>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 5: return launch_iter_mn<5>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    default: return launch_iter_mn<6>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
   }
 }
 
@@ -423,6 +631,7 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
   float* u_old = p.method == 2 ? static_cast<float*>(take(sizeof(float) * (size_t)T * n * K)) : nullptr;
   float* colsum = p.method == 1 ? static_cast<float*>(take(sizeof(float) * (size_t)T * K)) : nullptr;
   const bool coords = kmeans_sample_coordinates(n, D);
+  const bool fused = coords && kmeans_fused_assign(K);
   const float* Z = p.x;
   int zs = D, r = D;
   float *wt = nullptr, *w = p.w;
@@ -447,7 +656,7 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
   if (p.method == 1) KM_TRY(cudaMemsetAsync(p.v, 0, sizeof(float) * (size_t)T * K, st));
   // w_init (soft k-means, EM-Gaussian); hard k-means has none (hard_kmeans.py:186)
   if (p.method != 2) {
-    if (coords) KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, 0, 0, st));
+    if (coords) KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, 0, 0, nullptr, st));
     else KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, 0, st));
   } else {
     KM_TRY(cudaMemcpyAsync(u_old, p.u, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
@@ -455,14 +664,20 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
   if (p.iter_events && p.iter_events[0]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[0], st));
   for (int it = 0; it < p.iters; ++it) {
     const int mode = p.method == 2 ? 2 : 1;
-    if (coords) {
-      KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, st));
+    if (fused) {
+      // M-step, distances, u_update [and v_update] in one launch
+      const AssignArgs as{p.u, p.labels, p.method == 1 ? p.v : nullptr, p.temperature, p.lambd, p.method};
+      KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, &as, st));
     } else {
-      KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, mode == 2 ? 0 : 1, st));
-      KM_TRY(kmeans_sqdist(p.x, w, d2, T, n, K, D, st));
+      if (coords) {
+        KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, nullptr, st));
+      } else {
+        KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, mode == 2 ? 0 : 1, st));
+        KM_TRY(kmeans_sqdist(p.x, w, d2, T, n, K, D, st));
+      }
+      KM_TRY(kmeans_assign(d2, p.v, nullptr, p.temperature, p.lambd, p.u, p.labels, T, n, K, p.method, st));
+      if (p.method == 1) KM_TRY(colsum_v(p.u, colsum, p.v, nullptr, T, n, K, st));   // v_update after u_update (em_gaussian.py:212-218)
     }
-    KM_TRY(kmeans_assign(d2, p.v, nullptr, p.temperature, p.lambd, p.u, p.labels, T, n, K, p.method, st));
-    if (p.method == 1) KM_TRY(colsum_v(p.u, colsum, p.v, nullptr, T, n, K, st));   // v_update after u_update (em_gaussian.py:212-218)
     if (p.method == 2) {
       // logged twice per iteration upstream (hard_kmeans.py:203,208-209)
       KM_TRY(kmeans_udiff(u_old, p.u, task_norm, p.criterions + 2 * it, T, (long)n * K, st));
