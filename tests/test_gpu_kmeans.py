@@ -189,17 +189,17 @@ def test_feature_extraction_epilogue(dev):
         assert torch.allclose(got_s.sum(-1), torch.ones(N), atol=1e-5)
 
 
-def test_cluster_fused_softmax_matches(dev):
-    """TCLIP_KM_FUSED=1 (the soft-max finished inside the iteration kernel, class tiles of a task in one thread-block cluster,
-    row statistics exchanged through distributed shared memory) gives what the default separate kernels give.  The knob is
-    read once per process, so the fused run is a child process: the golden fixtures, config-4 shape and the rank-deficient
-    sample-coordinate cases of this file."""
+def test_unchained_loop_matches(dev):
+    """TCLIP_KM_CHAIN=0 (separate assignment / column-sum launches per iteration instead of the chained iteration kernel that
+    carries logits + per-tile row statistics from one launch to the next) passes the same parity cases.  The knob is read
+    once per process, so that run is a child process: the golden fixtures, the oracle cases incl. config-4 shape and the
+    rank-deficient sample-coordinate cases of this file."""
     import os
     import subprocess
     import sys
-    if os.environ.get("TCLIP_KM_FUSED") == "1":
-        pytest.skip("already the fused child")
-    env = dict(os.environ, TCLIP_KM_FUSED="1")
+    if os.environ.get("TCLIP_KM_CHAIN") == "0":
+        pytest.skip("already the unchained child")
+    env = dict(os.environ, TCLIP_KM_CHAIN="0")
     sel = "golden or vs_oracle or sample_coordinates"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel,
                         "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=600,

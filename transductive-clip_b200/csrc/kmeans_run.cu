@@ -19,14 +19,16 @@
 // When D <= n the features are used as they are (Z = x, r = D); with more than kMaxR = 96 samples per task the loop falls
 // back to the feature-space kernels of kmeans.cu.
 //
-// One outer iteration = kproj_iter_kernel (cluster sizes, centroids in sample coordinates with the reference's
-// empty-cluster rule, coefficients, squared distances) + assign_kernel (soft-max / arg-min rows, kmeans.cu)
-// [+ colsum_v for EM-Gaussian's v, + the logged criterion of hard k-means].
-#include <cooperative_groups.h>
+// One outer iteration of soft k-means / EM-Gaussian = ONE launch of kproj_iter_kernel<CHAIN = true>: u tile rebuilt from the
+// previous launch's logits and per-tile row statistics (u_update), cluster sizes [and v_update], centroids in sample
+// coordinates with the reference's empty-cluster rule, coefficients, squared distances, logits + row statistics for the next
+// launch; u, labels and v are materialised once after the last iteration (assign_kernel, colsum_v).  Hard k-means, whose
+// logged criterion needs every u: kproj_iter_kernel<false> + assign_kernel (arg-min rows, kmeans.cu) + criterion.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "tclip_kernels.cuh"
@@ -125,6 +127,17 @@ chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) 
   }
 }
 
+// Asynchronous global -> shared copies (cp.async, SASS LDGSTS); both addresses aligned to the request size
+__device__ __forceinline__ void cp_async_4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 // One outer iteration's M-step and distances for a tile of KT classes of one task, in sample coordinates.
 //   Z    [T, n, zs]   coordinates of the samples (Cholesky rows, or the features themselves), r used columns
 //   u    [T, n, K]    responsibilities the centroids are formed from
@@ -140,29 +153,31 @@ chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) 
 // KT classes per CTA (128: 4 class pairs per thread, 107 KB of shared memory = 2 CTAs per SM at RN50 shape; 64: 2 pairs, 69 KB =
 // 3 CTAs per SM).  kUS: row pitch of the u tile (keeps float4 / float2 alignment, spreads the staging stores over the banks);
 // kWS: row pitch of the transposed centroid tile (64-bit stores of 16 consecutive rows hit 16 bank pairs).
-// What the fused form needs to turn the distances into responsibilities inside the same launch
-struct AssignArgs {
-  float* u_out;        // [T, n, K] (may be the u the centroids were formed from: a CTA reads and writes its own class tile only)
-  int* labels;         // [T, n]
-  float* v;            // [T, K] EM-Gaussian: read (old v) for the logits, rewritten from the new u; nullptr otherwise
+// The chained form (soft k-means, EM-Gaussian): the launch of iteration i leaves the LOGITS of its distances,
+//   l = T (-d2 / 2) [+ lambda v / n]                      (soft_kmeans.py:105-125, em_gaussian.py:106-128)
+// and, per query and class tile, the tile's maximum m and sum of exp(l - m); the launch of iteration i + 1 turns them into
+// its u tile itself, u = exp(l - M) / S with M = max_tiles m and S = sum_tiles s exp(m - M) — the launch boundary is the
+// grid-wide barrier the soft-max over all K classes needs.  u, v and the labels are materialised once, after the last
+// iteration; no assignment / column-sum launch and no u round trip inside the loop.  EM-Gaussian's v_update
+// (em_gaussian.py:130-136) needs the column sums of u only, i.e. the cluster sizes the M-step forms anyway, per class: tile-local.
+struct ChainArgs {
+  const float2* stats_in;   // [T, n, tiles] of the logits in `lg`; nullptr: the input is u (first iteration)
+  float2* stats_out;        // [T, n, tiles] (the other buffer: CTAs of one task read all tiles while others write theirs)
+  float* lg;                // [T, n, K] logits, read (when stats_in) and rewritten in place: a CTA owns its class tile
+  const float* v0;          // [T, K] EM-Gaussian, u input only: the v the first logits use (zeros); nullptr otherwise
   float temperature;
   float lambd;
-  int method;          // 0 soft k-means, 1 EM-Gaussian, 2 hard k-means
+  int method;               // 0 soft k-means, 1 EM-Gaussian
 };
 
-// FUSED: the class tiles of a task form ONE thread-block cluster (K <= 8 * KT), and the soft-max / arg-min over all K classes
-// of every query is finished inside the launch: per-tile row maxima, sums and arg-extrema are exchanged through distributed
-// shared memory (three cluster barriers), u [and v, labels] are written directly and the distances never go to global
-// memory.  Replaces kproj_iter_kernel + assign_kernel [+ colsum_v_kernel] and the d2 round trip (2 x 30 MB per iteration at
-// RN50 shape).
-template <int MJ, int MN, int KT, bool FUSED>
+template <int MJ, int MN, int KT, bool CHAIN>
 __global__ void __launch_bounds__(256)
-kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* u, float* __restrict__ coef,
+kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__ u, float* __restrict__ coef,
                   float* __restrict__ wt, float* __restrict__ d2, int n, int K, int r, int mode, int want_d2,
-                  const AssignArgs as) {
+                  const ChainArgs ch) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
   constexpr int kUS = KT + 4, kWS = KT + 2, CPT = KT / 16, PQ = CPT / 2;   // classes / class pairs per thread
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* Zs = sm;                    // [NQ][ZP]   samples (rows >= n and columns >= r are zero)
   float* us = Zs + ((NQ * ZP + 3) & ~3);   // [NQ][kUS]  u tile, later the d2 tile (16-byte aligned for the float4 reads)
   float* nwT = us + NQ * kUS;        // [RQ][kWS]  MINUS the centroids, coordinate-major (class pairs are contiguous)
@@ -170,20 +185,96 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* u, float* __
   const int t = blockIdx.y, k0 = blockIdx.x * KT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const float* zb = Z + (long)t * n * zs;
-  const float* ub = u + (long)t * n * K;
-  for (int i = tid; i < NQ * RQ; i += 256) {
-    const int row = i / RQ, c = i - row * RQ;
-    Zs[row * ZP + c] = (row < n && c < r) ? zb[(long)row * zs + c] : 0.0f;
+  const bool from_logits = CHAIN && ch.stats_in != nullptr;
+  const float* ub = (from_logits ? ch.lg : u) + (long)t * n * K;
+  float* row_m = cs + KT;            // [NQ] chained form: maximum over all classes of the incoming logits, then of this tile's
+  float* row_s = row_m + NQ;         // [NQ] and the matching sum of exponentials
+  float* vt = row_s + NQ;            // [KT] EM-Gaussian: lambda v / n of this tile's classes
+  // Both tiles come in by asynchronous copies (LDGSTS: every request of the CTA is in flight at once, nothing is staged in
+  // registers); the padding is zeroed by plain stores to the other addresses.  With staged loads this phase was a chain of
+  // ~10 dependent DRAM round trips and 32 % of the kernel's warp time (profiles/r2_kmeans.md).
+  // Samples.  The Cholesky buffer has whole zero-padded rows of RQ floats: 128-bit loads, all issued before anything waits
+  // (the odd row pitch of the tile, which keeps the distance loop free of bank conflicts, rules out 16-byte async copies)
+  constexpr int ZV = RQ / 4, ZPER = (NQ * ZV + 255) / 256;
+  const bool z_rows = zs == RQ && (reinterpret_cast<uintptr_t>(zb) & 15) == 0;
+  float4 zr[ZPER];
+  if (z_rows) {
+#pragma unroll
+    for (int q = 0; q < ZPER; ++q) {
+      const int i = tid + 256 * q;
+      zr[q] = (i < n * ZV) ? __ldg(reinterpret_cast<const float4*>(zb) + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  } else {
+    for (int i = tid; i < NQ * RQ; i += 256) {
+      const int row = i / RQ, c = i - row * RQ;
+      if (row < n && c < r) cp_async_4(Zs + row * ZP + c, zb + (long)row * zs + c);
+      else Zs[row * ZP + c] = 0.0f;
+    }
   }
-  for (int i = tid; i < NQ * KT; i += 256) {
-    const int row = i / KT, c = i - row * KT;
-    us[row * kUS + c] = (row < n && k0 + c < K) ? ub[(long)row * K + k0 + c] : 0.0f;
+  if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(ub) & 15) == 0) {   // 16-byte requests: rows and tiles start on 16 bytes
+    for (int i = tid; i < NQ * (KT / 4); i += 256) {
+      const int row = i / (KT / 4), c = 4 * (i - row * (KT / 4));
+      if (row < n && k0 + c < K) cp_async_16(us + row * kUS + c, ub + (long)row * K + k0 + c);
+      else *reinterpret_cast<float4*>(us + row * kUS + c) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  } else {
+    for (int i = tid; i < NQ * KT; i += 256) {
+      const int row = i / KT, c = i - row * KT;
+      if (row < n && k0 + c < K) cp_async_4(us + row * kUS + c, ub + (long)row * K + k0 + c);
+      else us[row * kUS + c] = 0.0f;
+    }
   }
+  if (z_rows) {
+#pragma unroll
+    for (int q = 0; q < ZPER; ++q) {
+      const int i = tid + 256 * q;
+      if (i < NQ * ZV) {
+        const int row = i / ZV, c = 4 * (i - row * ZV);
+        float* dst = Zs + row * ZP + c;
+        dst[0] = zr[q].x;
+        dst[1] = zr[q].y;
+        dst[2] = zr[q].z;
+        dst[3] = zr[q].w;
+      }
+    }
+  }
+  if constexpr (CHAIN) {
+    if (from_logits && tid < n) {   // in the shadow of the copies: the soft-max statistics of the query over all tiles
+      const int tiles = gridDim.x;
+      const float2* sp = ch.stats_in + ((long)t * n + tid) * tiles;
+      float M = -CUDART_INF_F;
+      for (int i = 0; i < tiles; ++i) M = fmaxf(M, sp[i].x);
+      float S = 0.0f;
+      for (int i = 0; i < tiles; ++i) S += sp[i].y * expf(sp[i].x - M);   // tile order: reproducible
+      row_m[tid] = M;
+      row_s[tid] = S;
+    }
+  }
+  cp_async_wait_all();
   __syncthreads();
+  if constexpr (CHAIN) {
+    if (from_logits) {   // u tile = softmax row restricted to this tile (u_update); the padding stays zero
+      for (int row = tid >> 5; row < n; row += 8) {   // one warp per query
+        const float M = row_m[row], rS = 1.0f / row_s[row];
+#pragma unroll
+        for (int j = 0; j < KT / 32; ++j) {
+          const int c = (tid & 31) + 32 * j;
+          if (k0 + c < K) us[row * kUS + c] = expf(us[row * kUS + c] - M) * rS;
+        }
+      }
+      __syncthreads();
+    }
+  }
   if (tid < KT) {   // cluster sizes in sample order, like u.sum(1)
     float s = 0.0f;
     for (int i = 0; i < n; ++i) s += us[i * kUS + tid];
     cs[tid] = s;
+    if constexpr (CHAIN) {
+      if (ch.method == 1) {   // v_update of the u this launch started from (log(colsum / n + eps) + 1), or the given first v
+        const float v = from_logits ? logf(s / (float)n + kEps) + 1.0f : (k0 + tid < K ? ch.v0[(long)t * K + k0 + tid] : 0.0f);
+        vt[tid] = (ch.lambd * v) / (float)n;
+      }
+    }
   }
   __syncthreads();
   // centroids of this tile: wt[k, j] = sum_n u[n, k] Z[n, j] / max(cs, eps)
@@ -236,13 +327,14 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* u, float* __
   }
   // coefficients of the centroids in terms of the samples (what tclip_kmeans_expand_centroids turns into w)
   {
-    float* cb = coef + (long)t * n * K;
-    for (int i = tid; i < n * KT; i += 256) {
-      const int row = i / KT, kk = i - row * KT, k = k0 + kk;
-      if (k >= K) continue;
-      const float c = cs[kk];
-      if (mode == 0 || c > kEps) cb[(long)row * K + k] = us[row * kUS + kk] / fmaxf(c, kEps);
-      else if (mode == 2) cb[(long)row * K + k] = 0.0f;
+    // a thread keeps its class: one reciprocal of the cluster size, then a multiply per sample
+    const int kk = tid & (KT - 1), k = k0 + kk;
+    const float c = cs[kk];
+    const bool formed = mode == 0 || c > kEps;
+    if (k < K && (formed || mode == 2)) {
+      const float inv = formed ? 1.0f / fmaxf(c, kEps) : 0.0f;
+      float* cb = coef + (long)t * n * K + k;
+      for (int row = tid / KT; row < n; row += 256 / KT) cb[(long)row * K] = us[row * kUS + kk] * inv;
     }
   }
   if (!want_d2) return;
@@ -274,198 +366,68 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* u, float* __
 #pragma unroll
     for (int q = 0; q < PQ; ++q) *reinterpret_cast<float2*>(us + (tx + 16 * m) * kUS + ty * CPT + 2 * q) = acc[q][m];
   __syncthreads();
-  if constexpr (!FUSED) {
+  if constexpr (!CHAIN) {
     float* db = d2 + (long)t * n * K;
     for (int i = tid; i < n * KT; i += 256) {
       const int row = i / KT, kk = i - row * KT;
       if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[row * kUS + kk];
     }
   } else {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int n_tiles = (int)cluster.num_blocks();
-    constexpr int LPT = KT / 32;                  // logits per lane and row
-    // per-row exchange slots of this CTA (read by the other CTAs of the cluster through distributed shared memory)
-    float* xmax = cs + KT;                        // [NQ] row maximum over this tile
-    float* xsum = xmax + NQ;                      // [NQ] row sum of exp over this tile
-    float* xbest = xsum + NQ;                     // [NQ] best (arg-max / arg-min) probability of this tile
-    int* xbestk = reinterpret_cast<int*>(xbest + NQ);   // [NQ] its class
-    float* gstat = reinterpret_cast<float*>(xbestk + NQ);   // [NQ] cluster-wide maximum, then sum
+    // logits of this tile and their per-query statistics (one warp per query)
+    constexpr int LPT = KT / 32;
     const int lane = tid & 31, warp = tid >> 5;
-    const float fn = (float)n;
-    const bool hard = as.method == 2;
-    // logits of this tile (assign_kernel's formulas), classes beyond K never count
-    for (int i = tid; i < n * KT; i += 256) {
-      const int row = i / KT, kk = i - row * KT, k = k0 + kk;
-      const float d = us[row * kUS + kk];
-      float l = -CUDART_INF_F;
-      if (k < K) {
-        if (hard) l = d;
-        else {
-          l = as.temperature * (-0.5f * d);
-          if (as.method == 1) l += (as.lambd * as.v[(long)t * K + k]) / fn;
-        }
-      }
-      us[row * kUS + kk] = l;
-    }
-    __syncthreads();
+    const bool gauss = ch.method == 1;
     for (int row = warp; row < n; row += 8) {
+      float l[LPT];
       float mx = -CUDART_INF_F;
 #pragma unroll
-      for (int j = 0; j < LPT; ++j) mx = fmaxf(mx, us[row * kUS + lane + 32 * j]);
+      for (int j = 0; j < LPT; ++j) {
+        const int kk = lane + 32 * j;
+        l[j] = ch.temperature * (-0.5f * us[row * kUS + kk]);
+        if (gauss) l[j] += vt[kk];
+        if (k0 + kk >= K) l[j] = -CUDART_INF_F;
+        mx = fmaxf(mx, l[j]);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (lane == 0) xmax[row] = mx;
-    }
-    cluster.sync();
-    for (int row = tid; row < n; row += 256) {
-      float mx = -CUDART_INF_F;
-      for (int rk = 0; rk < n_tiles; ++rk) mx = fmaxf(mx, cluster.map_shared_rank(xmax, rk)[row]);
-      gstat[row] = mx;
-    }
-    __syncthreads();
-    for (int row = warp; row < n; row += 8) {
-      const float mx = gstat[row];
       float sum = 0.0f;
 #pragma unroll
       for (int j = 0; j < LPT; ++j) {
-        const float e = expf(us[row * kUS + lane + 32 * j] - mx);   // exp(-inf) = 0 for the padding classes
-        us[row * kUS + lane + 32 * j] = e;
-        sum += e;
+        sum += expf(l[j] - mx);   // exp(-inf) = 0 for the padding classes (every tile holds at least one class)
+        us[row * kUS + lane + 32 * j] = l[j];
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == 0) xsum[row] = sum;
-    }
-    cluster.sync();
-    __syncthreads();
-    for (int row = tid; row < n; row += 256) {
-      float sum = 0.0f;
-      for (int rk = 0; rk < n_tiles; ++rk) sum += cluster.map_shared_rank(xsum, rk)[row];   // rank order: reproducible
-      gstat[row] = sum;
+      if (lane == 0) ch.stats_out[((long)t * n + row) * gridDim.x + blockIdx.x] = make_float2(mx, sum);
     }
     __syncthreads();
-    // probabilities and the tile's arg-extremum (arg-max of u; hard k-means: arg-min of softmax(+d2), lowest class on ties)
-    for (int row = warp; row < n; row += 8) {
-      const float sum = gstat[row];
-      float best = hard ? CUDART_INF_F : -1.0f;
-      int best_k = 0x7fffffff;
-#pragma unroll
-      for (int j = 0; j < LPT; ++j) {
-        const int kk = lane + 32 * j, k = k0 + kk;
-        const float p = us[row * kUS + kk] / sum;
-        us[row * kUS + kk] = p;
-        if (k < K && (hard ? p < best : p > best)) {
-          best = p;
-          best_k = k;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
-        if ((hard ? ob < best : ob > best) || (ob == best && ok < best_k)) {
-          best = ob;
-          best_k = ok;
-        }
-      }
-      if (lane == 0) {
-        xbest[row] = best;
-        xbestk[row] = best_k;
-      }
-    }
-    cluster.sync();
-    int* gk = reinterpret_cast<int*>(gstat);
-    __syncthreads();
-    for (int row = tid; row < n; row += 256) {
-      float best = hard ? CUDART_INF_F : -1.0f;
-      int best_k = 0x7fffffff;
-      for (int rk = 0; rk < n_tiles; ++rk) {
-        const float ob = cluster.map_shared_rank(xbest, rk)[row];
-        const int ok = cluster.map_shared_rank(xbestk, rk)[row];
-        if ((hard ? ob < best : ob > best) || (ob == best && ok < best_k)) {
-          best = ob;
-          best_k = ok;
-        }
-      }
-      gk[row] = best_k;
-      if (blockIdx.x == 0 && as.labels) as.labels[(long)t * n + row] = best_k;
-    }
-    __syncthreads();
-    float* ub_out = as.u_out + (long)t * n * K;
+    float* lb = ch.lg + (long)t * n * K;
     for (int i = tid; i < n * KT; i += 256) {
-      const int row = i / KT, kk = i - row * KT, k = k0 + kk;
-      if (k >= K) continue;
-      const float p = hard ? (k == gk[row] ? 1.0f : 0.0f) : us[row * kUS + kk];
-      if (hard) us[row * kUS + kk] = p;
-      ub_out[(long)row * K + k] = p;
+      const int row = i / KT, kk = i - row * KT;
+      if (k0 + kk < K) lb[(long)row * K + k0 + kk] = us[row * kUS + kk];
     }
-    if (as.method == 1) {   // v_update from the new u (em_gaussian.py:130-136): column sums in query order, as colsum_v_kernel
-      __syncthreads();
-      if (tid < KT && k0 + tid < K) {
-        float sm_ = 0.0f;
-        for (int i = 0; i < n; ++i) sm_ += us[i * kUS + tid];
-        as.v[(long)t * K + k0 + tid] = logf(sm_ / fn + kEps) + 1.0f;
-      }
-    }
-    cluster.sync();   // no CTA may leave while another still reads its exchange slots
   }
 }
 
-// The fused form needs every class tile of a task in one (portable) cluster
-constexpr int kMaxClusterTiles = 8;
-
 template <int MJ, int MN, int KT>
 cudaError_t launch_iter_kt(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
-                           int r, int mode, int want_d2, const AssignArgs* as, cudaStream_t st) {
+                           int r, int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1, kUS = KT + 4, kWS = KT + 2;
-  const size_t smem_plain = sizeof(float) * ((size_t)NQ * ZP + 4 + (size_t)NQ * kUS + (size_t)RQ * kWS + KT);
-  const int tiles = (K + KT - 1) / KT;
+  // samples, u tile, centroids, cluster sizes + row statistics and v of the chained form
+  const size_t smem = sizeof(float) * ((size_t)NQ * ZP + 4 + (size_t)NQ * kUS + (size_t)RQ * kWS + KT + 2 * NQ + KT);
   static PerDeviceFlags attr_set;
   const int slot = current_device_slot();
-  const bool first = slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0;
-  if constexpr (KT == 128) {
-    if (as) {
-      const size_t smem = smem_plain + sizeof(float) * 5 * NQ;   // + the exchange slots
-      auto kern = kproj_iter_kernel<MJ, MN, KT, true>;
-      if (first) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem_plain);
-        if (e != cudaSuccess) return e;
-        if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
-      }
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(tiles, T);
-      cfg.blockDim = dim3(256);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = tiles;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      note_launch();
-      return cudaLaunchKernelEx(&cfg, kern, Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, *as);
-    }
-  }
-  if (as) return cudaErrorInvalidValue;   // the caller checks kmeans_fused_assign() first
-  if (smem_plain > 48 * 1024 && first) {
+  if (smem > 48 * 1024 && (slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0)) {
     cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_plain);
+                                         (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if constexpr (KT == 128) {
-      e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(smem_plain + sizeof(float) * 5 * NQ));
-      if (e != cudaSuccess) return e;
-    }
     if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
   }
-  kproj_iter_kernel<MJ, MN, KT, false><<<dim3(tiles, T), 256, smem_plain, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2,
-                                                                                AssignArgs{});
+  const dim3 grid((K + KT - 1) / KT, T);
+  if (ch) kproj_iter_kernel<MJ, MN, KT, true><<<grid, 256, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, *ch);
+  else kproj_iter_kernel<MJ, MN, KT, false><<<grid, 256, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, ChainArgs{});
   note_launch();
   return cudaGetLastError();
 }
@@ -480,50 +442,49 @@ int km_tile() {
   return tile;
 }
 
-// TCLIP_KM_FUSED=1 finishes the soft-max inside the iteration kernel when the class tiles of a task fit one cluster
-// (K <= 1024).  Off by default — measured SLOWER at the RN50 shape (profiles/r2_kmeans.md, "cluster-fused soft-max"): only
-// 33 clusters of 8 x 107 KB CTAs are resident (264 of the 296 CTA slots), so the 100 tasks of a batch take 4 quantised waves
-// of 56 us (224 us under ncu) where the separate kernels take 143 + 35 us; and per resident cluster the three exchange rounds
-// cost what the whole assign kernel costs (1.70 vs 1.73 us per task-iteration at any batch size).  Same results
-// (tests/test_gpu_kmeans.py::test_cluster_fused_softmax_matches).
-bool kmeans_fused_assign(int K) {
+// Soft k-means and EM-Gaussian run the chained form of the iteration kernel (ChainArgs); TCLIP_KM_CHAIN=0 keeps the separate
+// assignment / column-sum launches per iteration (what hard k-means, whose logged criterion needs every u, always does).
+// (Also tried: the class tiles of a task as one thread-block cluster, row statistics exchanged over distributed shared memory
+// inside the launch — commit 2e92692, TCLIP_KM_FUSED there.  Same results, slower: 33 resident clusters of 8 x 107 KB CTAs,
+// 4 quantised waves per 100 tasks, 224 us per iteration against 143 + 35; profiles/r2_kmeans.md.)
+bool kmeans_chained() {
   static const bool on = [] {
-    const char* e = std::getenv("TCLIP_KM_FUSED");
-    return e && std::atoi(e) == 1;
+    const char* e = std::getenv("TCLIP_KM_CHAIN");
+    return !(e && std::atoi(e) == 0);
   }();
-  return on && km_tile() == 128 && (K + 127) / 128 <= kMaxClusterTiles;
+  return on;
 }
 
 template <int MJ, int MN>
 cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
-                        int r, int mode, int want_d2, const AssignArgs* as, cudaStream_t st) {
-  if (km_tile() == 128) return launch_iter_kt<MJ, MN, 128>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-  return launch_iter_kt<MJ, MN, 64>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+                        int r, int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
+  if (km_tile() == 128) return launch_iter_kt<MJ, MN, 128>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+  return launch_iter_kt<MJ, MN, 64>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
 }
 
 template <int MJ>
 cudaError_t launch_iter_mn(int mn, const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n,
-                           int K, int r, int mode, int want_d2, const AssignArgs* as, cudaStream_t st) {
+                           int K, int r, int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
   switch (mn) {
-    case 1: return launch_iter<MJ, 1>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    case 2: return launch_iter<MJ, 2>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    case 3: return launch_iter<MJ, 3>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    case 4: return launch_iter<MJ, 4>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    case 5: return launch_iter<MJ, 5>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    default: return launch_iter<MJ, 6>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 1: return launch_iter<MJ, 1>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 2: return launch_iter<MJ, 2>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 3: return launch_iter<MJ, 3>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 4: return launch_iter<MJ, 4>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 5: return launch_iter<MJ, 5>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    default: return launch_iter<MJ, 6>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
   }
 }
 
 cudaError_t iterate(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K, int r,
-                    int mode, int want_d2, const AssignArgs* as, cudaStream_t st) {
+                    int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
   const int mj = (r + 15) / 16, mn = (n + 15) / 16;
   switch (mj) {
-    case 1: return launch_iter_mn<1>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    case 2: return launch_iter_mn<2>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    case 3: return launch_iter_mn<3>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    case 4: return launch_iter_mn<4>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    case 5: return launch_iter_mn<5>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
-    default: return launch_iter_mn<6>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, as, st);
+    case 1: return launch_iter_mn<1>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 2: return launch_iter_mn<2>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 3: return launch_iter_mn<3>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 4: return launch_iter_mn<4>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 5: return launch_iter_mn<5>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    default: return launch_iter_mn<6>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
   }
 }
 
@@ -593,6 +554,7 @@ size_t kmeans_run_workspace_bytes(const KMeansRun& p) {
   if (p.method == 1) b += align_up(sizeof(float) * T * K);       // colsum scratch
   if (kmeans_sample_coordinates(p.n, p.D)) {
     const size_t rq = coord_pitch(p.n, p.D);
+    if (p.method != 2) b += 2 * align_up(sizeof(float2) * T * n * ((K + km_tile() - 1) / km_tile()));   // row statistics
     b += align_up(sizeof(float) * T * K * rq);           // wt
     if (D > n) {
       b += align_up(sizeof(double) * T * kGramSplits * n * n);   // G (partial sums)
@@ -631,13 +593,19 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
   float* u_old = p.method == 2 ? static_cast<float*>(take(sizeof(float) * (size_t)T * n * K)) : nullptr;
   float* colsum = p.method == 1 ? static_cast<float*>(take(sizeof(float) * (size_t)T * K)) : nullptr;
   const bool coords = kmeans_sample_coordinates(n, D);
-  const bool fused = coords && kmeans_fused_assign(K);
+  const bool chained = coords && p.method != 2 && kmeans_chained() && p.iters > 0;
   const float* Z = p.x;
   int zs = D, r = D;
   float *wt = nullptr, *w = p.w;
+  float2* stats[2] = {nullptr, nullptr};
   if (coords) {
     const int rq = coord_pitch(n, D);
     wt = static_cast<float*>(take(sizeof(float) * (size_t)T * K * rq));
+    if (p.method != 2) {
+      const size_t sb = sizeof(float2) * (size_t)T * n * ((K + km_tile() - 1) / km_tile());
+      stats[0] = static_cast<float2*>(take(sb));
+      stats[1] = static_cast<float2*>(take(sb));
+    }
     if (D > n) {
       double* G = static_cast<double*>(take(sizeof(double) * (size_t)T * kGramSplits * n * n));
       float* Zc = static_cast<float*>(take(sizeof(float) * (size_t)T * n * rq));
@@ -664,10 +632,11 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
   if (p.iter_events && p.iter_events[0]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[0], st));
   for (int it = 0; it < p.iters; ++it) {
     const int mode = p.method == 2 ? 2 : 1;
-    if (fused) {
-      // M-step, distances, u_update [and v_update] in one launch
-      const AssignArgs as{p.u, p.labels, p.method == 1 ? p.v : nullptr, p.temperature, p.lambd, p.method};
-      KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, &as, st));
+    if (chained) {
+      // M-step of the u the previous launch's logits describe, distances, logits and their row statistics: one launch
+      const ChainArgs ch{it == 0 ? nullptr : stats[(it + 1) & 1], stats[it & 1], d2, p.method == 1 ? p.v : nullptr,
+                         p.temperature, p.lambd, p.method};
+      KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, &ch, st));
     } else {
       if (coords) {
         KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, nullptr, st));
@@ -685,6 +654,11 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
       KM_TRY(cudaMemcpyAsync(u_old, p.u, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
     }
     if (p.iter_events && p.iter_events[it + 1]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[it + 1], st));
+  }
+  if (chained) {
+    // u, labels [and v] of the last iteration, from its logits (mode 3 with scale 1: the plain soft-max of the given values)
+    KM_TRY(kmeans_assign(d2, nullptr, nullptr, 1.0f, 0.0f, p.u, p.labels, T, n, K, 3, st));
+    if (p.method == 1) KM_TRY(colsum_v(p.u, colsum, p.v, nullptr, T, n, K, st));
   }
   // the reference copies u_old after the update: the logged criterion of the soft variants is identically 0
   if (p.method != 2) KM_TRY(cudaMemsetAsync(p.criterions, 0, sizeof(float) * (size_t)std::max(p.iters, 1), st));
