@@ -39,47 +39,79 @@ namespace {
 
 constexpr float kEps = 1e-15f;
 constexpr int kMaxR = 96;     // largest coordinate count (and sample count) of the sample-coordinate form
-constexpr int kMaxPairs = (kMaxR * kMaxR + 255) / 256;
-
-// G[t] = X_t X_t^T in float64 (n <= kMaxR): kGramSplits CTAs per task, each over a contiguous range of the D columns walked
-// in slabs of 32 staged through shared memory; every thread owns <= kMaxPairs entries.  The partial matrices
-// G[t][split] are added in split order by chol_kernel (a fixed order: the factor is reproducible bit for bit).
+// G[t] = X_t X_t^T in float64 (n <= kMaxR), lower triangle: kGramSplits CTAs per task, each over a contiguous range of the D
+// columns walked in slabs of 32.  A slab is staged as float64, column-major (sample index contiguous), and a thread owns a
+// 4 x 4 block of sample pairs on or below the diagonal: per column 4 128-bit shared loads feed 16 DFMA, and the threads of a
+// warp (consecutive blocks of one block row) read consecutive 32-byte pieces.  Every entry is the same d-ascending fma chain
+// per split as a one-entry-per-thread loop would give; the partial matrices G[t][split] are added in split order by
+// chol_kernel (a fixed order: the factor is reproducible bit for bit).
 constexpr int kGramSplits = 4;
+constexpr int kGramPitch = kMaxR + 2;                                       // doubles per staged column (even: 16-byte loads)
+constexpr int kGramBlocks = (kMaxR / 4) * (kMaxR / 4 + 1) / 2;              // 4 x 4 blocks of the lower triangle at n = kMaxR
+constexpr int kGramPerThread = (kGramBlocks + 255) / 256;
 
 __global__ void __launch_bounds__(256)
 gram_kernel(const float* __restrict__ x, double* __restrict__ G, int n, int D) {
-  __shared__ float xs[kMaxR][33];
+  __shared__ __align__(16) double xs[32][kGramPitch];
   const int t = blockIdx.x, split = blockIdx.y;
   const float* xb = x + (long)t * n * D;
-  double acc[kMaxPairs];
+  const int nb = (n + 3) / 4, n_blocks = nb * (nb + 1) / 2;
+  int bi[kGramPerThread], bj[kGramPerThread];
+  double acc[kGramPerThread][4][4];
 #pragma unroll
-  for (int q = 0; q < kMaxPairs; ++q) acc[q] = 0.0;
-  const int pairs = n * n;
+  for (int q = 0; q < kGramPerThread; ++q) {
+    const int blk = threadIdx.x + 256 * q;
+    // block row of triangular index blk: the largest i with i (i + 1) / 2 <= blk
+    int i = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= blk) ++i;
+    while (i * (i + 1) / 2 > blk) --i;
+    bi[q] = i;
+    bj[q] = blk - i * (i + 1) / 2;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[q][a][b] = 0.0;
+  }
   const int slabs = (D + 31) / 32, per = (slabs + kGramSplits - 1) / kGramSplits;
   const int d_lo = split * per * 32, d_hi = min(D, (split + 1) * per * 32);
+  const int n4 = 4 * nb;   // rows n .. n4 - 1 are zero
   for (int d0 = d_lo; d0 < d_hi; d0 += 32) {
-    for (int i = threadIdx.x; i < n * 32; i += 256) {
+    for (int i = threadIdx.x; i < n4 * 32; i += 256) {
       const int r = i >> 5, c = i & 31;
-      xs[r][c] = (d0 + c < D) ? xb[(long)r * D + d0 + c] : 0.0f;
+      xs[c][r] = (r < n && d0 + c < D) ? (double)xb[(long)r * D + d0 + c] : 0.0;
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < kMaxPairs; ++q) {
-      const int p = threadIdx.x + 256 * q;
-      if (p < pairs) {
-        const int i = p / n, j = p - i * n;
-        double s = acc[q];
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c) s = fma((double)xs[i][c], (double)xs[j][c], s);
-        acc[q] = s;
+    for (int q = 0; q < kGramPerThread; ++q) {
+      if (threadIdx.x + 256 * q < n_blocks) {
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c) {
+          const double2 a01 = *reinterpret_cast<const double2*>(&xs[c][4 * bi[q]]);
+          const double2 a23 = *reinterpret_cast<const double2*>(&xs[c][4 * bi[q] + 2]);
+          const double2 b01 = *reinterpret_cast<const double2*>(&xs[c][4 * bj[q]]);
+          const double2 b23 = *reinterpret_cast<const double2*>(&xs[c][4 * bj[q] + 2]);
+          const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[q][a][b] = fma(av[a], bv[b], acc[q][a][b]);
+        }
       }
     }
     __syncthreads();
   }
+  double* gb = G + ((long)t * kGramSplits + split) * n * n;
 #pragma unroll
-  for (int q = 0; q < kMaxPairs; ++q) {
-    const int p = threadIdx.x + 256 * q;
-    if (p < pairs) G[((long)t * kGramSplits + split) * pairs + p] = acc[q];
+  for (int q = 0; q < kGramPerThread; ++q) {
+    if (threadIdx.x + 256 * q < n_blocks) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = 4 * bi[q] + a, j = 4 * bj[q] + b;
+          if (i < n && j <= i) gb[i * n + j] = acc[q][a][b];
+        }
+    }
   }
 }
 
@@ -94,13 +126,15 @@ chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) 
   __shared__ double diag[kMaxR];
   const int t = blockIdx.x;
   const double* gb = G + (long)t * kGramSplits * n * n;
-  for (int i = threadIdx.x; i < n * n; i += 256) {
-    double s = gb[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < n; i += 8)   // the lower triangle is all the factorisation reads (and all gram_kernel writes)
+    for (int k = lane; k <= i; k += 32) {
+      double s = gb[i * n + k];
 #pragma unroll
-    for (int sp = 1; sp < kGramSplits; ++sp) s += gb[(long)sp * n * n + i];
-    A[i] = s;
-    if (i / n == i % n) diag[i / n] = s;
-  }
+      for (int sp = 1; sp < kGramSplits; ++sp) s += gb[(long)sp * n * n + i * n + k];
+      A[i * n + k] = s;
+      if (k == i) diag[i] = s;
+    }
   __syncthreads();
   for (int j = 0; j < n; ++j) {
     if (threadIdx.x == 0) {
@@ -111,11 +145,10 @@ chol_kernel(const double* __restrict__ G, float* __restrict__ Z, int n, int zs) 
     const double d = piv;
     for (int i = j + threadIdx.x; i < n; i += 256) A[i * n + j] = (d > 0.0) ? (i == j ? d : A[i * n + j] / d) : 0.0;
     __syncthreads();
-    if (d > 0.0) {
-      const int m = n - j - 1;
-      for (int p = threadIdx.x; p < m * m; p += 256) {
-        const int i = j + 1 + p / m, k = j + 1 + p % m;
-        A[i * n + k] -= A[i * n + j] * A[k * n + j];
+    if (d > 0.0) {   // trailing update, lower triangle: one warp per row
+      for (int i = j + 1 + warp; i < n; i += 8) {
+        const double lij = A[i * n + j];
+        for (int k = j + 1 + lane; k <= i; k += 32) A[i * n + k] -= lij * A[k * n + j];
       }
     }
     __syncthreads();
@@ -170,13 +203,13 @@ struct ChainArgs {
   int method;               // 0 soft k-means, 1 EM-Gaussian
 };
 
-template <int MJ, int MN, int KT, bool CHAIN>
-__global__ void __launch_bounds__(256)
+template <int MJ, int MN, int KT, bool CHAIN, int NT>
+__global__ void __launch_bounds__(NT)
 kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__ u, float* __restrict__ coef,
                   float* __restrict__ wt, float* __restrict__ d2, int n, int K, int r, int mode, int want_d2,
                   const ChainArgs ch) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1;
-  constexpr int kUS = KT + 4, kWS = KT + 2, CPT = KT / 16, PQ = CPT / 2;   // classes / class pairs per thread
+  constexpr int kUS = KT + 4, kWS = KT + 2, CPT = KT / (NT / 16), PQ = CPT / 2;   // classes / class pairs per thread
   extern __shared__ __align__(16) float sm[];
   float* Zs = sm;                    // [NQ][ZP]   samples (rows >= n and columns >= r are zero)
   float* us = Zs + ((NQ * ZP + 3) & ~3);   // [NQ][kUS]  u tile, later the d2 tile (16-byte aligned for the float4 reads)
@@ -195,30 +228,30 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   // ~10 dependent DRAM round trips and 32 % of the kernel's warp time (profiles/r2_kmeans.md).
   // Samples.  The Cholesky buffer has whole zero-padded rows of RQ floats: 128-bit loads, all issued before anything waits
   // (the odd row pitch of the tile, which keeps the distance loop free of bank conflicts, rules out 16-byte async copies)
-  constexpr int ZV = RQ / 4, ZPER = (NQ * ZV + 255) / 256;
+  constexpr int ZV = RQ / 4, ZPER = (NQ * ZV + NT - 1) / NT;
   const bool z_rows = zs == RQ && (reinterpret_cast<uintptr_t>(zb) & 15) == 0;
   float4 zr[ZPER];
   if (z_rows) {
 #pragma unroll
     for (int q = 0; q < ZPER; ++q) {
-      const int i = tid + 256 * q;
+      const int i = tid + NT * q;
       zr[q] = (i < n * ZV) ? __ldg(reinterpret_cast<const float4*>(zb) + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
   } else {
-    for (int i = tid; i < NQ * RQ; i += 256) {
+    for (int i = tid; i < NQ * RQ; i += NT) {
       const int row = i / RQ, c = i - row * RQ;
       if (row < n && c < r) cp_async_4(Zs + row * ZP + c, zb + (long)row * zs + c);
       else Zs[row * ZP + c] = 0.0f;
     }
   }
   if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(ub) & 15) == 0) {   // 16-byte requests: rows and tiles start on 16 bytes
-    for (int i = tid; i < NQ * (KT / 4); i += 256) {
+    for (int i = tid; i < NQ * (KT / 4); i += NT) {
       const int row = i / (KT / 4), c = 4 * (i - row * (KT / 4));
       if (row < n && k0 + c < K) cp_async_16(us + row * kUS + c, ub + (long)row * K + k0 + c);
       else *reinterpret_cast<float4*>(us + row * kUS + c) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
   } else {
-    for (int i = tid; i < NQ * KT; i += 256) {
+    for (int i = tid; i < NQ * KT; i += NT) {
       const int row = i / KT, c = i - row * KT;
       if (row < n && k0 + c < K) cp_async_4(us + row * kUS + c, ub + (long)row * K + k0 + c);
       else us[row * kUS + c] = 0.0f;
@@ -227,7 +260,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   if (z_rows) {
 #pragma unroll
     for (int q = 0; q < ZPER; ++q) {
-      const int i = tid + 256 * q;
+      const int i = tid + NT * q;
       if (i < NQ * ZV) {
         const int row = i / ZV, c = 4 * (i - row * ZV);
         float* dst = Zs + row * ZP + c;
@@ -254,7 +287,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   __syncthreads();
   if constexpr (CHAIN) {
     if (from_logits) {   // u tile = softmax row restricted to this tile (u_update); the padding stays zero
-      for (int row = tid >> 5; row < n; row += 8) {   // one warp per query
+      for (int row = tid >> 5; row < n; row += NT / 32) {   // one warp per query
         const float M = row_m[row], rS = 1.0f / row_s[row];
 #pragma unroll
         for (int j = 0; j < KT / 32; ++j) {
@@ -334,7 +367,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
     if (k < K && (formed || mode == 2)) {
       const float inv = formed ? 1.0f / fmaxf(c, kEps) : 0.0f;
       float* cb = coef + (long)t * n * K + k;
-      for (int row = tid / KT; row < n; row += 256 / KT) cb[(long)row * K] = us[row * kUS + kk] * inv;
+      for (int row = tid / KT; row < n; row += NT / KT) cb[(long)row * K] = us[row * kUS + kk] * inv;
     }
   }
   if (!want_d2) return;
@@ -368,7 +401,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   __syncthreads();
   if constexpr (!CHAIN) {
     float* db = d2 + (long)t * n * K;
-    for (int i = tid; i < n * KT; i += 256) {
+    for (int i = tid; i < n * KT; i += NT) {
       const int row = i / KT, kk = i - row * KT;
       if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[row * kUS + kk];
     }
@@ -377,7 +410,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
     constexpr int LPT = KT / 32;
     const int lane = tid & 31, warp = tid >> 5;
     const bool gauss = ch.method == 1;
-    for (int row = warp; row < n; row += 8) {
+    for (int row = warp; row < n; row += NT / 32) {
       float l[LPT];
       float mx = -CUDART_INF_F;
 #pragma unroll
@@ -402,14 +435,14 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
     }
     __syncthreads();
     float* lb = ch.lg + (long)t * n * K;
-    for (int i = tid; i < n * KT; i += 256) {
+    for (int i = tid; i < n * KT; i += NT) {
       const int row = i / KT, kk = i - row * KT;
       if (k0 + kk < K) lb[(long)row * K + k0 + kk] = us[row * kUS + kk];
     }
   }
 }
 
-template <int MJ, int MN, int KT>
+template <int MJ, int MN, int KT, int NT>
 cudaError_t launch_iter_kt(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
                            int r, int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1, kUS = KT + 4, kWS = KT + 2;
@@ -418,16 +451,16 @@ cudaError_t launch_iter_kt(const float* Z, int zs, const float* u, float* coef, 
   static PerDeviceFlags attr_set;
   const int slot = current_device_slot();
   if (smem > 48 * 1024 && (slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0)) {
-    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
   }
   const dim3 grid((K + KT - 1) / KT, T);
-  if (ch) kproj_iter_kernel<MJ, MN, KT, true><<<grid, 256, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, *ch);
-  else kproj_iter_kernel<MJ, MN, KT, false><<<grid, 256, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, ChainArgs{});
+  if (ch) kproj_iter_kernel<MJ, MN, KT, true, NT><<<grid, NT, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, *ch);
+  else kproj_iter_kernel<MJ, MN, KT, false, NT><<<grid, NT, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, ChainArgs{});
   note_launch();
   return cudaGetLastError();
 }
@@ -458,8 +491,11 @@ bool kmeans_chained() {
 template <int MJ, int MN>
 cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
                         int r, int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
-  if (km_tile() == 128) return launch_iter_kt<MJ, MN, 128>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-  return launch_iter_kt<MJ, MN, 64>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+  // (NT = 512, i.e. 32 instead of 16 resident warps per SM with half the register tile each, measures the same: loop 2.563 vs
+  // 2.567 ms per batch — like the 64-class tile, and like scalar instead of packed multiply-adds: the kernel is bound by the
+  // rate at which the FMA pipe takes three-register-operand instructions, not by latency; profiles/r2_kmeans.md)
+  if (km_tile() == 128) return launch_iter_kt<MJ, MN, 128, 256>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+  return launch_iter_kt<MJ, MN, 64, 256>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
 }
 
 template <int MJ>
