@@ -113,10 +113,41 @@ def test_config4_shape_vs_oracle(dev, method):
     _check(m, logs, r.u.numpy(), r.w.numpy(), r.preds.numpy(), r.acc, r.criterions, r.v.numpy() if r.v is not None else None)
 
 
+def _loop_f64(x, u, method, iters, temperature, lambd):
+    """The reference loop (soft_kmeans.py:135-166,199-220, hard_kmeans.py:138-151,186-211, em_gaussian.py:106-136,199-229) in
+    float64, feature space, plain torch."""
+    from tclip_b200 import ops
+    eps = 1e-15
+    x, u = x.double(), u.double()
+    n, K = x.shape[1], u.shape[2]
+    v = torch.zeros(u.shape[0], K, dtype=torch.float64, device=x.device)
+    w = None
+    if method != ops.KMEANS_HARD:
+        w = torch.einsum("tnk,tnd->tkd", u, x) / u.sum(1).clamp_min(eps).unsqueeze(-1)
+    for _ in range(iters):
+        cs = u.sum(1)
+        wn = torch.einsum("tnk,tnd->tkd", u, x) / cs.clamp_min(eps).unsqueeze(-1)
+        w = torch.where((cs > eps).unsqueeze(-1), wn, torch.zeros_like(wn) if method == ops.KMEANS_HARD else w)
+        d2 = ((x.unsqueeze(2) - w.unsqueeze(1)) ** 2).sum(-1)
+        if method == ops.KMEANS_HARD:
+            u = torch.nn.functional.one_hot(torch.softmax(d2, -1).argmin(-1), K).double()
+            continue
+        logits = temperature * (-0.5 * d2)
+        if method == ops.KMEANS_GAUSS:
+            logits = logits + (lambd * v).unsqueeze(1) / n
+        u = torch.softmax(logits, -1)
+        if method == ops.KMEANS_GAUSS:
+            v = torch.log(u.sum(1) / n + eps) + 1
+    return u
+
+
 def test_sample_coordinates_equal_feature_space(dev):
-    """The loop in the coordinates of the task's samples (Cholesky factor of the Gram matrix) against the same loop run by
-    the feature-space kernels (tclip_kmeans_centroids / tclip_kmeans_assign), incl. a task with duplicated samples (singular
-    Gram matrix) and n > D."""
+    """The loop in the coordinates of the task's samples (Cholesky factor of the Gram matrix, triangular form of the iteration
+    kernel) against the same loop run by the feature-space kernels (tclip_kmeans_centroids / tclip_kmeans_assign) and against
+    a float64 evaluation, incl. a task with duplicated samples (singular Gram matrix) and n > D.
+    Tolerance: each float32 path within 2e-4 of float64 in u after 5 iterations at temperature 30 (measured, scripts/
+    gpu_km_coords_err.py: sample coordinates 7e-5, feature space 1.5e-4 on the worst case, EM-Gaussian K = 60), the two
+    float32 paths within 4e-4 of each other."""
     from tclip_b200 import ops, tasks
     for (K, D, n, seed) in ((60, 256, 75, 5), (40, 90, 33, 6), (30, 24, 75, 7), (30, 40, 120, 8), (20, 200, 96, 9)):   # n = 120: fallback
         td, _ = tasks.make_zero_shot_batch(3, K, n_query=n, seed=seed, softmax_feature=False, embed_dim=D)
@@ -126,22 +157,24 @@ def test_sample_coordinates_equal_feature_space(dev):
         g = torch.Generator().manual_seed(seed)
         u0 = torch.softmax(4.0 * torch.randn(3, n, K, generator=g), dim=-1).to(dev)
         for method, temperature in ((ops.KMEANS_SOFT, 30.0), (ops.KMEANS_GAUSS, 30.0), (ops.KMEANS_HARD, 30.0)):
-            res = ops.kmeans_run(x, u0.clone(), method, 5, temperature, lambd=float(int(K / 5) * n), want_w=True)
+            lam = float(int(K / 5) * n)
+            res = ops.kmeans_run(x, u0.clone(), method, 5, temperature, lambd=lam, want_w=True)
             # feature-space loop with the stage entry points
             u, v = u0.clone(), torch.zeros(3, K, device=dev)
             w = None if method == ops.KMEANS_HARD else ops.kmeans_centroids(u, x, None)
             for _ in range(5):
                 w = ops.kmeans_centroids(u, x, w, keep_old=(method != ops.KMEANS_HARD))
-                u, labels = ops.kmeans_assign(x, w, method, temperature, v=v, lambd=float(int(K / 5) * n))
+                u, labels = ops.kmeans_assign(x, w, method, temperature, v=v, lambd=lam)
                 if method == ops.KMEANS_GAUSS:
                     _, v, _ = ops.colsum_v(u, want_v=True, want_live=False)
+            u64 = _loop_f64(x, u0, method, 5, temperature, lam).cpu().numpy()
             assert (res["labels"] == labels).float().mean().item() >= 0.999
-            np.testing.assert_allclose(res["u"].cpu().numpy(), u.cpu().numpy(), atol=2e-4)
+            np.testing.assert_allclose(res["u"].cpu().numpy(), u64, atol=2e-4)
+            np.testing.assert_allclose(u.cpu().numpy(), u64, atol=2e-4)
+            np.testing.assert_allclose(res["u"].cpu().numpy(), u.cpu().numpy(), atol=4e-4)
             np.testing.assert_allclose(res["w"].cpu().numpy(), w.cpu().numpy(), rtol=1e-3, atol=2e-5)
             if res["coef"] is not None:
                 np.testing.assert_allclose(ops.kmeans_expand_centroids(res["coef"], x).cpu().numpy(), res["w"].cpu().numpy(), atol=1e-6)
-            else:
-                assert n > 96    # the feature-space fallback of the driver
 
 
 def test_kmeans_rn50_shape_properties(dev):

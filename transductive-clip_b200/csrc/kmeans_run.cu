@@ -203,7 +203,11 @@ struct ChainArgs {
   int method;               // 0 soft k-means, 1 EM-Gaussian
 };
 
-template <int MJ, int MN, int KT, bool CHAIN, int NT>
+// TRI: Z is a Cholesky factor (lower triangular: sample n has no coordinate beyond n; MJ == MN).  In blocks of 16 the
+// centroid sums then skip the samples below a coordinate block (they would add u * 0: bit-identical), and the distance of a
+// sample group takes the coordinate blocks beyond it as the running sum of squares of the centroid alone, (0 - w)^2 = w^2:
+// the same terms in another order.  57 % / 63 % of the multiply-adds of the two phases remain at n = 75.
+template <int MJ, int MN, int KT, bool CHAIN, int NT, bool TRI>
 __global__ void __launch_bounds__(NT)
 kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__ u, float* __restrict__ coef,
                   float* __restrict__ wt, float* __restrict__ d2, int n, int K, int r, int mode, int want_d2,
@@ -317,20 +321,25 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
     for (int q = 0; q < PQ; ++q)
 #pragma unroll
       for (int m = 0; m < MJ; ++m) acc[q][m] = make_float2(0.0f, 0.0f);
-    for (int nn = 0; nn < n; ++nn) {
-      float2 uv[PQ];
 #pragma unroll
-      for (int q = 0; q < PQ; q += 2) {
-        const float4 u4 = *reinterpret_cast<const float4*>(us + nn * kUS + ty * CPT + 2 * q);
-        uv[q] = make_float2(u4.x, u4.y);
-        uv[q + 1] = make_float2(u4.z, u4.w);
-      }
+    for (int nb = 0; nb < (TRI ? MN : 1); ++nb) {   // TRI: sample block nb reaches the coordinate blocks m <= nb only
+      const int n_lo = TRI ? 16 * nb : 0, n_hi = TRI ? min(n, 16 * nb + 16) : n;
+      for (int nn = n_lo; nn < n_hi; ++nn) {
+        float2 uv[PQ];
 #pragma unroll
-      for (int m = 0; m < MJ; ++m) {
-        const float z = Zs[nn * ZP + tx + 16 * m];
-        const float2 zz = make_float2(z, z);
+        for (int q = 0; q < PQ; q += 2) {
+          const float4 u4 = *reinterpret_cast<const float4*>(us + nn * kUS + ty * CPT + 2 * q);
+          uv[q] = make_float2(u4.x, u4.y);
+          uv[q + 1] = make_float2(u4.z, u4.w);
+        }
 #pragma unroll
-        for (int q = 0; q < PQ; ++q) acc[q][m] = __ffma2_rn(uv[q], zz, acc[q][m]);
+        for (int m = 0; m < MJ; ++m) {
+          if (TRI && m > nb) continue;
+          const float z = Zs[nn * ZP + tx + 16 * m];
+          const float2 zz = make_float2(z, z);
+#pragma unroll
+          for (int q = 0; q < PQ; ++q) acc[q][m] = __ffma2_rn(uv[q], zz, acc[q][m]);
+        }
       }
     }
 #pragma unroll
@@ -378,18 +387,50 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   for (int q = 0; q < PQ; ++q)
 #pragma unroll
     for (int m = 0; m < MN; ++m) acc[q][m] = make_float2(0.0f, 0.0f);
-  for (int j = 0; j < r; ++j) {
-    float2 nw[PQ];
+  if constexpr (!TRI) {
+    for (int j = 0; j < r; ++j) {
+      float2 nw[PQ];
 #pragma unroll
-    for (int q = 0; q < PQ; ++q) nw[q] = *reinterpret_cast<const float2*>(nwT + j * kWS + ty * CPT + 2 * q);
+      for (int q = 0; q < PQ; ++q) nw[q] = *reinterpret_cast<const float2*>(nwT + j * kWS + ty * CPT + 2 * q);
 #pragma unroll
-    for (int m = 0; m < MN; ++m) {
-      const float z = Zs[(tx + 16 * m) * ZP + j];
-      const float2 zz = make_float2(z, z);
+      for (int m = 0; m < MN; ++m) {
+        const float z = Zs[(tx + 16 * m) * ZP + j];
+        const float2 zz = make_float2(z, z);
 #pragma unroll
-      for (int q = 0; q < PQ; ++q) {
-        const float2 df = __fadd2_rn(zz, nw[q]);
-        acc[q][m] = __ffma2_rn(df, df, acc[q][m]);
+        for (int q = 0; q < PQ; ++q) {
+          const float2 df = __fadd2_rn(zz, nw[q]);
+          acc[q][m] = __ffma2_rn(df, df, acc[q][m]);
+        }
+      }
+    }
+  } else {
+    // coordinate blocks from the last to the first; sq = sum of w^2 over the blocks already walked, which is all that the
+    // sample group entering at this block (m == jb: its samples are zero beyond coordinate 16 jb + 15) has of them
+    float2 sq[PQ];
+#pragma unroll
+    for (int q = 0; q < PQ; ++q) sq[q] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int jb = MJ - 1; jb >= 0; --jb) {
+#pragma unroll
+      for (int q = 0; q < PQ; ++q) acc[q][jb] = sq[q];
+      const int j_hi = min(r, 16 * jb + 16);
+      for (int j = 16 * jb; j < j_hi; ++j) {
+        float2 nw[PQ];
+#pragma unroll
+        for (int q = 0; q < PQ; ++q) nw[q] = *reinterpret_cast<const float2*>(nwT + j * kWS + ty * CPT + 2 * q);
+#pragma unroll
+        for (int m = 0; m < MN; ++m) {
+          if (m < jb) continue;
+          const float z = Zs[(tx + 16 * m) * ZP + j];
+          const float2 zz = make_float2(z, z);
+#pragma unroll
+          for (int q = 0; q < PQ; ++q) {
+            const float2 df = __fadd2_rn(zz, nw[q]);
+            acc[q][m] = __ffma2_rn(df, df, acc[q][m]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < PQ; ++q) sq[q] = __ffma2_rn(nw[q], nw[q], sq[q]);
       }
     }
   }
@@ -442,7 +483,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   }
 }
 
-template <int MJ, int MN, int KT, int NT>
+template <int MJ, int MN, int KT, int NT, bool TRI>
 cudaError_t launch_iter_kt(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
                            int r, int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
   constexpr int RQ = 16 * MJ, NQ = 16 * MN, ZP = RQ + 1, kUS = KT + 4, kWS = KT + 2;
@@ -451,16 +492,16 @@ cudaError_t launch_iter_kt(const float* Z, int zs, const float* u, float* coef, 
   static PerDeviceFlags attr_set;
   const int slot = current_device_slot();
   if (smem > 48 * 1024 && (slot < 0 || attr_set.v[slot].load(std::memory_order_acquire) == 0)) {
-    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, false, NT, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(kproj_iter_kernel<MJ, MN, KT, true, NT, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (slot >= 0) attr_set.v[slot].store(1, std::memory_order_release);
   }
   const dim3 grid((K + KT - 1) / KT, T);
-  if (ch) kproj_iter_kernel<MJ, MN, KT, true, NT><<<grid, NT, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, *ch);
-  else kproj_iter_kernel<MJ, MN, KT, false, NT><<<grid, NT, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, ChainArgs{});
+  if (ch) kproj_iter_kernel<MJ, MN, KT, true, NT, TRI><<<grid, NT, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, *ch);
+  else kproj_iter_kernel<MJ, MN, KT, false, NT, TRI><<<grid, NT, smem, st>>>(Z, zs, u, coef, wt, d2, n, K, r, mode, want_d2, ChainArgs{});
   note_launch();
   return cudaGetLastError();
 }
@@ -480,6 +521,15 @@ int km_tile() {
 // (Also tried: the class tiles of a task as one thread-block cluster, row statistics exchanged over distributed shared memory
 // inside the launch — commit 2e92692, TCLIP_KM_FUSED there.  Same results, slower: 33 resident clusters of 8 x 107 KB CTAs,
 // 4 quantised waves per 100 tasks, 224 us per iteration against 143 + 35; profiles/r2_kmeans.md.)
+// TCLIP_KM_TRI=0: the iteration kernel treats the Cholesky factor as a dense matrix (measurement / cross-check)
+bool kmeans_triangular() {
+  static const bool on = [] {
+    const char* e = std::getenv("TCLIP_KM_TRI");
+    return !(e && std::atoi(e) == 0);
+  }();
+  return on;
+}
+
 bool kmeans_chained() {
   static const bool on = [] {
     const char* e = std::getenv("TCLIP_KM_CHAIN");
@@ -488,39 +538,51 @@ bool kmeans_chained() {
   return on;
 }
 
-template <int MJ, int MN>
+template <int MJ, int MN, bool TRI>
 cudaError_t launch_iter(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K,
                         int r, int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
   // (NT = 512, i.e. 32 instead of 16 resident warps per SM with half the register tile each, measures the same: loop 2.563 vs
   // 2.567 ms per batch — like the 64-class tile, and like scalar instead of packed multiply-adds: the kernel is bound by the
   // rate at which the FMA pipe takes three-register-operand instructions, not by latency; profiles/r2_kmeans.md)
-  if (km_tile() == 128) return launch_iter_kt<MJ, MN, 128, 256>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-  return launch_iter_kt<MJ, MN, 64, 256>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+  if (km_tile() == 128) return launch_iter_kt<MJ, MN, 128, 256, TRI>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+  return launch_iter_kt<MJ, MN, 64, 256, TRI>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
 }
 
-template <int MJ>
-cudaError_t launch_iter_mn(int mn, const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n,
+// r <= n always (r = min(n, D)): coordinate blocks MJ <= sample blocks MN
+template <int MN>
+cudaError_t launch_iter_mj(int mj, const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n,
                            int K, int r, int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
-  switch (mn) {
-    case 1: return launch_iter<MJ, 1>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    case 2: return launch_iter<MJ, 2>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    case 3: return launch_iter<MJ, 3>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    case 4: return launch_iter<MJ, 4>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    case 5: return launch_iter<MJ, 5>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    default: return launch_iter<MJ, 6>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-  }
+#define TCLIP_KM_CASE(J) \
+  if constexpr (J <= MN)  \
+    if (mj == J) return launch_iter<J, MN, false>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+  TCLIP_KM_CASE(1) TCLIP_KM_CASE(2) TCLIP_KM_CASE(3) TCLIP_KM_CASE(4) TCLIP_KM_CASE(5) TCLIP_KM_CASE(6)
+#undef TCLIP_KM_CASE
+  return cudaErrorInvalidValue;
 }
 
+// tri: Z is the Cholesky buffer (lower triangular rows of zs = 16 ceil(n / 16) floats, r == n)
 cudaError_t iterate(const float* Z, int zs, const float* u, float* coef, float* wt, float* d2, int T, int n, int K, int r,
-                    int mode, int want_d2, const ChainArgs* ch, cudaStream_t st) {
+                    int mode, int want_d2, const ChainArgs* ch, bool tri, cudaStream_t st) {
   const int mj = (r + 15) / 16, mn = (n + 15) / 16;
-  switch (mj) {
-    case 1: return launch_iter_mn<1>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    case 2: return launch_iter_mn<2>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    case 3: return launch_iter_mn<3>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    case 4: return launch_iter_mn<4>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    case 5: return launch_iter_mn<5>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
-    default: return launch_iter_mn<6>(mn, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+  if (mn < 1 || mn > 6 || mj > mn) return cudaErrorInvalidValue;
+  if (tri) {
+    if (mj != mn) return cudaErrorInvalidValue;
+    switch (mn) {
+      case 1: return launch_iter<1, 1, true>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+      case 2: return launch_iter<2, 2, true>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+      case 3: return launch_iter<3, 3, true>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+      case 4: return launch_iter<4, 4, true>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+      case 5: return launch_iter<5, 5, true>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+      default: return launch_iter<6, 6, true>(Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    }
+  }
+  switch (mn) {
+    case 1: return launch_iter_mj<1>(mj, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 2: return launch_iter_mj<2>(mj, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 3: return launch_iter_mj<3>(mj, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 4: return launch_iter_mj<4>(mj, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    case 5: return launch_iter_mj<5>(mj, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
+    default: return launch_iter_mj<6>(mj, Z, zs, u, coef, wt, d2, T, n, K, r, mode, want_d2, ch, st);
   }
 }
 
@@ -634,6 +696,7 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
   int zs = D, r = D;
   float *wt = nullptr, *w = p.w;
   float2* stats[2] = {nullptr, nullptr};
+  bool tri = false;   // Z is a Cholesky factor
   if (coords) {
     const int rq = coord_pitch(n, D);
     wt = static_cast<float*>(take(sizeof(float) * (size_t)T * K * rq));
@@ -653,6 +716,7 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
       Z = Zc;
       zs = rq;
       r = n;
+      tri = kmeans_triangular();
     }
   } else if (!w) {
     w = static_cast<float*>(take(sizeof(float) * (size_t)T * K * D));
@@ -660,7 +724,7 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
   if (p.method == 1) KM_TRY(cudaMemsetAsync(p.v, 0, sizeof(float) * (size_t)T * K, st));
   // w_init (soft k-means, EM-Gaussian); hard k-means has none (hard_kmeans.py:186)
   if (p.method != 2) {
-    if (coords) KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, 0, 0, nullptr, st));
+    if (coords) KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, 0, 0, nullptr, tri, st));
     else KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, 0, st));
   } else {
     KM_TRY(cudaMemcpyAsync(u_old, p.u, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
@@ -672,10 +736,10 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
       // M-step of the u the previous launch's logits describe, distances, logits and their row statistics: one launch
       const ChainArgs ch{it == 0 ? nullptr : stats[(it + 1) & 1], stats[it & 1], d2, p.method == 1 ? p.v : nullptr,
                          p.temperature, p.lambd, p.method};
-      KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, &ch, st));
+      KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, &ch, tri, st));
     } else {
       if (coords) {
-        KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, nullptr, st));
+        KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, mode, 1, nullptr, tri, st));
       } else {
         KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, mode == 2 ? 0 : 1, st));
         KM_TRY(kmeans_sqdist(p.x, w, d2, T, n, K, D, st));
