@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <math_constants.h>
 
+#include <cstdint>
 #include <cstdlib>
 #include <string>
 
@@ -814,23 +815,49 @@ __global__ void cluster_order_kernel(const int* __restrict__ labels, int* __rest
 }
 
 // proto[t,c,:] = mean of the raw features of the queries in cluster c (index order), c < n_clusters[t]; rest zero.
-__global__ void prototypes_kernel(const float* __restrict__ feats, const int* __restrict__ sample_cluster,
-                                  const int* __restrict__ cluster_size, const int* __restrict__ n_clusters,
-                                  float* __restrict__ proto, int n, int D) {
+// One CTA per (cluster, task): the cluster indices of the task's queries are staged once, a thread owns four feature
+// dimensions and walks the queries (a CTA-uniform branch skips the non-members).  Sums in query order per dimension.
+__global__ void __launch_bounds__(256)
+prototypes_kernel(const float* __restrict__ feats, const int* __restrict__ sample_cluster,
+                  const int* __restrict__ cluster_size, const int* __restrict__ n_clusters, float* __restrict__ proto, int n,
+                  int D) {
+  extern __shared__ int sc_s[];   // [n]
   const int t = blockIdx.y, c = blockIdx.x;
   float* out = proto + ((long)t * n + c) * D;
+  const float* x = feats + (long)t * n * D;
+  const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(proto) & 15) == 0;
   if (c >= n_clusters[t]) {
-    for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = 0.0f;
+    if (vec)
+      for (int d = threadIdx.x; d < D / 4; d += blockDim.x) reinterpret_cast<float4*>(out)[d] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    else
+      for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = 0.0f;
     return;
   }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sc_s[i] = sample_cluster[(long)t * n + i];
+  __syncthreads();
   const float inv = fmaxf((float)cluster_size[(long)t * n + c], kEps);
-  const int* sc = sample_cluster + (long)t * n;
-  const float* x = feats + (long)t * n * D;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float acc = 0.0f;
-    for (int i = 0; i < n; ++i)
-      if (sc[i] == c) acc += x[(long)i * D + d];
-    out[d] = acc / inv;
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const int D4 = D / 4;
+    for (int d = threadIdx.x; d < D4; d += blockDim.x) {
+      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      for (int i = 0; i < n; ++i) {
+        if (sc_s[i] != c) continue;
+        const float4 v = __ldg(x4 + (long)i * D4 + d);
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(out)[d] = make_float4(acc.x / inv, acc.y / inv, acc.z / inv, acc.w / inv);
+    }
+  } else {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float acc = 0.0f;
+      for (int i = 0; i < n; ++i)
+        if (sc_s[i] == c) acc += x[(long)i * D + d];
+      out[d] = acc / inv;
+    }
   }
 }
 
@@ -962,7 +989,7 @@ cudaError_t cluster_prototypes(const int* labels, const float* feats, int* clust
   if (n > 1024) return cudaErrorInvalidValue;
   cluster_order_kernel<<<T, 128, 3 * n * sizeof(int), st>>>(labels, cluster_label, cluster_size, sample_cluster,
                                                             n_clusters, n);
-  prototypes_kernel<<<dim3(n, T), 256, 0, st>>>(feats, sample_cluster, cluster_size, n_clusters, proto, n, D);
+  prototypes_kernel<<<dim3(n, T), 256, n * sizeof(int), st>>>(feats, sample_cluster, cluster_size, n_clusters, proto, n, D);
   note_launch(2);
   return cudaGetLastError();
 }
