@@ -676,7 +676,7 @@ def bench_kmeans(a):
     h.close()
 
 
-KM_TRAFFIC = {(1000, 100, 1024): 72.65e6}   # (K, T, D) -> dram__bytes_read.sum + dram__bytes_write.sum of one kproj_iter_kernel
+KM_TRAFFIC = {(1000, 100, 1024): 71.04e6}   # (K, T, D) -> dram__bytes_read.sum + dram__bytes_write.sum of one kproj_iter_kernel
                                              # launch (ncu --set full, profiles/r2_kmeans.md)
 
 
