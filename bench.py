@@ -367,6 +367,8 @@ def concurrency_note(a):
 
 def main():
     a = parse()
+    if os.environ.get("TCLIP_SWITCH_INTERVAL"):   # measurement knob: the interpreter's thread switch interval (default 5 ms)
+        sys.setswitchinterval(float(os.environ["TCLIP_SWITCH_INTERVAL"]))
     if a.impl == "reference":
         run_reference(a)
     elif a.tasks > 0:

@@ -559,9 +559,13 @@ def test_batches_in_flight_equal_serial(dev):
         logs = m.run_task({k: v.clone() for k, v in batches[i].items()})
         return logs["acc"], logs["criterions"], m.alpha.cpu(), m.mm_iters.cpu()
 
+    import sys
     serial = [run(i) for i in range(len(batches))]
+    before = sys.getswitchinterval()
     with BatchPipeline(dev, streams=3) as pipe:
+        assert sys.getswitchinterval() <= 5e-4        # workers hand the interpreter over quickly while the pipeline is open
         piped = pipe.map(run, range(len(batches)))
+    assert sys.getswitchinterval() == before          # and the setting is restored
     for a, b in zip(serial, piped):
         np.testing.assert_array_equal(a[0], b[0])
         np.testing.assert_array_equal(a[1], b[1])

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(128) half_logdet_kernel(const float* __restric
 // `u` may alias `d2`.  labels (optional) = argmax_k of the final u.
 __global__ void __launch_bounds__(128)
 assign_kernel(const float* d2, const float* __restrict__ v, const float* __restrict__ bias, float temperature, float lambd,
-              float* u, int* __restrict__ labels, int rows, int n, int K, int mode) {
+              float* u, int* __restrict__ labels, int rows, int n, int K, int mode, double* __restrict__ row_sq) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -363,8 +363,23 @@ assign_kernel(const float* d2, const float* __restrict__ v, const float* __restr
       best_k = ok;
     }
   }
-  if (mode == 2)
-    for (int k = lane; k < K; k += 32) out[k] = (k == best_k) ? 1.0f : 0.0f;
+  if (mode == 2) {
+    if (row_sq) {   // || u_old - u ||^2 of this row while the old row is replaced (hard_kmeans.py:201: the logged criterion)
+      // float32 per row (<= 1000 terms of a row that sums to <= 2; exact when both rows are one-hot), float64 across the
+      // rows and tasks: the float64 units are too slow for a per-element term (measured: 32 -> 102 us per launch)
+      float s = 0.0f;
+      for (int k = lane; k < K; k += 32) {
+        const float nw = (k == best_k) ? 1.0f : 0.0f;
+        const float d = out[k] - nw;
+        s = fmaf(d, d, s);
+        out[k] = nw;
+      }
+      s = warp_sum_f32(s);
+      if (lane == 0) row_sq[row] = (double)s;
+    } else {
+      for (int k = lane; k < K; k += 32) out[k] = (k == best_k) ? 1.0f : 0.0f;
+    }
+  }
   if (lane == 0 && labels) labels[row] = best_k;
 }
 
@@ -387,6 +402,29 @@ udiff_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __
     __syncthreads();
   }
   if (threadIdx.x == 0) task_norm[t] = sqrtf((float)red[0]);
+}
+
+// crit[2 it], crit[2 it + 1] = mean_t sqrt(sum_n row_sq[it, t, n]) (logged twice per iteration upstream,
+// hard_kmeans.py:203,208-209): one CTA per iteration, one warp per task (lane-strided, then a shuffle tree: a fixed order),
+// then the mean over the tasks in task order.  task_norm: [iters, T] scratch.
+__global__ void __launch_bounds__(256)
+row_norm_mean_kernel(const double* __restrict__ row_sq, float* __restrict__ task_norm, float* __restrict__ crit, int T, int n) {
+  const int it = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* rs = row_sq + (long)it * T * n;
+  float* tn = task_norm + (long)it * T;
+  for (int t = warp; t < T; t += 8) {
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += rs[(long)t * n + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) tn[t] = sqrtf((float)s);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int t = 0; t < T; ++t) total += (double)tn[t];
+    crit[2 * it] = crit[2 * it + 1] = (float)(total / (double)T);
+  }
 }
 
 __global__ void mean_kernel(const float* __restrict__ vals, float* __restrict__ out, int T) {
@@ -419,7 +457,7 @@ cudaError_t kmeans_similarity(const float* a, const float* text, float scale, fl
         a, text, nullptr, u, (int)M, K, D, 0, 0, 0);
     note_launch();
   }
-  assign_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(u, nullptr, nullptr, scale, 0.0f, u, nullptr, (int)M, 1, K, 3);
+  assign_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(u, nullptr, nullptr, scale, 0.0f, u, nullptr, (int)M, 1, K, 3, nullptr);
   note_launch();
   return cudaGetLastError();
 }
@@ -466,7 +504,25 @@ cudaError_t kmeans_kl_div(const float* x, const float* w, float* div, int T, int
 cudaError_t kmeans_assign(const float* d2, const float* v, const float* bias, float temperature, float lambd, float* u,
                           int* labels, int T, int n, int K, int mode, cudaStream_t st) {
   const int rows = T * n;
-  assign_kernel<<<(rows + 3) / 4, 128, 0, st>>>(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode);
+  assign_kernel<<<(rows + 3) / 4, 128, 0, st>>>(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode, nullptr);
+  note_launch();
+  return cudaGetLastError();
+}
+
+// hard k-means u_update in place: u <- one-hot(argmin softmax(+d2)); row_sq [T * n] receives || u_old - u ||^2 per query
+cudaError_t kmeans_assign_hard_tracked(const float* d2, float* u, int* labels, double* row_sq, int T, int n, int K,
+                                       cudaStream_t st) {
+  const int rows = T * n;
+  assign_kernel<<<(rows + 3) / 4, 128, 0, st>>>(d2, nullptr, nullptr, 1.0f, 0.0f, u, labels, rows, n, K, 2, row_sq);
+  note_launch();
+  return cudaGetLastError();
+}
+
+// the logged criteria of `iters` iterations from their per-query terms row_sq [iters, T, n]; task_norm [iters, T] scratch
+cudaError_t kmeans_hard_criterions(const double* row_sq, float* task_norm, float* crit, int iters, int T, int n,
+                                   cudaStream_t st) {
+  if (iters <= 0) return cudaSuccess;
+  row_norm_mean_kernel<<<iters, 256, 0, st>>>(row_sq, task_norm, crit, T, n);
   note_launch();
   return cudaGetLastError();
 }

@@ -647,8 +647,9 @@ size_t kmeans_run_workspace_bytes(const KMeansRun& p) {
   const size_t T = p.T, n = p.n, K = p.K, D = p.D;
   size_t b = 0;
   b += align_up(sizeof(float) * T * n * K);              // d2
-  b += align_up(sizeof(float) * T);                      // task norms (criterion)
-  if (p.method == 2) b += align_up(sizeof(float) * T * n * K);   // u_old
+  const size_t its = (size_t)std::max(p.iters, 1);
+  b += align_up(sizeof(float) * T * its);                // task norms (criterion)
+  if (p.method == 2) b += align_up(sizeof(double) * T * n * its);   // per-query terms of the logged criteria
   if (p.method == 1) b += align_up(sizeof(float) * T * K);       // colsum scratch
   if (kmeans_sample_coordinates(p.n, p.D)) {
     const size_t rq = coord_pitch(p.n, p.D);
@@ -687,8 +688,9 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
     return r;
   };
   float* d2 = static_cast<float*>(take(sizeof(float) * (size_t)T * n * K));
-  float* task_norm = static_cast<float*>(take(sizeof(float) * (size_t)T));
-  float* u_old = p.method == 2 ? static_cast<float*>(take(sizeof(float) * (size_t)T * n * K)) : nullptr;
+  const size_t its = (size_t)std::max(p.iters, 1);
+  float* task_norm = static_cast<float*>(take(sizeof(float) * (size_t)T * its));
+  double* row_sq = p.method == 2 ? static_cast<double*>(take(sizeof(double) * (size_t)T * n * its)) : nullptr;
   float* colsum = p.method == 1 ? static_cast<float*>(take(sizeof(float) * (size_t)T * K)) : nullptr;
   const bool coords = kmeans_sample_coordinates(n, D);
   const bool chained = coords && p.method != 2 && kmeans_chained() && p.iters > 0;
@@ -726,8 +728,6 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
   if (p.method != 2) {
     if (coords) KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, 0, 0, nullptr, tri, st));
     else KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, 0, st));
-  } else {
-    KM_TRY(cudaMemcpyAsync(u_old, p.u, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
   }
   if (p.iter_events && p.iter_events[0]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[0], st));
   for (int it = 0; it < p.iters; ++it) {
@@ -744,14 +744,14 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
         KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, mode == 2 ? 0 : 1, st));
         KM_TRY(kmeans_sqdist(p.x, w, d2, T, n, K, D, st));
       }
-      KM_TRY(kmeans_assign(d2, p.v, nullptr, p.temperature, p.lambd, p.u, p.labels, T, n, K, p.method, st));
-      if (p.method == 1) KM_TRY(colsum_v(p.u, colsum, p.v, nullptr, T, n, K, st));   // v_update after u_update (em_gaussian.py:212-218)
-    }
-    if (p.method == 2) {
-      // logged twice per iteration upstream (hard_kmeans.py:203,208-209)
-      KM_TRY(kmeans_udiff(u_old, p.u, task_norm, p.criterions + 2 * it, T, (long)n * K, st));
-      KM_TRY(cudaMemcpyAsync(p.criterions + 2 * it + 1, p.criterions + 2 * it, sizeof(float), cudaMemcpyDeviceToDevice, st));
-      KM_TRY(cudaMemcpyAsync(u_old, p.u, sizeof(float) * (size_t)T * n * K, cudaMemcpyDeviceToDevice, st));
+      if (p.method == 2) {
+        // u_update in place; the per-query terms of || u_old - u || are taken as the old row is replaced (no copy of u is
+        // kept), the criteria of all iterations are reduced after the loop
+        KM_TRY(kmeans_assign_hard_tracked(d2, p.u, p.labels, row_sq + (size_t)it * T * n, T, n, K, st));
+      } else {
+        KM_TRY(kmeans_assign(d2, p.v, nullptr, p.temperature, p.lambd, p.u, p.labels, T, n, K, p.method, st));
+        if (p.method == 1) KM_TRY(colsum_v(p.u, colsum, p.v, nullptr, T, n, K, st));   // v_update after u_update (em_gaussian.py:212-218)
+      }
     }
     if (p.iter_events && p.iter_events[it + 1]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[it + 1], st));
   }
@@ -760,6 +760,7 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
     KM_TRY(kmeans_assign(d2, nullptr, nullptr, 1.0f, 0.0f, p.u, p.labels, T, n, K, 3, st));
     if (p.method == 1) KM_TRY(colsum_v(p.u, colsum, p.v, nullptr, T, n, K, st));
   }
+  if (p.method == 2) KM_TRY(kmeans_hard_criterions(row_sq, task_norm, p.criterions, p.iters, T, n, st));
   // the reference copies u_old after the update: the logged criterion of the soft variants is identically 0
   if (p.method != 2) KM_TRY(cudaMemsetAsync(p.criterions, 0, sizeof(float) * (size_t)std::max(p.iters, 1), st));
   if (coords && p.w) KM_TRY(kmeans_expand_centroids(p.coef, p.x, p.w, T, n, K, D, st));

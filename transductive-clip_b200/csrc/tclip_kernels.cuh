@@ -165,6 +165,10 @@ cudaError_t kmeans_kl_div(const float* x, const float* w, float* div, int T, int
 cudaError_t kmeans_sqdist(const float* x, const float* w, float* d2, int T, int n, int K, int D, cudaStream_t st);
 cudaError_t kmeans_assign(const float* d2, const float* v, const float* bias, float temperature, float lambd, float* u,
                           int* labels, int T, int n, int K, int mode, cudaStream_t st);
+cudaError_t kmeans_assign_hard_tracked(const float* d2, float* u, int* labels, double* row_sq, int T, int n, int K,
+                                       cudaStream_t st);
+cudaError_t kmeans_hard_criterions(const double* row_sq, float* task_norm, float* crit, int iters, int T, int n,
+                                   cudaStream_t st);
 cudaError_t kmeans_udiff(const float* a, const float* b, float* task_norm, float* mean_out, int T, long per_task,
                          cudaStream_t st);
 

@@ -14,6 +14,7 @@ CUDA synchronisation calls release the GIL), with its own scratch buffers; resul
 """
 from __future__ import annotations
 
+import sys
 import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Iterable, List
@@ -30,6 +31,13 @@ def batches_in_flight() -> int:
     return getattr(_IN_FLIGHT, "streams", 1)
 
 
+# While a pipeline with several workers is open the interpreter's thread switch interval is lowered from its default 5 ms:
+# a worker that comes back from a CUDA call must get the interpreter quickly to enqueue its batch's next kernels, and with
+# batches of ~3 ms (k-means family at RN50 shape) a 5 ms hand-over leaves the GPU idle (measured: 29.8k -> 32.7k tasks/s for
+# soft k-means; no effect on the 22 ms EM-Dirichlet batches).  Restored by close().
+_SWITCH_INTERVAL = 5e-4
+
+
 class BatchPipeline:
     def __init__(self, device, streams: int = 3):
         self.device = torch.device(device)
@@ -42,6 +50,10 @@ class BatchPipeline:
         self._stream_ids = set()
         self._lock = threading.Lock()
         self._pool = ThreadPoolExecutor(max_workers=self.streams, thread_name_prefix="tclip-batch")
+        self._saved_switch_interval = None
+        if self.streams > 1 and sys.getswitchinterval() > _SWITCH_INTERVAL:
+            self._saved_switch_interval = sys.getswitchinterval()
+            sys.setswitchinterval(_SWITCH_INTERVAL)
 
     def _run(self, fn: Callable, item):
         if getattr(self._local, "stream", None) is None:
@@ -67,6 +79,9 @@ class BatchPipeline:
 
     def close(self):
         self._pool.shutdown(wait=True)
+        if self._saved_switch_interval is not None:
+            sys.setswitchinterval(self._saved_switch_interval)
+            self._saved_switch_interval = None
         from . import ops
         ops.release_workspaces(self._stream_ids)   # the per-stream scratch (1-2 GB each at ImageNet shape)
         self._stream_ids = set()
