@@ -149,7 +149,8 @@ def test_sample_coordinates_equal_feature_space(dev):
     gpu_km_coords_err.py: sample coordinates 7e-5, feature space 1.5e-4 on the worst case, EM-Gaussian K = 60), the two
     float32 paths within 4e-4 of each other."""
     from tclip_b200 import ops, tasks
-    for (K, D, n, seed) in ((60, 256, 75, 5), (40, 90, 33, 6), (30, 24, 75, 7), (30, 40, 120, 8), (20, 200, 96, 9)):   # n = 120: fallback
+    for (K, D, n, seed) in ((60, 256, 75, 5), (40, 90, 33, 6), (30, 24, 75, 7), (30, 40, 120, 8), (20, 200, 96, 9),   # n = 120: fallback
+                            (10, 64, 7, 10), (260, 128, 40, 12), (131, 300, 17, 13)):   # one sample block; 3 class tiles; ragged K
         td, _ = tasks.make_zero_shot_batch(3, K, n_query=n, seed=seed, softmax_feature=False, embed_dim=D)
         x = td["x_q"].to(dev)
         x[1, 5] = x[1, 2]                      # duplicated sample: rank-deficient Gram matrix
