@@ -242,7 +242,10 @@ mm_chunk_kernel(const ChunkArgs g) {
         PsiAnchor an = anchors[warp];        // broadcast read: the 32 lanes hold the same row total, hence the same anchor
         const double anchored_at = an.s;
         rp = row_psi_anchored(s, an);
-        if (an.s != anchored_at && lane == 0) anchors[warp] = an;  // re-anchored (rare): one lane publishes it
+        if (an.s != anchored_at) {           // re-anchored (rare, warp-uniform): one lane publishes it, once every lane has read
+          __syncwarp();
+          if (lane == 0) anchors[warp] = an;
+        }
         __syncwarp();
       }
       const bool any_small = __any_sync(0xffffffffu, amin < kSmallA);
