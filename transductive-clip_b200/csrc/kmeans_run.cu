@@ -724,14 +724,18 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
     w = static_cast<float*>(take(sizeof(float) * (size_t)T * K * D));
   }
   if (p.method == 1) KM_TRY(cudaMemsetAsync(p.v, 0, sizeof(float) * (size_t)T * K, st));
-  // w_init (soft k-means, EM-Gaussian); hard k-means has none (hard_kmeans.py:186)
-  if (p.method != 2) {
+  // w_init (soft k-means, EM-Gaussian); hard k-means has none (hard_kmeans.py:186).  In sample coordinates it is folded into
+  // the first iteration: w_init and the first w_update form the centroids of the SAME u, and where the masked update keeps
+  // the old centroid (cluster size <= eps) the old one is w_init's unmasked value — so the first iteration simply runs
+  // unmasked (mode 0) and leaves bit for bit what the two launches would.
+  const bool fold_init = coords && p.method != 2 && p.iters > 0;
+  if (p.method != 2 && !fold_init) {
     if (coords) KM_TRY(iterate(Z, zs, p.u, p.coef, wt, d2, T, n, K, r, 0, 0, nullptr, tri, st));
     else KM_TRY(kmeans_centroids(p.u, p.x, w, T, n, K, D, 0, st));
   }
   if (p.iter_events && p.iter_events[0]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[0], st));
   for (int it = 0; it < p.iters; ++it) {
-    const int mode = p.method == 2 ? 2 : 1;
+    const int mode = p.method == 2 ? 2 : ((fold_init && it == 0) ? 0 : 1);
     if (chained) {
       // M-step of the u the previous launch's logits describe, distances, logits and their row statistics: one launch
       const ChainArgs ch{it == 0 ? nullptr : stats[(it + 1) & 1], stats[it & 1], d2, p.method == 1 ? p.v : nullptr,
