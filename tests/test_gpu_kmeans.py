@@ -240,3 +240,45 @@ def test_unchained_loop_matches(dev):
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+_ASSIGN_CHILD = r"""
+import hashlib, sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+from tclip_b200 import ops, tasks
+dev = torch.device("cuda:0")
+h = hashlib.sha256()
+for (K, D, n) in ((37, 64, 75), (130, 96, 40), (600, 64, 33), (1000, 128, 75)):
+    td, _ = tasks.make_zero_shot_batch(3, K, n_query=n, seed=K, softmax_feature=False, embed_dim=D)
+    x = td["x_q"].to(dev)
+    g = torch.Generator().manual_seed(K)
+    w = torch.randn(3, K, D, generator=g).to(dev) * 0.1
+    v = torch.randn(3, K, generator=g).to(dev)
+    for method in (ops.KMEANS_SOFT, ops.KMEANS_GAUSS, ops.KMEANS_HARD):
+        u, labels = ops.kmeans_assign(x, w, method, 30.0, v=v, lambd=float(3 * n))
+        h.update(u.cpu().numpy().tobytes()); h.update(labels.cpu().numpy().tobytes())
+    res = ops.kmeans_run(x, torch.softmax(torch.randn(3, n, K, generator=g), -1).to(dev), ops.KMEANS_HARD, 3, 30.0)
+    h.update(res["u"].cpu().numpy().tobytes()); h.update(res["criterions"].cpu().numpy().tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_register_resident_assignment_is_bit_identical(dev):
+    """assign_reg_kernel (K <= 1024: the logits of a row stay in registers, d2 read once) and the any-K assign_kernel
+    (TCLIP_ASSIGN=generic) take every sum and arg-extremum in the same order: identical bits for u, labels and the logged
+    criterion of hard k-means, at K below / across / above one warp stripe and at K = 1000."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for knob in ("", "generic"):
+        env = dict(os.environ)
+        env.pop("TCLIP_ASSIGN", None)
+        if knob:
+            env["TCLIP_ASSIGN"] = knob
+        r = subprocess.run([sys.executable, "-c", _ASSIGN_CHILD, root, os.path.join(root, "transductive-clip_b200")], env=env,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        digests.append([ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1], digests

@@ -23,6 +23,8 @@
 #include <math_constants.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <string>
 
 #include "tclip_kernels.cuh"
 
@@ -289,6 +291,17 @@ __global__ void __launch_bounds__(128) half_logdet_kernel(const float* __restric
 //   mode 4 (EM-Gaussian, diagonal covariance)  u = softmax(-1/2 d2s + det + lambd * v / n)   (em_gaussian_cov.py:117-130)
 //   mode 5 (KL k-means)    u = one-hot(argmin_k div), NaN counts as the minimum like torch.argmin (kl_kmeans.py:174-177)
 // `u` may alias `d2`.  labels (optional) = argmax_k of the final u.
+// The logit of one (query, class) pair, every operation rounded on its own like the reference's tensor expressions (no fused
+// multiply-add across them: the two assignment kernels must agree bit for bit, and contraction is the compiler's choice)
+__device__ __forceinline__ float assign_logit(int mode, float d, float temperature, float lambd, float vk, float bk, float fn) {
+  if (mode == 2) return d;
+  if (mode == 3) return __fmul_rn(temperature, d);
+  if (mode == 4) return __fadd_rn(__fadd_rn(__fmul_rn(-0.5f, d), bk), __fdiv_rn(__fmul_rn(lambd, vk), fn));
+  float l = __fmul_rn(temperature, __fmul_rn(-0.5f, d));
+  if (mode == 1) l = __fadd_rn(l, __fdiv_rn(__fmul_rn(lambd, vk), fn));
+  return l;
+}
+
 __global__ void __launch_bounds__(128)
 assign_kernel(const float* d2, const float* __restrict__ v, const float* __restrict__ bias, float temperature, float lambd,
               float* u, int* __restrict__ labels, int rows, int n, int K, int mode, double* __restrict__ row_sq) {
@@ -327,25 +340,19 @@ assign_kernel(const float* d2, const float* __restrict__ v, const float* __restr
   }
   const float fn = (float)n;
   auto logit = [&](int k) -> float {
-    const float d = x[k];
-    if (mode == 2) return d;
-    if (mode == 3) return temperature * d;
-    if (mode == 4) return (-0.5f * d + bb[k]) + (lambd * vv[k]) / fn;
-    float l = temperature * (-0.5f * d);
-    if (mode == 1) l += (lambd * vv[k]) / fn;
-    return l;
+    return assign_logit(mode, x[k], temperature, lambd, vv ? vv[k] : 0.0f, bb ? bb[k] : 0.0f, fn);
   };
   float mx = -CUDART_INF_F;
   for (int k = lane; k < K; k += 32) mx = fmaxf(mx, logit(k));
   mx = warp_max_f32(mx);
   float sum = 0.0f;
-  for (int k = lane; k < K; k += 32) sum += expf(logit(k) - mx);
+  for (int k = lane; k < K; k += 32) sum += expf(__fsub_rn(logit(k), mx));
   sum = warp_sum_f32(sum);
   // arg-extremum of the soft-maxed values: max for the soft variants (label output), min for hard k-means
   float best = mode == 2 ? CUDART_INF_F : -1.0f;
   int best_k = 0x7fffffff;
   for (int k = lane; k < K; k += 32) {
-    const float p = expf(logit(k) - mx) / sum;
+    const float p = __fdiv_rn(expf(__fsub_rn(logit(k), mx)), sum);
     const bool better = mode == 2 ? p < best : p > best;  // strict: the lowest k of this lane's stripe wins ties
     if (better) {
       best = p;
@@ -381,6 +388,108 @@ assign_kernel(const float* d2, const float* __restrict__ v, const float* __restr
     }
   }
   if (lane == 0 && labels) labels[row] = best_k;
+}
+
+// The same rows with the NV = ceil(K / 32) logits of a lane kept in registers (K <= 1024; modes 0-4): d2 is read once instead
+// of three times.  Every sum, maximum and arg-extremum is taken in the order of assign_kernel (a lane's classes ascending,
+// then the shuffle tree), so the two kernels agree bit for bit.
+template <int NV>
+__global__ void __launch_bounds__(128)
+assign_reg_kernel(const float* d2, const float* __restrict__ v, const float* __restrict__ bias, float temperature, float lambd,
+                  float* u, int* __restrict__ labels, int rows, int n, int K, int mode, double* __restrict__ row_sq) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int t = row / n;
+  const float* x = d2 + (long)row * K;
+  const float* vv = v ? v + (long)t * K : nullptr;
+  const float* bb = bias ? bias + (long)t * K : nullptr;
+  float* out = u + (long)row * K;
+  const float fn = (float)n;
+  float l[NV];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int k = lane + 32 * j;
+    float lg = -CUDART_INF_F;
+    if (k < K) {
+      lg = assign_logit(mode, x[k], temperature, lambd, vv ? vv[k] : 0.0f, bb ? bb[k] : 0.0f, fn);
+      mx = fmaxf(mx, lg);
+    }
+    l[j] = lg;
+  }
+  mx = warp_max_f32(mx);
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (lane + 32 * j < K) {
+      l[j] = expf(__fsub_rn(l[j], mx));
+      sum += l[j];
+    }
+  }
+  sum = warp_sum_f32(sum);
+  float best = mode == 2 ? CUDART_INF_F : -1.0f;
+  int best_k = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int k = lane + 32 * j;
+    if (k < K) {
+      const float p = __fdiv_rn(l[j], sum);
+      const bool better = mode == 2 ? p < best : p > best;  // strict: the lowest k of this lane's stripe wins ties
+      if (better) {
+        best = p;
+        best_k = k;
+      }
+      if (mode != 2) out[k] = p;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    const bool better = mode == 2 ? ob < best : ob > best;
+    if (better || (ob == best && ok < best_k)) {
+      best = ob;
+      best_k = ok;
+    }
+  }
+  if (mode == 2) {
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int k = lane + 32 * j;
+      if (k < K) {
+        const float nw = (k == best_k) ? 1.0f : 0.0f;
+        if (row_sq) {
+          const float d = out[k] - nw;
+          s = fmaf(d, d, s);
+        }
+        out[k] = nw;
+      }
+    }
+    if (row_sq) {
+      s = warp_sum_f32(s);
+      if (lane == 0) row_sq[row] = (double)s;
+    }
+  }
+  if (lane == 0 && labels) labels[row] = best_k;
+}
+
+void launch_assign(const float* d2, const float* v, const float* bias, float temperature, float lambd, float* u, int* labels,
+                   int rows, int n, int K, int mode, double* row_sq, cudaStream_t st) {
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+  static const bool generic = [] {   // TCLIP_ASSIGN=generic: the any-K kernel for every shape (cross-check of the two forms)
+    const char* e = std::getenv("TCLIP_ASSIGN");
+    return e && std::string(e) == "generic";
+  }();
+  if (generic || mode == 5 || K > 1024)
+    assign_kernel<<<grid, 128, 0, st>>>(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode, row_sq);
+  else if (K <= 128)
+    assign_reg_kernel<4><<<grid, 128, 0, st>>>(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode, row_sq);
+  else if (K <= 512)
+    assign_reg_kernel<16><<<grid, 128, 0, st>>>(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode, row_sq);
+  else
+    assign_reg_kernel<32><<<grid, 128, 0, st>>>(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode, row_sq);
 }
 
 // task_norm[t] = ||a[t] - b[t]||_F (one CTA per task, fixed reduction tree), then the mean over tasks in task order
@@ -457,7 +566,7 @@ cudaError_t kmeans_similarity(const float* a, const float* text, float scale, fl
         a, text, nullptr, u, (int)M, K, D, 0, 0, 0);
     note_launch();
   }
-  assign_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(u, nullptr, nullptr, scale, 0.0f, u, nullptr, (int)M, 1, K, 3, nullptr);
+  launch_assign(u, nullptr, nullptr, scale, 0.0f, u, nullptr, (int)M, 1, K, 3, nullptr, st);
   note_launch();
   return cudaGetLastError();
 }
@@ -504,7 +613,7 @@ cudaError_t kmeans_kl_div(const float* x, const float* w, float* div, int T, int
 cudaError_t kmeans_assign(const float* d2, const float* v, const float* bias, float temperature, float lambd, float* u,
                           int* labels, int T, int n, int K, int mode, cudaStream_t st) {
   const int rows = T * n;
-  assign_kernel<<<(rows + 3) / 4, 128, 0, st>>>(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode, nullptr);
+  launch_assign(d2, v, bias, temperature, lambd, u, labels, rows, n, K, mode, nullptr, st);
   note_launch();
   return cudaGetLastError();
 }
@@ -513,7 +622,7 @@ cudaError_t kmeans_assign(const float* d2, const float* v, const float* bias, fl
 cudaError_t kmeans_assign_hard_tracked(const float* d2, float* u, int* labels, double* row_sq, int T, int n, int K,
                                        cudaStream_t st) {
   const int rows = T * n;
-  assign_kernel<<<(rows + 3) / 4, 128, 0, st>>>(d2, nullptr, nullptr, 1.0f, 0.0f, u, labels, rows, n, K, 2, row_sq);
+  launch_assign(d2, nullptr, nullptr, 1.0f, 0.0f, u, labels, rows, n, K, 2, row_sq, st);
   note_launch();
   return cudaGetLastError();
 }

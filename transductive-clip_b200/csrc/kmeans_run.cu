@@ -183,7 +183,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // Thread tile: 4 class PAIRS x MJ coordinates (centroids), 4 class pairs x MN samples (distances); all multiply-adds are
 // packed FFMA2 / FADD2 over the class pair (sm_100 issues two fp32 lanes per instruction).  MJ = ceil(r / 16),
 // MN = ceil(n / 16); rq = 16 MJ.
-// KT classes per CTA (128: 4 class pairs per thread, 107 KB of shared memory = 2 CTAs per SM at RN50 shape; 64: 2 pairs, 69 KB =
+// KT classes per CTA (128: 4 class pairs per thread, 111 KB of shared memory = 2 CTAs per SM at RN50 shape; 64: 2 pairs, 72 KB =
 // 3 CTAs per SM).  kUS: row pitch of the u tile (keeps float4 / float2 alignment, spreads the staging stores over the banks);
 // kWS: row pitch of the transposed centroid tile (64-bit stores of 16 consecutive rows hit 16 bank pairs).
 // The chained form (soft k-means, EM-Gaussian): the launch of iteration i leaves the LOGITS of its distances,
@@ -227,11 +227,13 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   float* row_m = cs + KT;            // [NQ] chained form: maximum over all classes of the incoming logits, then of this tile's
   float* row_s = row_m + NQ;         // [NQ] and the matching sum of exponentials
   float* vt = row_s + NQ;            // [KT] EM-Gaussian: lambda v / n of this tile's classes
-  // Both tiles come in by asynchronous copies (LDGSTS: every request of the CTA is in flight at once, nothing is staged in
-  // registers); the padding is zeroed by plain stores to the other addresses.  With staged loads this phase was a chain of
-  // ~10 dependent DRAM round trips and 32 % of the kernel's warp time (profiles/r2_kmeans.md).
-  // Samples.  The Cholesky buffer has whole zero-padded rows of RQ floats: 128-bit loads, all issued before anything waits
-  // (the odd row pitch of the tile, which keeps the distance loop free of bank conflicts, rules out 16-byte async copies)
+  // Every global request of the CTA is in flight before anything waits: the u / logits tile comes in by asynchronous copies
+  // (LDGSTS, nothing staged in registers), the padding is zeroed by plain stores to the other addresses.  With a loop of
+  // load -> store pairs this phase was a chain of ~10 dependent DRAM round trips and 32 % of the kernel's warp time
+  // (profiles/r2_kmeans.md).
+  // Samples: the Cholesky buffer has whole zero-padded rows of RQ floats — 128-bit loads into registers, issued first and
+  // stored after the tile's copies are on their way (the odd row pitch of the shared tile, which keeps the distance loop
+  // free of bank conflicts, rules out 16-byte async copies); any other Z: 4-byte async copies.
   constexpr int ZV = RQ / 4, ZPER = (NQ * ZV + NT - 1) / NT;
   const bool z_rows = zs == RQ && (reinterpret_cast<uintptr_t>(zb) & 15) == 0;
   float4 zr[ZPER];
