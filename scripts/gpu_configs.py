@@ -31,10 +31,23 @@ def timed(name, make, run, n_tasks, reps=3):
 
 def pin(td): return {k: v.pin_memory() for k, v in td.items()}
 
+def timed_in_flight(name, batches, run, n_tasks, streams):
+    """The same run_task calls with `streams` batches in flight (tclip_b200.pipeline), 2 rounds after 1 warm-up round."""
+    from tclip_b200.pipeline import BatchPipeline
+    with BatchPipeline(dev, streams=streams) as pipe:
+        pipe.map(run, [batches[i % len(batches)] for i in range(streams)])
+        torch.cuda.synchronize(); t0 = time.time()
+        n = 2 * streams
+        pipe.map(run, [batches[i % len(batches)] for i in range(n)])
+        torch.cuda.synchronize(); dt = (time.time() - t0) / n
+    print(f"{name:78s} {n_tasks / dt:9.1f} tasks/s  ({dt * 1e3:8.1f} ms per batch of {n_tasks}, {streams} batches in flight)", flush=True)
+
 # config 1: EM-Dirichlet zero-shot, Caltech101 shape
 a = make_args(100, iters=20)
 timed("cfg1 EM-Dirichlet zero-shot K=D=100, batch 100", lambda i: pin(tasks.make_zero_shot_batch(100, 100, seed=2020, batch_index=i)[0]),
       lambda td: D.EM_DIRICHLET(model=None, device=dev, log_file=None, args=a).run_task(dict(td)), 100)
+timed_in_flight("cfg1 in flight", [pin(tasks.make_zero_shot_batch(100, 100, seed=2020, batch_index=i)[0]) for i in range(4)],
+                lambda td: D.EM_DIRICHLET(model=None, device=dev, log_file=None, args=a).run_task(dict(td)), 100, 8)
 # config 2: Hard EM-Dirichlet zero-shot, ImageNet shape, iter 10
 a2 = make_args(1000, iters=10)
 timed("cfg2 Hard EM-Dirichlet zero-shot K=D=1000, batch 75, iter 10", lambda i: pin(tasks.make_zero_shot_batch(75, 1000, seed=2020, batch_index=i)[0]),
@@ -65,6 +78,7 @@ ops.probe_issue_rate("ffma", n_sm * 8, 4000); flop, ms = ops.probe_issue_rate("f
 td = mk_few(1); torch.cuda.synchronize(); t0 = time.time(); run_few(td); torch.cuda.synchronize(); dt = time.time() - t0
 print(f"     cfg3 at T=75: {run_few.updates:.3e} element-updates per batch in {dt * 1e3:.1f} ms = "
       f"{run_few.updates * 74 / dt / 1e12 / (flop / (ms * 1e-3) / 1e12):.2f} of the FP32 peak (whole run_task incl. 1.2 GB H2D)", flush=True)
+timed_in_flight("cfg3 in flight", [_fs[i] for i in sorted(_fs)], run_few, 75, 3)
 # config 4: soft k-means / EM-Gaussian on visual features D=1024, K=1000, batch 100
 for cls, nm in ((KM.SOFT_KMEANS, "soft k-means"), (KM.EM_GAUSSIAN, "EM-Gaussian"), (KM.HARD_KMEANS, "hard k-means (iter 10)")):
     a4 = make_args(1000, iters=10 if "hard" in nm else 20, use_softmax_feature=False)
