@@ -632,6 +632,7 @@ def bench_kmeans(a):
     per_rank = h.gather_list([ms_e2e_rank / a.steps, h.h2d_ms(host[a.warmup]["x_q"])])
     acc_mean = h.gather_mean(sum(accs) / len(accs))
 
+    fp32_peak, _ = h.peaks()
     if rank == 0:
         tasks_total = T * a.steps * world
         step_ms, step_serial_ms = ms_resident / a.steps, ms_resident_serial / a.steps
@@ -670,12 +671,33 @@ def bench_kmeans(a):
                 "traffic": KM_TRAFFIC.get((K, T, D)), "traffic_unit": "bytes per kproj_iter_kernel launch (one iteration of all tasks)",
                 "note": "the loop runs in the coordinates of the task's own samples (csrc/kmeans_run.cu), so a fraction above 1 of the "
                         "w-space HBM bound is possible: it measures the reformulation, not DRAM efficiency",
+                # what the loop is really bound by: the FP32 rate of the iteration kernel in sample coordinates
+                "loop_fp32": km_loop_fp32(N_QUERY, K, D, T, iters, loop_ms, fp32_peak),
             },
         }
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_sample(a, iters)
         print(json.dumps(out))
     h.close()
+
+
+def km_loop_fp32(n, K, D, T, iters, loop_ms, fp32_peak):
+    """FP32 work of the k-means loop in sample coordinates (csrc/kmeans_run.cu), per iteration of one task, r = min(n, D)
+    coordinates: centroids 2 K r n flop (multiply-add), distances 3 n K r flop (subtract, multiply-add).  The triangular
+    form (D > n: Cholesky coordinates) runs the 16 x 16 blocks on and below the diagonal of the r x n index square only."""
+    r = min(n, D)
+    dense = 5.0 * K * r * n
+    executed = dense
+    if D > n:
+        nb = -(-n // 16)
+        blocks_c = sum(min(16, n - 16 * b) * 16 * (b + 1) for b in range(nb))          # sample block b x coordinate blocks <= b
+        blocks_d = sum(min(16, r - 16 * b) * 16 * (nb - b) for b in range(nb))         # coordinate block b x sample groups >= b
+        executed = 2.0 * K * blocks_c + 3.0 * K * blocks_d + 2.0 * K * r               # + the running sum of w^2
+    tf = executed * T * iters / (loop_ms * 1e-3) / 1e12
+    return {"bound": "fp32", "flop_per_task_iteration": executed, "dense_flop_per_task_iteration": dense,
+            "achieved": tf, "dense_equivalent": dense * T * iters / (loop_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": tf / fp32_peak, "scope": "the loop of a strictly serial batch (loop_ms_serial), padding to 16-blocks counted as work",
+            "peak_source": "FFMA issue-rate probe of this run (no FP32 line in MEASURED_PEAKS.json)"}
 
 
 KM_TRAFFIC = {(1000, 100, 1024): 71.04e6}   # (K, T, D) -> dram__bytes_read.sum + dram__bytes_write.sum of one kproj_iter_kernel
