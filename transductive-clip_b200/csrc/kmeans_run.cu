@@ -347,25 +347,25 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
 #pragma unroll
     for (int q = 0; q < PQ; ++q) {
       const int kk = ty * CPT + 2 * q;
+      // One reciprocal per class, a multiply per coordinate (these are sample coordinates: there is no reference value a
+      // true division would reproduce bit for bit; the unrolled divisions and their branches were 26 % of the kernel's time).
       const float c0 = cs[kk], c1 = cs[kk + 1];
-      const bool f0 = (mode == 0) || (c0 > kEps), f1 = (mode == 0) || (c1 > kEps);
+      const bool in0 = k0 + kk < K, in1 = k0 + kk + 1 < K;
+      const bool f0 = in0 && ((mode == 0) || (c0 > kEps)), f1 = in1 && ((mode == 0) || (c1 > kEps));
+      const bool keep0 = in0 && !f0 && mode == 1, keep1 = in1 && !f1 && mode == 1;   // empty cluster keeps its centroid
+      const bool store0 = f0 || (in0 && mode == 2), store1 = f1 || (in1 && mode == 2);   // (mode 2: zeroed)
+      const float2 inv = make_float2(f0 ? 1.0f / fmaxf(c0, kEps) : 0.0f, f1 ? 1.0f / fmaxf(c1, kEps) : 0.0f);
       float* w0 = wt + ((long)t * K + k0 + kk) * RQ;
       float* w1 = w0 + RQ;
 #pragma unroll
       for (int m = 0; m < MJ; ++m) {
         const int j = tx + 16 * m;
-        float v0 = 0.0f, v1 = 0.0f;
-        if (k0 + kk < K) {
-          if (f0) v0 = acc[q][m].x / fmaxf(c0, kEps);
-          else if (mode == 1) v0 = w0[j];       // empty cluster keeps its centroid
-          if (f0 || mode == 2) w0[j] = v0;      // (mode 2: zeroed)
-        }
-        if (k0 + kk + 1 < K) {
-          if (f1) v1 = acc[q][m].y / fmaxf(c1, kEps);
-          else if (mode == 1) v1 = w1[j];
-          if (f1 || mode == 2) w1[j] = v1;
-        }
-        *reinterpret_cast<float2*>(nwT + j * kWS + kk) = make_float2(-v0, -v1);
+        float2 v = __fmul2_rn(acc[q][m], inv);
+        if (keep0) v.x = w0[j];
+        if (keep1) v.y = w1[j];
+        if (store0) w0[j] = v.x;
+        if (store1) w1[j] = v.y;
+        *reinterpret_cast<float2*>(nwT + j * kWS + kk) = make_float2(-v.x, -v.y);
       }
     }
   }
