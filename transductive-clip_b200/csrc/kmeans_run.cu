@@ -467,20 +467,15 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       float sum = 0.0f;
+      float* lrow = ch.lg + ((long)t * n + row) * K + k0;   // the warp writes its query's 128 logits: 4 coalesced stores
 #pragma unroll
       for (int j = 0; j < LPT; ++j) {
         sum += expf(l[j] - mx);   // exp(-inf) = 0 for the padding classes (every tile holds at least one class)
-        us[row * kUS + lane + 32 * j] = l[j];
+        if (k0 + lane + 32 * j < K) lrow[lane + 32 * j] = l[j];
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       if (lane == 0) ch.stats_out[((long)t * n + row) * gridDim.x + blockIdx.x] = make_float2(mx, sum);
-    }
-    __syncthreads();
-    float* lb = ch.lg + (long)t * n * K;
-    for (int i = tid; i < n * KT; i += NT) {
-      const int row = i / KT, kk = i - row * KT;
-      if (k0 + kk < K) lb[(long)row * K + k0 + kk] = us[row * kUS + kk];
     }
   }
 }
