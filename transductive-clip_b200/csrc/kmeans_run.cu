@@ -326,6 +326,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
 #pragma unroll
     for (int nb = 0; nb < (TRI ? MN : 1); ++nb) {   // TRI: sample block nb reaches the coordinate blocks m <= nb only
       const int n_lo = TRI ? 16 * nb : 0, n_hi = TRI ? min(n, 16 * nb + 16) : n;
+#pragma unroll 4
       for (int nn = n_lo; nn < n_hi; ++nn) {
         float2 uv[PQ];
 #pragma unroll
@@ -390,6 +391,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
 #pragma unroll
     for (int m = 0; m < MN; ++m) acc[q][m] = make_float2(0.0f, 0.0f);
   if constexpr (!TRI) {
+#pragma unroll 4
     for (int j = 0; j < r; ++j) {
       float2 nw[PQ];
 #pragma unroll
@@ -416,6 +418,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
 #pragma unroll
       for (int q = 0; q < PQ; ++q) acc[q][jb] = sq[q];
       const int j_hi = min(r, 16 * jb + 16);
+#pragma unroll 4
       for (int j = 16 * jb; j < j_hi; ++j) {
         float2 nw[PQ];
 #pragma unroll
