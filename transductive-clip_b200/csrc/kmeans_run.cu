@@ -186,17 +186,18 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // KT classes per CTA (128: 4 class pairs per thread, 111 KB of shared memory = 2 CTAs per SM at RN50 shape; 64: 2 pairs, 72 KB =
 // 3 CTAs per SM).  kUS: row pitch of the u tile (keeps float4 / float2 alignment, spreads the staging stores over the banks);
 // kWS: row pitch of the transposed centroid tile (64-bit stores of 16 consecutive rows hit 16 bank pairs).
-// The chained form (soft k-means, EM-Gaussian): the launch of iteration i leaves the LOGITS of its distances,
+// The chained form (soft k-means, EM-Gaussian): from the logits of its distances,
 //   l = T (-d2 / 2) [+ lambda v / n]                      (soft_kmeans.py:105-125, em_gaussian.py:106-128)
-// and, per query and class tile, the tile's maximum m and sum of exp(l - m); the launch of iteration i + 1 turns them into
-// its u tile itself, u = exp(l - M) / S with M = max_tiles m and S = sum_tiles s exp(m - M) — the launch boundary is the
-// grid-wide barrier the soft-max over all K classes needs.  u, v and the labels are materialised once, after the last
+// the launch of iteration i leaves, per query and class tile, the tile's maximum m, the exponentials e = exp(l - m) and their
+// sum s; the launch of iteration i + 1 turns them into its u tile itself, u = e exp(m - M) / S with M = max_tiles m and
+// S = sum_tiles s exp(m - M) (one scale factor per query and tile: every exponential is computed once) — the launch boundary
+// is the grid-wide barrier the soft-max over all K classes needs.  u, v and the labels are materialised once, after the last
 // iteration; no assignment / column-sum launch and no u round trip inside the loop.  EM-Gaussian's v_update
 // (em_gaussian.py:130-136) needs the column sums of u only, i.e. the cluster sizes the M-step forms anyway, per class: tile-local.
 struct ChainArgs {
-  const float2* stats_in;   // [T, n, tiles] of the logits in `lg`; nullptr: the input is u (first iteration)
+  const float2* stats_in;   // [T, n, tiles] (m, s) of the exponentials in `lg`; nullptr: the input is u (first iteration)
   float2* stats_out;        // [T, n, tiles] (the other buffer: CTAs of one task read all tiles while others write theirs)
-  float* lg;                // [T, n, K] logits, read (when stats_in) and rewritten in place: a CTA owns its class tile
+  float* lg;                // [T, n, K] exponentials e, read (when stats_in) and rewritten in place: a CTA owns its class tile
   const float* v0;          // [T, K] EM-Gaussian, u input only: the v the first logits use (zeros); nullptr otherwise
   float temperature;
   float lambd;
@@ -224,9 +225,8 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   const float* zb = Z + (long)t * n * zs;
   const bool from_logits = CHAIN && ch.stats_in != nullptr;
   const float* ub = (from_logits ? ch.lg : u) + (long)t * n * K;
-  float* row_m = cs + KT;            // [NQ] chained form: maximum over all classes of the incoming logits, then of this tile's
-  float* row_s = row_m + NQ;         // [NQ] and the matching sum of exponentials
-  float* vt = row_s + NQ;            // [KT] EM-Gaussian: lambda v / n of this tile's classes
+  float* row_m = cs + KT;            // [NQ] chained form: exp(m_tile - M) / S of every query
+  float* vt = row_m + 2 * NQ;        // [KT] EM-Gaussian: lambda v / n of this tile's classes
   // Every global request of the CTA is in flight before anything waits: the u / logits tile comes in by asynchronous copies
   // (LDGSTS, nothing staged in registers), the padding is zeroed by plain stores to the other addresses.  With a loop of
   // load -> store pairs this phase was a chain of ~10 dependent DRAM round trips and 32 % of the kernel's warp time
@@ -285,8 +285,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
       for (int i = 0; i < tiles; ++i) M = fmaxf(M, sp[i].x);
       float S = 0.0f;
       for (int i = 0; i < tiles; ++i) S += sp[i].y * expf(sp[i].x - M);   // tile order: reproducible
-      row_m[tid] = M;
-      row_s[tid] = S;
+      row_m[tid] = expf(sp[blockIdx.x].x - M) / S;   // the factor that turns this tile's exponentials into u
     }
   }
   cp_async_wait_all();
@@ -294,11 +293,11 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
   if constexpr (CHAIN) {
     if (from_logits) {   // u tile = softmax row restricted to this tile (u_update); the padding stays zero
       for (int row = tid >> 5; row < n; row += NT / 32) {   // one warp per query
-        const float M = row_m[row], rS = 1.0f / row_s[row];
+        const float f = row_m[row];
 #pragma unroll
         for (int j = 0; j < KT / 32; ++j) {
           const int c = (tid & 31) + 32 * j;
-          if (k0 + c < K) us[row * kUS + c] = expf(us[row * kUS + c] - M) * rS;
+          us[row * kUS + c] *= f;   // (the padding is zero and stays zero)
         }
       }
       __syncthreads();
@@ -452,7 +451,7 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
       if (k0 + kk < K) db[(long)row * K + k0 + kk] = us[row * kUS + kk];
     }
   } else {
-    // logits of this tile and their per-query statistics (one warp per query)
+    // logits of this tile, their per-query maximum, exponentials and sum (one warp per query)
     constexpr int LPT = KT / 32;
     const int lane = tid & 31, warp = tid >> 5;
     const bool gauss = ch.method == 1;
@@ -470,17 +469,59 @@ kproj_iter_kernel(const float* __restrict__ Z, int zs, const float* __restrict__
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       float sum = 0.0f;
-      float* lrow = ch.lg + ((long)t * n + row) * K + k0;   // the warp writes its query's 128 logits: 4 coalesced stores
+      float* erow = ch.lg + ((long)t * n + row) * K + k0;   // the warp writes its query's 128 exponentials: 4 coalesced stores
 #pragma unroll
       for (int j = 0; j < LPT; ++j) {
-        sum += expf(l[j] - mx);   // exp(-inf) = 0 for the padding classes (every tile holds at least one class)
-        if (k0 + lane + 32 * j < K) lrow[lane + 32 * j] = l[j];
+        const float e = expf(l[j] - mx);   // exp(-inf) = 0 for the padding classes (every tile holds at least one class)
+        sum += e;
+        if (k0 + lane + 32 * j < K) erow[lane + 32 * j] = e;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       if (lane == 0) ch.stats_out[((long)t * n + row) * gridDim.x + blockIdx.x] = make_float2(mx, sum);
     }
   }
+}
+
+// After the last chained iteration: u [T,n,K] = e exp(m_tile - M) / S from the exponentials and tile statistics it left, and
+// labels = arg-max_k u (first maximum).  One warp per query; same M and S (tile order) as the iteration kernel would form.
+__global__ void __launch_bounds__(128)
+finish_chain_kernel(const float* ex, const float2* __restrict__ stats, float* u, int* __restrict__ labels, int rows, int K,
+                    int tiles, int kt) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float2* sp = stats + (long)row * tiles;
+  float M = -CUDART_INF_F;
+  for (int i = 0; i < tiles; ++i) M = fmaxf(M, sp[i].x);
+  float S = 0.0f;
+  for (int i = 0; i < tiles; ++i) S += sp[i].y * expf(sp[i].x - M);
+  const float* e = ex + (long)row * K;
+  float* out = u + (long)row * K;
+  float best = -1.0f;
+  int best_k = 0x7fffffff;
+  for (int i = 0; i < tiles; ++i) {
+    const float f = expf(sp[i].x - M) / S;
+    const int k_hi = min(K, (i + 1) * kt);
+    for (int k = i * kt + lane; k < k_hi; k += 32) {
+      const float p = e[k] * f;
+      if (p > best) {   // strict: the lowest k of this lane's classes wins ties
+        best = p;
+        best_k = k;
+      }
+      out[k] = p;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    if (ob > best || (ob == best && ok < best_k)) {
+      best = ob;
+      best_k = ok;
+    }
+  }
+  if (lane == 0 && labels) labels[row] = best_k;
 }
 
 template <int MJ, int MN, int KT, int NT, bool TRI>
@@ -760,8 +801,10 @@ cudaError_t kmeans_run(const KMeansRun& p, void* workspace, cudaStream_t st) {
     if (p.iter_events && p.iter_events[it + 1]) KM_TRY(cudaEventRecord((cudaEvent_t)p.iter_events[it + 1], st));
   }
   if (chained) {
-    // u, labels [and v] of the last iteration, from its logits (mode 3 with scale 1: the plain soft-max of the given values)
-    KM_TRY(kmeans_assign(d2, nullptr, nullptr, 1.0f, 0.0f, p.u, p.labels, T, n, K, 3, st));
+    // u, labels [and v] of the last iteration, from the exponentials and tile statistics it left
+    const int tiles = (K + km_tile() - 1) / km_tile();
+    finish_chain_kernel<<<(T * n + 3) / 4, 128, 0, st>>>(d2, stats[(p.iters - 1) & 1], p.u, p.labels, T * n, K, tiles, km_tile());
+    note_launch();
     if (p.method == 1) KM_TRY(colsum_v(p.u, colsum, p.v, nullptr, T, n, K, st));
   }
   if (p.method == 2) KM_TRY(kmeans_hard_criterions(row_sq, task_norm, p.criterions, p.iters, T, n, st));
