@@ -20,9 +20,10 @@
 // back to the feature-space kernels of kmeans.cu.
 //
 // One outer iteration of soft k-means / EM-Gaussian = ONE launch of kproj_iter_kernel<CHAIN = true>: u tile rebuilt from the
-// previous launch's logits and per-tile row statistics (u_update), cluster sizes [and v_update], centroids in sample
-// coordinates with the reference's empty-cluster rule, coefficients, squared distances, logits + row statistics for the next
-// launch; u, labels and v are materialised once after the last iteration (assign_kernel, colsum_v).  Hard k-means, whose
+// previous launch's exponentials and per-tile row statistics (u_update), cluster sizes [and v_update], centroids in sample
+// coordinates with the reference's empty-cluster rule, coefficients, squared distances, exponentials of the logits + row
+// statistics for the next launch; u, labels and v are materialised once after the last iteration (finish_chain_kernel,
+// colsum_v).  Hard k-means, whose
 // logged criterion needs every u: kproj_iter_kernel<false> + assign_kernel (arg-min rows, kmeans.cu) + criterion.
 #include <cuda_runtime.h>
 #include <math_constants.h>
