@@ -700,7 +700,7 @@ def km_loop_fp32(n, K, D, T, iters, loop_ms, fp32_peak):
             "peak_source": "FFMA issue-rate probe of this run (no FP32 line in MEASURED_PEAKS.json)"}
 
 
-KM_TRAFFIC = {(1000, 100, 1024): 71.04e6}   # (K, T, D) -> dram__bytes_read.sum + dram__bytes_write.sum of one kproj_iter_kernel
+KM_TRAFFIC = {(1000, 100, 1024): 69.26e6}   # (K, T, D) -> dram__bytes_read.sum + dram__bytes_write.sum of one kproj_iter_kernel
                                              # launch (ncu --set full, profiles/r2_kmeans.md)
 
 
