@@ -178,6 +178,37 @@ def test_sample_coordinates_equal_feature_space(dev):
                 np.testing.assert_allclose(ops.kmeans_expand_centroids(res["coef"], x).cpu().numpy(), res["w"].cpu().numpy(), atol=1e-6)
 
 
+@pytest.mark.parametrize("iters", [0, 1, 2])
+def test_few_iterations_chain_boundaries(dev, iters):
+    """iters = 0 (no loop: u stays the initial assignment, w is w_init), 1 (the chained form's first launch takes u, its
+    only statistics go straight to the final pass) and 2 (one hand-over between launches) against the feature-space stage
+    kernels."""
+    from tclip_b200 import ops, tasks
+    K, D, n = 150, 96, 40
+    td, _ = tasks.make_zero_shot_batch(3, K, n_query=n, seed=21, softmax_feature=False, embed_dim=D)
+    x = td["x_q"].to(dev)
+    g = torch.Generator().manual_seed(3)
+    u0 = torch.softmax(4.0 * torch.randn(3, n, K, generator=g), dim=-1).to(dev)
+    lam = float(int(K / 5) * n)
+    for method in (ops.KMEANS_SOFT, ops.KMEANS_GAUSS, ops.KMEANS_HARD):
+        res = ops.kmeans_run(x, u0.clone(), method, iters, 30.0, lambd=lam, want_w=True)
+        u, v = u0.clone(), torch.zeros(3, K, device=dev)
+        labels = None
+        w = None if method == ops.KMEANS_HARD else ops.kmeans_centroids(u, x, None)
+        for _ in range(iters):
+            w = ops.kmeans_centroids(u, x, w, keep_old=(method != ops.KMEANS_HARD))
+            u, labels = ops.kmeans_assign(x, w, method, 30.0, v=v, lambd=lam)
+            if method == ops.KMEANS_GAUSS:
+                _, v, _ = ops.colsum_v(u, want_v=True, want_live=False)
+        np.testing.assert_allclose(res["u"].cpu().numpy(), u.cpu().numpy(), atol=2e-5)
+        if labels is not None:
+            assert (res["labels"] == labels).float().mean().item() >= 0.999
+        if w is not None:
+            np.testing.assert_allclose(res["w"].cpu().numpy(), w.cpu().numpy(), rtol=1e-3, atol=2e-5)
+        if method == ops.KMEANS_GAUSS and iters > 0:
+            np.testing.assert_allclose(res["v"].cpu().numpy(), v.cpu().numpy(), atol=1e-4)
+
+
 def test_kmeans_rn50_shape_properties(dev):
     """BASELINE config 4 shape (D = 1024 visual features, K = 1000): size-independent properties — rows of u are
     stochastic (hard: one-hot), every centroid of a non-empty cluster is the mean of its members, empty clusters of hard

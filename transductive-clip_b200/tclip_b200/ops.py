@@ -358,11 +358,12 @@ def kmeans_run(x: torch.Tensor, u0: torch.Tensor, method: int, iters: int, tempe
     dev = x.device
     coords = bool(lib.tclip_kmeans_sample_coordinates(n, D))
     n_crit = (2 * iters) if method == KMEANS_HARD else iters
+    crit = torch.zeros(max(n_crit, 1), device=dev, dtype=torch.float32)   # (iters = 0: the library still wants a buffer)
     out = {
         "u": u0,
         "labels": torch.zeros(T, n, device=dev, dtype=torch.int32),
         "v": torch.zeros(T, K, device=dev, dtype=torch.float32) if method == KMEANS_GAUSS else None,
-        "criterions": torch.zeros(max(n_crit, 1), device=dev, dtype=torch.float32)[:n_crit],
+        "criterions": crit[:n_crit],
         "coef": torch.empty(T, n, K, device=dev, dtype=torch.float32) if coords else None,
         "w": torch.empty(T, K, D, device=dev, dtype=torch.float32) if (want_w or not coords) else None,
     }
@@ -375,7 +376,7 @@ def kmeans_run(x: torch.Tensor, u0: torch.Tensor, method: int, iters: int, tempe
     p = _lib.KMeansProblem(
         n_task=T, n_query=n, n_class=K, dim=D, iters=int(iters), method=int(method), temperature=float(temperature),
         lambd=float(lambd), x=_ptr(x), u=_ptr(u0), v=_ptr(out["v"]), labels=_ptr(out["labels"]), coef=_ptr(out["coef"]),
-        w=_ptr(out["w"]), criterions=_ptr(out["criterions"]),
+        w=_ptr(out["w"]), criterions=_ptr(crit),
         iter_events=ctypes.cast(ev_arr, ctypes.POINTER(ctypes.c_void_p)) if ev_arr is not None else None)
     nbytes = lib.tclip_kmeans_workspace_bytes(ctypes.byref(p))
     if nbytes == 0:
