@@ -380,3 +380,25 @@ def test_logger_handlers_are_shared_and_released_without_blocking(tmp_path):
     c.del_logger()
     assert py.handlers == []
     assert open(path).read().count("one line") == 1
+
+
+def test_bench_kmeans_loop_flop_count():
+    """bench.py's FP32 work model of the k-means loop in sample coordinates (roofline.loop_fp32): dense 5 K r n flop per task and
+    iteration; the triangular form counts the 16-blocks on and below the diagonal (+ the running sum of squares); features
+    used as coordinates (D <= n) have no triangular form."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    r = bench.km_loop_fp32(75, 1000, 1024, 100, 20, 2.0, 73.0)
+    assert r["dense_flop_per_task_iteration"] == 5.0 * 1000 * 75 * 75
+    blocks = [(min(16, 75 - 16 * b), b) for b in range(5)]
+    tri_c = sum(sz * 16 * (b + 1) for sz, b in blocks)
+    tri_d = sum(sz * 16 * (5 - b) for sz, b in blocks)
+    assert r["flop_per_task_iteration"] == 2.0 * 1000 * tri_c + 3.0 * 1000 * tri_d + 2.0 * 1000 * 75
+    assert 0.6 < r["flop_per_task_iteration"] / r["dense_flop_per_task_iteration"] < 0.7
+    np.testing.assert_allclose(r["achieved"], r["flop_per_task_iteration"] * 100 * 20 / 2.0e-3 / 1e12)
+    np.testing.assert_allclose(r["frac"], r["achieved"] / 73.0)
+    d = bench.km_loop_fp32(75, 30, 24, 10, 5, 1.0, 73.0)          # D <= n: r = D, dense
+    assert d["flop_per_task_iteration"] == d["dense_flop_per_task_iteration"] == 5.0 * 30 * 24 * 75
