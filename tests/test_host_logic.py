@@ -402,3 +402,34 @@ def test_bench_kmeans_loop_flop_count():
     np.testing.assert_allclose(r["frac"], r["achieved"] / 73.0)
     d = bench.km_loop_fp32(75, 30, 24, 10, 5, 1.0, 73.0)          # D <= n: r = D, dense
     assert d["flop_per_task_iteration"] == d["dense_flop_per_task_iteration"] == 5.0 * 30 * 24 * 75
+
+
+def test_chained_softmax_algebra_float32():
+    """The algebra of the chained k-means launches (csrc/kmeans_run.cu, ChainArgs) restated in numpy float32: per class tile
+    of 128 the maximum m, e = exp(l - m) and s = sum e; then M = max m, S = sum_tiles s exp(m - M) and u = e exp(m - M) / S.
+    Against the float64 soft-max of the same float32 logits the result is within a few ulp of the largest probability — the
+    same bound as the one-pass float32 soft-max — also when a tile lies far below the maximum (its factor underflows to 0)."""
+    rng = np.random.default_rng(0)
+    for K, spread in ((1000, 30.0), (131, 5.0), (600, 200.0)):
+        l = (rng.standard_normal((75, K)) * spread).astype(np.float32)
+        tiles = [(a, min(K, a + 128)) for a in range(0, K, 128)]
+        m = np.stack([l[:, a:b].max(1) for a, b in tiles], 1)
+        e = [np.exp(l[:, a:b] - m[:, [i]], dtype=np.float32) for i, (a, b) in enumerate(tiles)]
+        s = np.stack([x.sum(1, dtype=np.float32) for x in e], 1)
+        M = m.max(1, keepdims=True)
+        S = np.zeros(75, np.float32)
+        for i in range(len(tiles)):                       # tile order, like the kernel
+            S = S + s[:, i] * np.exp(m[:, i] - M[:, 0], dtype=np.float32)
+        u = np.concatenate([e[i] * (np.exp(m[:, [i]] - M, dtype=np.float32) / S[:, None]).astype(np.float32)
+                            for i in range(len(tiles))], 1)
+        l64 = l.astype(np.float64)
+        ref = np.exp(l64 - l64.max(1, keepdims=True))
+        ref /= ref.sum(1, keepdims=True)
+        one_pass = np.exp(l - l.max(1, keepdims=True), dtype=np.float32)
+        one_pass = one_pass / one_pass.sum(1, dtype=np.float32, keepdims=True)
+        err_chain = np.abs(u - ref).max()
+        err_one = np.abs(one_pass - ref).max()
+        assert err_chain <= 8 * np.finfo(np.float32).eps, (K, spread, err_chain)
+        assert err_chain <= max(4 * err_one, 4 * np.finfo(np.float32).eps), (K, spread, err_chain, err_one)
+        assert (u.argmax(1) == ref.argmax(1)).all()
+        np.testing.assert_allclose(u.sum(1), 1.0, atol=1e-5)
