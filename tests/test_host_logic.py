@@ -433,3 +433,40 @@ def test_chained_softmax_algebra_float32():
         assert err_chain <= max(4 * err_one, 4 * np.finfo(np.float32).eps), (K, spread, err_chain, err_one)
         assert (u.argmax(1) == ref.argmax(1)).all()
         np.testing.assert_allclose(u.sum(1), 1.0, atol=1e-5)
+
+
+def test_sample_coordinate_identities_float64():
+    """The two identities the k-means loop of csrc/kmeans_run.cu rests on, in numpy float64:
+    (1) with G = X X^T = L L^T, a centroid w = c^T X (a combination of the task's samples) and wt = c^T L satisfy
+        ||w - x_n||^2 = ||wt - L_n||^2 for every sample n — also when samples are duplicated (singular G, zero pivots);
+    (2) L is lower triangular, so the distance of sample n splits at any block boundary b > n into the direct differences
+        over the coordinates below b and the plain sum of wt_j^2 over the coordinates from b on (the triangular form)."""
+    rng = np.random.default_rng(1)
+    n, D, K = 40, 96, 7
+    X = rng.standard_normal((n, D))
+    X[5] = X[2]                                   # duplicated sample
+    X[9] = 0.5 * (X[0] + X[3])                    # dependent sample
+    G = X @ X.T
+    # Cholesky with zeroed columns at (numerically) zero pivots, as chol_kernel does
+    A = G.copy()
+    diag = np.diag(G).copy()
+    L = np.zeros_like(G)
+    for j in range(n):
+        p = A[j, j]
+        d = np.sqrt(p) if (p > 1e-9 * diag[j] and p > 0) else 0.0
+        if d > 0:
+            L[j:, j] = A[j:, j] / d
+            L[j, j] = d
+            A[j + 1:, j + 1:] -= np.outer(L[j + 1:, j], L[j + 1:, j])
+    np.testing.assert_allclose(L @ L.T, G, atol=1e-8)
+    c = rng.random((n, K))
+    c /= c.sum(0, keepdims=True)
+    W, Wt = c.T @ X, c.T @ L
+    d_feat = ((X[:, None, :] - W[None, :, :]) ** 2).sum(-1)
+    d_coord = ((L[:, None, :] - Wt[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(d_coord, d_feat, rtol=1e-7, atol=1e-7)
+    assert np.allclose(np.triu(L, 1), 0.0)
+    for b in (16, 32):
+        rows = np.arange(n) < b                   # samples of the groups below the boundary have no coordinate >= b
+        split = ((L[rows][:, None, :b] - Wt[None, :, :b]) ** 2).sum(-1) + (Wt[:, b:] ** 2).sum(-1)[None, :]
+        np.testing.assert_allclose(split, d_coord[rows], rtol=1e-12, atol=1e-12)
