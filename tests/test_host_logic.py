@@ -470,3 +470,21 @@ def test_sample_coordinate_identities_float64():
         rows = np.arange(n) < b                   # samples of the groups below the boundary have no coordinate >= b
         split = ((L[rows][:, None, :b] - Wt[None, :, :b]) ** 2).sum(-1) + (Wt[:, b:] ** 2).sum(-1)[None, :]
         np.testing.assert_allclose(split, d_coord[rows], rtol=1e-12, atol=1e-12)
+
+
+def test_diagnostic_switches_are_documented():
+    """Every TCLIP_* environment variable the library or the Python package reads appears in INTEGRATION.md §9."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "transductive-clip_b200")
+    names = set()
+    for path in glob.glob(os.path.join(pkg, "csrc", "*.cu")) + glob.glob(os.path.join(pkg, "csrc", "*.cuh")):
+        names |= set(re.findall(r'getenv\("(TCLIP_[A-Z0-9_]+)"', open(path).read()))
+    for path in glob.glob(os.path.join(pkg, "tclip_b200", "**", "*.py"), recursive=True):
+        names |= set(re.findall(r'environ(?:\.get)?[\[(]\s*"(TCLIP_[A-Z0-9_]+)"', open(path).read()))
+    assert {"TCLIP_KM_CHAIN", "TCLIP_KM_TRI", "TCLIP_SPARSE_SOFTMAX", "TCLIP_MM_MODE", "TCLIP_LIB"} <= names
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
