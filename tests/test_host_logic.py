@@ -488,3 +488,17 @@ def test_diagnostic_switches_are_documented():
     doc = open(os.path.join(root, "INTEGRATION.md")).read()
     missing = sorted(n for n in names if n not in doc)
     assert not missing, missing
+
+
+def test_every_entry_point_is_in_the_integration_table():
+    """Every function include/tclip_b200.h declares is named in INTEGRATION.md §3 (`X_workspace_bytes` may ride on `X`)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "tclip_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(tclip_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 30
+    missing = [n for n in names if n not in doc and not (n.endswith("_workspace_bytes") and
+                                                         (n[:-len("_workspace_bytes")] in doc or n.replace("_workspace_bytes", "_run") in doc))]
+    assert not missing, missing
